@@ -1,0 +1,147 @@
+/* protnote_b200 - C ABI of the B200-native ProtNote scoring path (sm_100a).
+ *
+ * The reference (microsoft/protnote) has no FFI layer: its boundary for this path is the Python nn.Module
+ * contract (protnote/models/ProtNote.py:168-177, protnote/models/protein_encoders.py:109-123).  This header is
+ * what a binding for that contract calls; every entry point cites the reference code whose arithmetic it replaces.
+ * INTEGRATION.md shows the ctypes stub and the reference-side module that uses it.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name says host; the caller owns all memory,
+ *     the library never allocates device memory and never synchronises the device;
+ *   - `stream` is a cudaStream_t passed as void*;
+ *   - every function returns 0 on success, non-zero on error (pn_last_error() describes it); nothing throws;
+ *   - fp32 in, fp32 out.  Internally a value travels as two fp16 planes (hi, lo) and every contraction runs on the
+ *     tcgen05 tensor cores; mode PN_STRICT issues hi*hi + hi*lo + lo*hi (fp32-grade, |logit error| << 1e-4),
+ *     PN_FAST issues hi*hi only (fp16 operands, comparable to the reference under torch.autocast);
+ *   - a handle is not thread-safe: one per process / GPU.
+ */
+#ifndef PROTNOTE_B200_H
+#define PROTNOTE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PN_STRICT 3 /* three tensor-core passes per k-step: fp32-grade result   */
+#define PN_FAST 1   /* one pass: fp16 operands, fp32 accumulate                 */
+
+#define PN_FUSION_CONCAT 0      /* [p; t]        configs/base_config.yaml:44 (default)      */
+#define PN_FUSION_CONCAT_DIFF 1 /* [p; t; p - t] protnote/models/ProtNote.py:128-138        */
+#define PN_FUSION_CONCAT_PROD 2 /* [p; t; p * t] protnote/models/ProtNote.py:139-150        */
+
+int pn_version(void);
+/* Thread-local description of the last error on this thread ("" if none). */
+const char* pn_last_error(void);
+/* 0 if `device` is a compute-capability 10.x GPU this library can run on. */
+int pn_device_check(int device);
+/* Engine knobs: "bk" = 32 | 64 (k-block / swizzle width), "chunk_rows" (pairs per scorer chunk, 0 = auto). */
+int pn_set_option(const char* name, long long value);
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+long long pn_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Sequence encoder: ProteInfer dilated ResNet, eval mode.
+ * Replaces ProteInfer.get_embeddings (protnote/models/protein_encoders.py:109-118), i.e. MaskedConv1D (:8-17),
+ * Residual (:23-67) and set_padding_to_sentinel (protnote/data/datasets.py:535-569).
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct pn_encoder_cfg {
+  int input_channels;  /* 20   embed_sequences_params.INPUT_CHANNELS   */
+  int channels;        /* 1100 OUTPUT_CHANNELS                         */
+  int bottleneck;      /* 550  floor(channels * BOTTLENECK_FACTOR)     */
+  int kernel_size;     /* 9                                            */
+  int dilation_base;   /* 3                                            */
+  int num_blocks;      /* 5                                            */
+  float bn_eps;        /* 1e-3 (protein_encoders.py:36,48)             */
+} pn_encoder_cfg;
+
+/* Parameter pointers in reference state_dict order, num_batches_tracked omitted:
+ *   conv1.weight (C,Cin,k), conv1.bias,
+ *   then per block i: bn_activation_1.0.{weight,bias,running_mean,running_var},
+ *                     masked_conv1.{weight (Cb,C,k), bias},
+ *                     bn_activation_2.0.{weight,bias,running_mean,running_var},
+ *                     masked_conv2.{weight (C,Cb,1), bias}
+ * -> 2 + 12 * num_blocks fp32 device pointers (`params` itself is a HOST array). */
+size_t pn_encoder_packed_bytes(const pn_encoder_cfg* cfg);
+int pn_encoder_pack(const pn_encoder_cfg* cfg, const float* const* params, int num_params, void* packed,
+                    size_t packed_bytes, void* stream);
+size_t pn_encoder_workspace_bytes(const pn_encoder_cfg* cfg, int batch, int T);
+/* x [batch][input_channels][T] fp32 (any float values, not only one-hot), lengths [batch] int64,
+ * out [batch][channels] fp32 = masked mean over positions < length. */
+int pn_encoder_forward(const pn_encoder_cfg* cfg, const void* packed, const float* x, const int64_t* lengths,
+                       int batch, int T, float* out, void* workspace, size_t workspace_bytes, int mode,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Projection heads + pair scorer: ProtNote.forward from the projections on, eval mode
+ * (protnote/models/ProtNote.py:270-322): W_p / W_l (torchvision MLP, :63-81), _get_joint_embeddings (:112-152),
+ * output MLP get_mlp (:337-378), probability-space ensembling of k description rows (:308-322).
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct pn_scorer_cfg {
+  int protein_dim;       /* 1100 PROTEIN_EMBEDDING_DIM                                   */
+  int label_dim;         /* 1024 LABEL_EMBEDDING_DIM                                     */
+  int latent_dim;        /* 1024 LATENT_EMBEDDING_DIM                                    */
+  int proj_hidden;       /* 3072 latent_dim * PROJECTION_HEAD_HIDDEN_DIM_SCALE_FACTOR    */
+  int proj_layers;       /* 4    PROJECTION_HEAD_NUM_LAYERS (>= 1)                       */
+  int out_hidden;        /* 3072 int(round(OUTPUT_MLP_HIDDEN_DIM_SCALE_FACTOR * latent)) */
+  int out_layers;        /* 3    OUTPUT_MLP_NUM_LAYERS hidden layers (>= 2)              */
+  int out_batchnorm;     /* 1    OUTPUT_MLP_BATCHNORM (0: hidden Linear layers have a bias) */
+  int fusion;            /* PN_FUSION_*                                                  */
+  int descriptions_per_label; /* k: consecutive label rows ensembled per label (>= 1)   */
+  float bn_eps;          /* 1e-5 torch.nn.BatchNorm1d default                            */
+} pn_scorer_cfg;
+
+/* Parameter pointers (HOST array of fp32 device pointers), reference module order:
+ *   W_p: for i < proj_layers-1: {Linear.weight, BN.weight, BN.bias, BN.running_mean, BN.running_var}; last: Linear.weight
+ *   W_l: same
+ *   output_layer: for each hidden layer: Linear.weight, then (out_batchnorm ? BN x4 : Linear.bias);
+ *                 final Linear.weight (1,H), final Linear.bias (1)
+ */
+int pn_scorer_num_params(const pn_scorer_cfg* cfg);
+size_t pn_scorer_packed_bytes(const pn_scorer_cfg* cfg);
+int pn_scorer_pack(const pn_scorer_cfg* cfg, const float* const* params, int num_params, void* packed,
+                   size_t packed_bytes, void* stream);
+
+/* W_p then the protein half of output layer 1:  P_f [n][protein_dim] -> P_e [n][latent_dim] (nullable) and
+ * a [n][out_hidden] (BatchNorm-1 scale AND shift folded in).  workspace: pn_project_workspace_bytes(cfg, n). */
+size_t pn_project_workspace_bytes(const pn_scorer_cfg* cfg, long long rows);
+int pn_project_sequences(const pn_scorer_cfg* cfg, const void* packed, const float* P_f, long long n, float* P_e,
+                         float* a, void* workspace, size_t workspace_bytes, int mode, void* stream);
+/* W_l then the label half of output layer 1: L_f [n][label_dim] -> L_e (nullable), c [n][out_hidden]
+ * (BatchNorm-1 scale folded in).  Constant across batches in eval mode: compute once, cache (the reference
+ * recomputes W_l(label_embeddings) every batch, ProtNote.py:271). */
+int pn_project_labels(const pn_scorer_cfg* cfg, const void* packed, const float* L_f, long long n, float* L_e,
+                      float* c, void* workspace, size_t workspace_bytes, int mode, void* stream);
+
+/* logits[b][l / k] for b < B, label rows l < L (L multiple of k); logits row stride ld_logits floats.
+ * a [B][out_hidden], c [L][out_hidden] from the two calls above; P_e / L_e only for PN_FUSION_CONCAT_PROD.
+ * workspace: any size >= pn_scorer_min_workspace_bytes(cfg); more lets it run bigger chunks
+ * (pn_scorer_workspace_bytes(cfg, B, L) = the size that scores everything in one chunk, capped). */
+size_t pn_scorer_min_workspace_bytes(const pn_scorer_cfg* cfg);
+size_t pn_scorer_workspace_bytes(const pn_scorer_cfg* cfg, long long B, long long L);
+int pn_score_pairs(const pn_scorer_cfg* cfg, const void* packed, const float* a, const float* c, const float* P_e,
+                   const float* L_e, long long B, long long L, float* logits, long long ld_logits, void* workspace,
+                   size_t workspace_bytes, int mode, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Plain dense layer on the same engine: y[M][N] = x[M][K] * w[N][K]^T + bias   (ProteInfer.output_layer,
+ * protnote/models/protein_encoders.py:120-123, and the unit tests of the engine).
+ * workspace >= pn_linear_workspace_bytes(M, N, K).
+ * ---------------------------------------------------------------------------------------------------------- */
+size_t pn_linear_workspace_bytes(long long M, long long N, long long K);
+int pn_linear(const float* x, long long M, long long K, long long ldx, const float* w, long long N,
+              const float* bias, float* y, long long ldy, void* workspace, size_t workspace_bytes, int mode,
+              void* stream);
+/* 'same'-padded dilated Conv1d over channels-last activations on the same engine (unit test of the tap path):
+ * x [batch][channels_in][T] fp32 (reference layout), w (channels_out, channels_in, taps), y [batch][T][channels_out]. */
+size_t pn_conv1d_workspace_bytes(int batch, int T, int cin, int cout, int taps);
+int pn_conv1d(const float* x, const int64_t* lengths, int batch, int cin, int T, const float* w, const float* bias,
+              int cout, int taps, int dilation, float* y, void* workspace, size_t workspace_bytes, int mode,
+              void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PROTNOTE_B200_H */

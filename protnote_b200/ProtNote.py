@@ -1,0 +1,225 @@
+"""B200-native mirror of the reference's `protnote/models/ProtNote.py`.
+
+`ProtNote` keeps the reference constructor (ProtNote.py:10-36, incl. the `outout_mlp_add_batchnorm` spelling),
+`forward()` signature and return value (:168-177,324-334), submodule / state_dict names (`W_p.{0,4,8,12}`,
+`W_l.*`, `output_layer.{0,1,4,5,8,9,11}`, `sequence_encoder.*`, `label_encoder.*`) and error behaviour
+(ValueError on incompatible arguments, :217,262-264,305), so it drops into `bin/main.py:407-452` and
+`ProtNoteTrainer.evaluation_step` (ProtNoteTrainer.py:247-292) unchanged.
+
+What differs is where the arithmetic happens: eval-mode forward = sm_100a kernels behind the C ABI
+  sequence_encoder.get_embeddings -> pn_encoder_forward
+  W_p (+ protein half of output layer 1) -> pn_project_sequences
+  W_l (+ label half of output layer 1)   -> pn_project_labels   (cached across batches: constant in eval mode)
+  joint features + output MLP + ensembling -> pn_score_pairs    (the [B*L, 2d] joint tensor never exists)
+There is no PyTorch/CPU implementation of that path here; unsupported modes raise.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+
+from . import native
+from ._lib import ProtnoteB200Error
+from .protein_encoders import _versions
+
+
+def _projection_mlp(in_dim: int, hidden_dims, dropout: float) -> nn.Sequential:
+    """Same module sequence (hence the same state_dict indices) as torchvision.ops.MLP(in, hidden, bias=False,
+    norm_layer=BatchNorm1d, dropout=dropout) used at ProtNote.py:63-81: [Linear, BN, ReLU, Dropout]*, Linear, Dropout."""
+    layers = []
+    d = in_dim
+    for h in hidden_dims[:-1]:
+        layers += [nn.Linear(d, h, bias=False), nn.BatchNorm1d(h), nn.ReLU(), nn.Dropout(dropout)]
+        d = h
+    layers += [nn.Linear(d, hidden_dims[-1], bias=False), nn.Dropout(dropout)]
+    return nn.Sequential(*layers)
+
+
+def get_mlp(input_dim, hidden_dim, num_layers, input_dropout=0.0, dropout=0.0, batch_norm=False,
+            output_neuron_bias=None):
+    """Parameter container with the reference's layer order (ProtNote.py:337-378)."""
+    layers = []
+    if input_dropout > 0:
+        layers.append(nn.Dropout(input_dropout))
+    for idx in range(num_layers):
+        layers.append(nn.Linear(input_dim if idx == 0 else hidden_dim, hidden_dim, bias=not batch_norm))
+        if batch_norm:
+            layers.append(nn.BatchNorm1d(hidden_dim))
+        layers.append(nn.ReLU())
+        if idx < num_layers - 1:
+            layers.append(nn.Dropout(dropout))
+    output_neuron = nn.Linear(hidden_dim, 1)
+    if output_neuron_bias is not None:
+        output_neuron.bias.data.fill_(output_neuron_bias)
+    layers.append(output_neuron)
+    return nn.Sequential(*layers)
+
+
+class ProtNote(nn.Module):
+    def __init__(
+        self,
+        protein_embedding_dim=1100,
+        label_embedding_dim=1024,
+        label_embedding_pooling_method="mean",
+        inference_descriptions_per_label=1,
+        latent_dim=1024,
+        label_encoder=None,
+        sequence_encoder=None,
+        label_encoder_num_trainable_layers=False,
+        train_sequence_encoder=False,
+        output_mlp_hidden_dim_scale_factor=1024,
+        output_mlp_num_layers=2,
+        output_neuron_bias=None,
+        outout_mlp_add_batchnorm=True,
+        residual_connection=False,
+        dropout=0.0,
+        sequence_embedding_dropout=0.0,
+        label_embedding_dropout=0.0,
+        label_embedding_noising_alpha=0.0,
+        projection_head_num_layers=1,
+        projection_head_hidden_dim_scale_factor=1,
+        label_batch_size_limit=float("inf"),
+        sequence_batch_size_limit=float("inf"),
+        feature_fusion="concatenation",
+        temperature=0.07,
+        precision="strict",
+    ):
+        super().__init__()
+        self.label_encoder_num_trainable_layers, self.train_sequence_encoder = (
+            label_encoder_num_trainable_layers, train_sequence_encoder)
+        self.label_encoder, self.sequence_encoder = label_encoder, sequence_encoder
+        self.inference_descriptions_per_label = inference_descriptions_per_label
+        self.label_batch_size_limit, self.sequence_batch_size_limit = label_batch_size_limit, sequence_batch_size_limit
+        self.feature_fusion = feature_fusion
+        self.temperature = temperature
+        self.label_embedding_pooling_method = label_embedding_pooling_method
+        self.latent_dim = latent_dim
+        self.label_embedding_noising_alpha = label_embedding_noising_alpha
+        self.residual_connection = residual_connection
+        self.precision = precision
+
+        hidden = [latent_dim * projection_head_hidden_dim_scale_factor] * (projection_head_num_layers - 1) + [latent_dim]
+        self.W_p = _projection_mlp(protein_embedding_dim, hidden, dropout)
+        self.W_l = _projection_mlp(label_embedding_dim, hidden, dropout)
+        # the reference wraps the heads when these are > 0, which renames the keys to W_p.1.* / W_l.1.* (:83-86)
+        if sequence_embedding_dropout > 0:
+            self.W_p = nn.Sequential(nn.Dropout(sequence_embedding_dropout), self.W_p)
+        if label_embedding_dropout > 0:
+            self.W_l = nn.Sequential(nn.Dropout(label_embedding_dropout), self.W_l)
+        if self.label_embedding_pooling_method == "all":
+            self.raw_attn_scorer = nn.Linear(label_embedding_dim, 1, bias=True)
+        if self.feature_fusion.startswith("concatenation"):
+            self.output_layer = get_mlp(
+                input_dim=self._get_concatenated_features_dim(),
+                hidden_dim=int(round(output_mlp_hidden_dim_scale_factor * latent_dim)),
+                num_layers=output_mlp_num_layers,
+                output_neuron_bias=output_neuron_bias,
+                batch_norm=outout_mlp_add_batchnorm,
+                dropout=dropout,
+            )
+        self._cfg = dict(protein_dim=protein_embedding_dim, label_dim=label_embedding_dim, latent_dim=latent_dim,
+                         proj_hidden=latent_dim * projection_head_hidden_dim_scale_factor,
+                         proj_layers=projection_head_num_layers,
+                         out_hidden=int(round(output_mlp_hidden_dim_scale_factor * latent_dim)),
+                         out_layers=output_mlp_num_layers, out_batchnorm=bool(outout_mlp_add_batchnorm))
+        self._packed = None
+        self._packed_key = None
+        self._label_cache = None
+
+    def _get_concatenated_features_dim(self):
+        dim = {"concatenation_diff": self.latent_dim * 3, "concatenation_prod": self.latent_dim * 3,
+               "concatenation": self.latent_dim * 2}
+        return dim[self.feature_fusion]
+
+    # ------------------------------------------------------------------ packed-weight cache
+    @staticmethod
+    def _head_sources(head: nn.Module):
+        if isinstance(head[0], nn.Dropout) and isinstance(head[1], nn.Sequential):
+            head = head[1]
+        srcs, mods = [], list(head)
+        for i, m in enumerate(mods):
+            if isinstance(m, nn.Linear):
+                srcs.append(m.weight)
+                if i + 1 < len(mods) and isinstance(mods[i + 1], nn.BatchNorm1d):
+                    bn = mods[i + 1]
+                    srcs += [bn.weight, bn.bias, bn.running_mean, bn.running_var]
+        return srcs
+
+    def _pack_sources(self):
+        srcs = self._head_sources(self.W_p) + self._head_sources(self.W_l)
+        mods = list(self.output_layer)
+        for i, m in enumerate(mods[:-1]):
+            if isinstance(m, nn.Linear):
+                srcs.append(m.weight)
+                if isinstance(mods[i + 1], nn.BatchNorm1d):
+                    bn = mods[i + 1]
+                    srcs += [bn.weight, bn.bias, bn.running_mean, bn.running_var]
+                else:
+                    srcs.append(m.bias)
+        srcs += [mods[-1].weight, mods[-1].bias]
+        return srcs
+
+    def _ensure_packed(self):
+        srcs = self._pack_sources()
+        key = _versions(srcs) + (self.feature_fusion, self.inference_descriptions_per_label)
+        if self._packed is None or key != self._packed_key:
+            bn_eps = next((m.eps for m in self.output_layer if isinstance(m, nn.BatchNorm1d)), 1e-5)
+            sc = native.PackedScorer(fusion=self.feature_fusion,
+                                     descriptions_per_label=self.inference_descriptions_per_label, bn_eps=bn_eps,
+                                     **self._cfg)
+            sc.pack(srcs)
+            self._packed, self._packed_key, self._label_cache = sc, key, None
+        return self._packed
+
+    def _projected_labels(self, scorer, L_f, mode, want_embedding):
+        key = (L_f.data_ptr(), L_f._version, tuple(L_f.shape), self._packed_key, mode, want_embedding)
+        if self._label_cache is not None and self._label_cache[0] == key:
+            return self._label_cache[1]
+        out = scorer.project_labels(L_f, mode, want_embedding=want_embedding)
+        # keep a reference to L_f so its storage (the cache key) cannot be recycled for other data
+        self._label_cache = (key, out, L_f)
+        return out
+
+    # ------------------------------------------------------------------ reference interface
+    def forward(self, sequence_onehots=None, sequence_embeddings=None, sequence_lengths=None, tokenized_labels=None,
+                label_embeddings=None, label_token_counts=None, save_embeddings=False):
+        if self.training:
+            raise ProtnoteB200Error("protnote_b200.ProtNote implements the eval-mode scoring path (BatchNorm running "
+                                    "statistics, no dropout/noise); call .eval().  Training is out of scope this round.")
+        # ---- label embeddings (ProtNote.py:192-217): cached embeddings only
+        if label_embeddings is not None:
+            L_f = label_embeddings
+        else:
+            raise ValueError("Incompatible label parameters passed to forward method.")
+        if self.label_embedding_pooling_method == "all":
+            raise ProtnoteB200Error("LABEL_EMBEDDING_POOLING_METHOD 'all' (token-level attention pooling, "
+                                    "ProtNote.py:154-166) is not on the cached-embedding path")
+        if not self.feature_fusion.startswith("concatenation"):
+            if self.feature_fusion == "similarity":
+                raise ProtnoteB200Error("FEATURE_FUSION 'similarity' has no fused kernel yet")
+            raise ValueError("feature fusion method not implemented")
+        if save_embeddings:
+            raise ProtnoteB200Error("save_embeddings=True would materialise the [B*L, 2d] joint tensor the fused "
+                                    "scorer exists to avoid; not supported")
+        dev = self.output_layer[-1].weight.device
+        mode = native.MODES[self.precision]
+        scorer = self._ensure_packed()
+        # ---- sequence embeddings (ProtNote.py:243-264)
+        if sequence_embeddings is not None:
+            P_f = sequence_embeddings.to(dev, non_blocking=True)
+        elif sequence_onehots is not None and sequence_lengths is not None:
+            if self.sequence_encoder is None:
+                raise ValueError("Incompatible sequence parameters passed to forward method.")
+            P_f = self.sequence_encoder.get_embeddings(sequence_onehots.to(dev, non_blocking=True),
+                                                       sequence_lengths.to(dev, non_blocking=True))
+        else:
+            raise ValueError("Incompatible sequence parameters passed to forward method.")
+        L_f = L_f.to(dev, non_blocking=True)
+        need_emb = self.feature_fusion == "concatenation_prod"
+        P_e, a = scorer.project_sequences(P_f, mode, want_embedding=need_emb)
+        L_e, c = self._projected_labels(scorer, L_f, mode, need_emb)
+        logits = scorer.score(a, c, P_e, L_e, mode)
+        embeddings = {"output_layer_embeddings": [], "joint_embeddings": []}
+        return logits, embeddings

@@ -1,0 +1,104 @@
+"""ctypes binding of include/protnote_b200.h.  There is no fallback: if the library is missing the import of any
+compute entry point raises (the product path must fail loudly, never drop to PyTorch or CPU arithmetic)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG_DIR, "lib", "libprotnote_b200.so")
+
+PN_STRICT = 3
+PN_FAST = 1
+FUSIONS = {"concatenation": 0, "concatenation_diff": 1, "concatenation_prod": 2}
+
+
+class EncoderCfg(C.Structure):
+    _fields_ = [("input_channels", C.c_int), ("channels", C.c_int), ("bottleneck", C.c_int),
+                ("kernel_size", C.c_int), ("dilation_base", C.c_int), ("num_blocks", C.c_int),
+                ("bn_eps", C.c_float)]
+
+
+class ScorerCfg(C.Structure):
+    _fields_ = [("protein_dim", C.c_int), ("label_dim", C.c_int), ("latent_dim", C.c_int),
+                ("proj_hidden", C.c_int), ("proj_layers", C.c_int), ("out_hidden", C.c_int),
+                ("out_layers", C.c_int), ("out_batchnorm", C.c_int), ("fusion", C.c_int),
+                ("descriptions_per_label", C.c_int), ("bn_eps", C.c_float)]
+
+
+_P = C.c_void_p
+_LL = C.c_longlong
+_SZ = C.c_size_t
+_I = C.c_int
+
+# name -> (restype, argtypes); every symbol include/protnote_b200.h declares
+SIGNATURES = {
+    "pn_version": (_I, []),
+    "pn_last_error": (C.c_char_p, []),
+    "pn_device_check": (_I, [_I]),
+    "pn_set_option": (_I, [C.c_char_p, _LL]),
+    "pn_launch_count": (_LL, []),
+    "pn_encoder_packed_bytes": (_SZ, [C.POINTER(EncoderCfg)]),
+    "pn_encoder_pack": (_I, [C.POINTER(EncoderCfg), C.POINTER(_P), _I, _P, _SZ, _P]),
+    "pn_encoder_workspace_bytes": (_SZ, [C.POINTER(EncoderCfg), _I, _I]),
+    "pn_encoder_forward": (_I, [C.POINTER(EncoderCfg), _P, _P, _P, _I, _I, _P, _P, _SZ, _I, _P]),
+    "pn_scorer_num_params": (_I, [C.POINTER(ScorerCfg)]),
+    "pn_scorer_packed_bytes": (_SZ, [C.POINTER(ScorerCfg)]),
+    "pn_scorer_pack": (_I, [C.POINTER(ScorerCfg), C.POINTER(_P), _I, _P, _SZ, _P]),
+    "pn_project_workspace_bytes": (_SZ, [C.POINTER(ScorerCfg), _LL]),
+    "pn_project_sequences": (_I, [C.POINTER(ScorerCfg), _P, _P, _LL, _P, _P, _P, _SZ, _I, _P]),
+    "pn_project_labels": (_I, [C.POINTER(ScorerCfg), _P, _P, _LL, _P, _P, _P, _SZ, _I, _P]),
+    "pn_scorer_min_workspace_bytes": (_SZ, [C.POINTER(ScorerCfg)]),
+    "pn_scorer_workspace_bytes": (_SZ, [C.POINTER(ScorerCfg), _LL, _LL]),
+    "pn_score_pairs": (_I, [C.POINTER(ScorerCfg), _P, _P, _P, _P, _P, _LL, _LL, _P, _LL, _P, _SZ, _I, _P]),
+    "pn_linear_workspace_bytes": (_SZ, [_LL, _LL, _LL]),
+    "pn_linear": (_I, [_P, _LL, _LL, _LL, _P, _LL, _P, _P, _LL, _P, _SZ, _I, _P]),
+    "pn_conv1d_workspace_bytes": (_SZ, [_I, _I, _I, _I, _I]),
+    "pn_conv1d": (_I, [_P, _P, _I, _I, _I, _P, _P, _I, _I, _I, _P, _P, _SZ, _I, _P]),
+}
+
+_lib = None
+
+
+class ProtnoteB200Error(RuntimeError):
+    pass
+
+
+def load():
+    """Loads the shared library (once).  Raises if it has not been built: there is no other compute path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ProtnoteB200Error(
+            f"{LIB_PATH} is missing: build it with `python -m protnote_b200.build` (nvcc, sm_100a). "
+            "protnote_b200 has no PyTorch/CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status: int):
+    if status != 0:
+        raise ProtnoteB200Error(load().pn_last_error().decode("utf-8", "replace"))
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def pointer_array(tensors):
+    arr = (_P * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr()
+    return arr

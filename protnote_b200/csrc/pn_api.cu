@@ -1,0 +1,954 @@
+// C ABI + host-side orchestration of the B200-native ProtNote scoring path (see include/protnote_b200.h).
+// Everything here is launch logic: buffer carving, TMA descriptors, kernel sequencing.  No device allocation,
+// no synchronisation, no CPU arithmetic on tensor data.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/protnote_b200.h"
+#include "pn_kernels.cuh"
+
+namespace {
+
+using namespace pn;
+
+thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+int g_bk_option = 0;             // 0 = auto (strict: 32, fast: 64)
+long long g_chunk_rows = 0;      // 0 = auto
+
+int fail(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return 1;
+}
+
+#define PN_CUDA(expr)                                                                       \
+  do {                                                                                      \
+    cudaError_t e_ = (expr);                                                                \
+    if (e_ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+#define PN_TRY(expr)          \
+  do {                        \
+    int r_ = (expr);          \
+    if (r_ != 0) return r_;   \
+  } while (0)
+
+inline long long round_up(long long x, long long m) { return (x + m - 1) / m * m; }
+
+// ------------------------------------------------------------------------------------------------
+// TMA descriptors (driver entry point resolved at run time: the library links no libcuda)
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+
+int resolve_encode() {
+  if (g_encode) return 0;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  PN_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (qres != cudaDriverEntryPointSuccess || fn == nullptr) return fail("cuTensorMapEncodeTiled not available");
+  g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  return 0;
+}
+
+// fp16 tensor, dims fastest-first.  strides_bytes[i] = stride of dim i+1.
+int make_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+             const cuuint32_t* box, int swizzle_bytes) {
+  PN_TRY(resolve_encode());
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128  ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                      : CU_TENSOR_MAP_SWIZZLE_32B;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return fail("TMA base %p not 16-byte aligned", base);
+  for (int i = 0; i + 1 < rank; ++i)
+    if (strides_bytes[i] % 16 != 0) return fail("TMA stride %llu not a multiple of 16", (unsigned long long)strides_bytes[i]);
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims,
+                        strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail("cuTensorMapEncodeTiled failed (%d): rank %d dims %llu,%llu box %u,%u", (int)r, rank,
+                (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// engine launch
+// ------------------------------------------------------------------------------------------------
+struct Planes {             // an fp32 tensor carried as fp16 planes, row-major, K fastest
+  const __half* hi = nullptr;
+  const __half* lo = nullptr;
+  long long rows = 0;       // plain: M or N.  conv: batch * T
+  long long cols = 0;       // logical K extent (channels for conv)
+  long long ld = 0;         // row pitch in elements (multiple of 8)
+};
+
+struct ConvView {           // A operand as [batch][T][C] with taps (taps == 0 -> plain matrix)
+  int taps = 0, dil = 1, T = 0, batch = 0;
+  int cpad = 0;             // K offset between taps in the packed weight rows
+  const long long* lengths = nullptr;
+};
+
+struct Epilogue {
+  const float* scale = nullptr; const float* shift = nullptr;
+  const float* resid = nullptr; long long ld_resid = 0;
+  float* out_f32 = nullptr; long long ld_out = 0;
+  const float* scale2 = nullptr; const float* shift2 = nullptr;
+  int relu = 0;
+  __half* out_hi = nullptr; __half* out_lo = nullptr; long long ld_split = 0;
+  const float* dot_w = nullptr; float* dot_out = nullptr;
+  int pair_nl = 0;
+  const float* add_p = nullptr; long long ld_add_p = 0;
+  const float* add_l = nullptr; long long ld_add_l = 0;
+};
+
+int choose_bn(long long N) {
+  if (N <= 256) return (int)round_up(N, 32);
+  const int cand[] = {256, 224, 192};
+  int best = 256;
+  long long best_waste = 1LL << 60;
+  for (int bn : cand) {
+    const long long waste = round_up(N, bn) - N;
+    if (waste < best_waste) {
+      best_waste = waste;
+      best = bn;
+    }
+  }
+  return best;
+}
+
+int tiles_n_for(long long N) { return (int)((N + choose_bn(N) - 1) / choose_bn(N)); }
+
+int pick_bk(int mode) {
+  if (g_bk_option == 32 || g_bk_option == 64) return g_bk_option;
+  return mode == PN_STRICT ? 32 : 64;
+}
+
+int g_num_sms = 0;
+int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+template <int BK, int NPASS>
+int launch_gemm_t(const GemmParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BK, NPASS>;
+  static bool configured = false;
+  if (!configured) {
+    PN_CUDA(cudaFuncSetAttribute(gemm_kernel<BK, NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured = true;
+  }
+  const int total = p.tiles_m * p.tiles_n;
+  const int grid = total < num_sms() ? total : num_sms();
+  gemm_kernel<BK, NPASS><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(p);
+  PN_CUDA(cudaGetLastError());
+  g_launches++;
+  return 0;
+}
+
+// D = A * B^T with the fused epilogue.  A: plain [M][K] or conv view; B: packed weights [N][K_total].
+int launch_gemm(const Planes& A, const ConvView& cv, const Planes& B, long long N, const Epilogue& e, int mode,
+                cudaStream_t stream) {
+  if (mode != PN_STRICT && mode != PN_FAST) return fail("mode must be PN_STRICT or PN_FAST");
+  const int bk = pick_bk(mode);
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = (int)N;
+  p.bn = choose_bn(N);
+  p.tiles_n = (int)((N + p.bn - 1) / p.bn);
+  const bool need_lo = mode == PN_STRICT;
+  if (need_lo && (A.lo == nullptr || B.lo == nullptr)) return fail("strict mode needs lo planes");
+  if (cv.taps > 0) {
+    const int cblocks = (int)((A.cols + bk - 1) / bk);
+    p.conv_taps = cv.taps;
+    p.conv_cblocks = cblocks;
+    p.conv_cpad = cv.cpad;
+    p.conv_dil = cv.dil;
+    p.conv_T = cv.T;
+    p.conv_tiles_per_seq = (cv.T + kBM - 1) / kBM;
+    p.lengths = cv.lengths;
+    p.M = cv.batch * cv.T;
+    p.tiles_m = cv.batch * p.conv_tiles_per_seq;
+    p.num_kblocks = cv.taps * cblocks;
+    const cuuint64_t dims[3] = {(cuuint64_t)A.cols, (cuuint64_t)cv.T, (cuuint64_t)cv.batch};
+    const cuuint64_t strides[2] = {(cuuint64_t)A.ld * 2, (cuuint64_t)A.ld * 2 * cv.T};
+    const cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)kBM, 1};
+    PN_TRY(make_map(&p.tm_a_hi, A.hi, 3, dims, strides, box, bk * 2));
+    if (need_lo) PN_TRY(make_map(&p.tm_a_lo, A.lo, 3, dims, strides, box, bk * 2));
+  } else {
+    p.M = (int)A.rows;
+    p.tiles_m = (int)((A.rows + kBM - 1) / kBM);
+    p.num_kblocks = (int)((A.cols + bk - 1) / bk);
+    const cuuint64_t dims[2] = {(cuuint64_t)A.cols, (cuuint64_t)A.rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)A.ld * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)kBM};
+    PN_TRY(make_map(&p.tm_a_hi, A.hi, 2, dims, strides, box, bk * 2));
+    if (need_lo) PN_TRY(make_map(&p.tm_a_lo, A.lo, 2, dims, strides, box, bk * 2));
+  }
+  if (A.rows >= (1LL << 31) || p.tiles_m <= 0 || p.num_kblocks <= 0) return fail("bad GEMM shape");
+  {
+    const cuuint64_t dims[2] = {(cuuint64_t)B.cols, (cuuint64_t)B.rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)B.ld * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)p.bn};
+    PN_TRY(make_map(&p.tm_b_hi, B.hi, 2, dims, strides, box, bk * 2));
+    if (need_lo) PN_TRY(make_map(&p.tm_b_lo, B.lo, 2, dims, strides, box, bk * 2));
+  }
+  p.scale = e.scale; p.shift = e.shift;
+  p.resid = e.resid; p.ld_resid = e.ld_resid;
+  p.out_f32 = e.out_f32; p.ld_out = e.ld_out;
+  p.scale2 = e.scale2; p.shift2 = e.shift2;
+  p.relu = e.relu;
+  p.out_hi = e.out_hi; p.out_lo = need_lo ? e.out_lo : nullptr; p.ld_split = e.ld_split;
+  p.dot_w = e.dot_w; p.dot_out = e.dot_out;
+  p.pair_nl = e.pair_nl;
+  p.add_p = e.add_p; p.ld_add_p = e.ld_add_p;
+  p.add_l = e.add_l; p.ld_add_l = e.ld_add_l;
+  auto aligned16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  p.vec_out = e.out_f32 && aligned16(e.out_f32) && e.ld_out % 4 == 0;
+  p.vec_resid = e.resid && aligned16(e.resid) && e.ld_resid % 4 == 0;
+  p.vec_split = e.out_hi && aligned16(e.out_hi) && (!p.out_lo || aligned16(p.out_lo)) && e.ld_split % 8 == 0;
+  if (bk == 32) return mode == PN_STRICT ? launch_gemm_t<32, 3>(p, stream) : launch_gemm_t<32, 1>(p, stream);
+  return mode == PN_STRICT ? launch_gemm_t<64, 3>(p, stream) : launch_gemm_t<64, 1>(p, stream);
+}
+
+inline int ew_grid(long long work_items, int block = 256) {
+  long long g = (work_items + block - 1) / block;
+  const long long cap = (long long)num_sms() * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// ------------------------------------------------------------------------------------------------
+// buffer carving
+// ------------------------------------------------------------------------------------------------
+struct Arena {
+  char* base;
+  size_t size, off = 0;
+  Arena(void* b, size_t s) : base(static_cast<char*>(b)), size(s) {}
+  size_t take(size_t bytes) {   // returns offset (valid even when base == nullptr: used for sizing)
+    const size_t o = off;
+    off = (size_t)round_up((long long)(off + bytes), 256);
+    return o;
+  }
+  template <typename T>
+  T* at(size_t o) const { return reinterpret_cast<T*>(base + o); }
+  bool ok() const { return off <= size; }
+};
+
+struct PackedLinear {         // offsets into the packed arena
+  int N = 0, cin = 0, taps = 1, cpad = 0, ld = 0;
+  size_t hi = 0, lo = 0, wscale = 0, absmax = 0, scale = 0, shift = 0;
+};
+
+PackedLinear carve_linear(Arena& ar, int N, int cin, int taps) {
+  PackedLinear pl;
+  pl.N = N;
+  pl.cin = cin;
+  pl.taps = taps;
+  pl.cpad = (int)round_up(cin, 64);
+  pl.ld = pl.cpad * taps;
+  pl.hi = ar.take((size_t)N * pl.ld * 2);
+  pl.lo = ar.take((size_t)N * pl.ld * 2);
+  pl.wscale = ar.take(4);
+  pl.absmax = ar.take(4);
+  pl.scale = ar.take((size_t)N * 4);
+  pl.shift = ar.take((size_t)N * 4);
+  return pl;
+}
+
+Planes weight_planes(const Arena& ar, const PackedLinear& pl) {
+  Planes B;
+  B.hi = ar.at<__half>(pl.hi);
+  B.lo = ar.at<__half>(pl.lo);
+  B.rows = pl.N;
+  B.cols = pl.ld;
+  B.ld = pl.ld;
+  return B;
+}
+
+// w laid out (N, cin, taps) with element strides (sn, sc, st); optional second matrix added with `sign2`
+// is not needed: concatenation_diff is folded by two packs into separate buffers (see pack_scorer).
+int pack_linear(const Arena& ar, const PackedLinear& pl, const float* w, long long sn, long long sc, long long st,
+                long long span, const float* bias, const float* gamma, const float* beta, const float* mean,
+                const float* var, float eps, cudaStream_t stream) {
+  unsigned* am = ar.at<unsigned>(pl.absmax);
+  PN_CUDA(cudaMemsetAsync(am, 0, 4, stream));
+  // absmax over the rows' used span (row n covers w[n*sn .. n*sn + span))
+  absmax_kernel<<<ew_grid((long long)pl.N * span), 256, 0, stream>>>(w, pl.N, span, sn, am);
+  g_launches++;
+  PN_CUDA(cudaGetLastError());
+  pack_weight_kernel<<<ew_grid((long long)pl.N * pl.ld), 256, 0, stream>>>(
+      w, pl.N, pl.cin, pl.taps, sn, sc, st, pl.cpad, pl.ld, am, ar.at<float>(pl.wscale), ar.at<__half>(pl.hi),
+      ar.at<__half>(pl.lo));
+  g_launches++;
+  PN_CUDA(cudaGetLastError());
+  fold_affine_kernel<<<(pl.N + 255) / 256, 256, 0, stream>>>(pl.N, bias, gamma, beta, mean, var, eps,
+                                                             ar.at<float>(pl.wscale), ar.at<float>(pl.scale),
+                                                             ar.at<float>(pl.shift));
+  g_launches++;
+  PN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// encoder
+// ------------------------------------------------------------------------------------------------
+struct EncoderLayout {
+  PackedLinear conv1;
+  struct Block {
+    size_t bn1_scale, bn1_shift;
+    PackedLinear conv_d, conv_p;
+  };
+  std::vector<Block> blocks;
+  size_t bytes = 0;
+};
+
+EncoderLayout encoder_layout(const pn_encoder_cfg& c) {
+  Arena ar(nullptr, 0);
+  EncoderLayout L;
+  L.conv1 = carve_linear(ar, c.channels, c.input_channels, c.kernel_size);
+  for (int i = 0; i < c.num_blocks; ++i) {
+    EncoderLayout::Block b;
+    b.bn1_scale = ar.take((size_t)c.channels * 4);
+    b.bn1_shift = ar.take((size_t)c.channels * 4);
+    b.conv_d = carve_linear(ar, c.bottleneck, c.channels, c.kernel_size);
+    b.conv_p = carve_linear(ar, c.channels, c.bottleneck, 1);
+    L.blocks.push_back(b);
+  }
+  L.bytes = ar.off;
+  return L;
+}
+
+int check_encoder_cfg(const pn_encoder_cfg* c) {
+  if (!c) return fail("null encoder cfg");
+  if (c->input_channels < 1 || c->channels < 1 || c->bottleneck < 1 || c->num_blocks < 0 || c->dilation_base < 1)
+    return fail("bad encoder cfg");
+  if (c->kernel_size < 1 || c->kernel_size % 2 == 0) return fail("kernel_size must be odd (got %d)", c->kernel_size);
+  return 0;
+}
+
+struct EncoderWs {
+  size_t in_hi, in_lo, x, act_hi, act_lo, hid_hi, hid_lo;
+  int cin_pad, ldc, ldb;
+  size_t bytes;
+};
+
+EncoderWs encoder_ws(const pn_encoder_cfg& c, long long batch, long long T) {
+  Arena ar(nullptr, 0);
+  EncoderWs w;
+  w.cin_pad = (int)round_up(c.input_channels, 64);
+  w.ldc = (int)round_up(c.channels, 64);
+  w.ldb = (int)round_up(c.bottleneck, 64);
+  const size_t pos = (size_t)batch * T;
+  w.in_hi = ar.take(pos * w.cin_pad * 2);
+  w.in_lo = ar.take(pos * w.cin_pad * 2);
+  w.x = ar.take(pos * w.ldc * 4);
+  w.act_hi = ar.take(pos * w.ldc * 2);
+  w.act_lo = ar.take(pos * w.ldc * 2);
+  w.hid_hi = ar.take(pos * w.ldb * 2);
+  w.hid_lo = ar.take(pos * w.ldb * 2);
+  w.bytes = ar.off;
+  return w;
+}
+
+// ------------------------------------------------------------------------------------------------
+// scorer
+// ------------------------------------------------------------------------------------------------
+struct ScorerLayout {
+  std::vector<PackedLinear> wp, wl;      // projection heads
+  PackedLinear l1_p, l1_l, l1_x;         // output layer 1 split over [p; t; (p*t)]
+  size_t l1_shift = 0;                   // folded BN1 shift (+ bias) applied on the protein side
+  std::vector<PackedLinear> hidden;      // output hidden layers 2..n
+  size_t w_out = 0, b_out = 0;           // final Linear(H -> 1)
+  size_t tmp = 0;                        // scratch for the concatenation_diff weight fold [H][latent]
+  size_t bytes = 0;
+};
+
+ScorerLayout scorer_layout(const pn_scorer_cfg& c) {
+  Arena ar(nullptr, 0);
+  ScorerLayout L;
+  for (int head = 0; head < 2; ++head) {
+    int in_dim = head == 0 ? c.protein_dim : c.label_dim;
+    for (int i = 0; i < c.proj_layers; ++i) {
+      const int out_dim = i == c.proj_layers - 1 ? c.latent_dim : c.proj_hidden;
+      (head == 0 ? L.wp : L.wl).push_back(carve_linear(ar, out_dim, in_dim, 1));
+      in_dim = out_dim;
+    }
+  }
+  L.l1_p = carve_linear(ar, c.out_hidden, c.latent_dim, 1);
+  L.l1_l = carve_linear(ar, c.out_hidden, c.latent_dim, 1);
+  if (c.fusion == PN_FUSION_CONCAT_PROD) L.l1_x = carve_linear(ar, c.out_hidden, c.latent_dim, 1);
+  L.l1_shift = ar.take((size_t)c.out_hidden * 4);
+  for (int j = 1; j < c.out_layers; ++j) L.hidden.push_back(carve_linear(ar, c.out_hidden, c.out_hidden, 1));
+  L.w_out = ar.take((size_t)c.out_hidden * 4);
+  L.b_out = ar.take(4);
+  if (c.fusion == PN_FUSION_CONCAT_DIFF) L.tmp = ar.take((size_t)c.out_hidden * c.latent_dim * 4 * 2);
+  L.bytes = ar.off;
+  return L;
+}
+
+int check_scorer_cfg(const pn_scorer_cfg* c) {
+  if (!c) return fail("null scorer cfg");
+  if (c->protein_dim < 1 || c->label_dim < 1 || c->latent_dim < 1 || c->proj_hidden < 1 || c->out_hidden < 1)
+    return fail("bad scorer dims");
+  if (c->proj_layers < 1) return fail("proj_layers must be >= 1");
+  if (c->out_layers < 2) return fail("out_layers must be >= 2 (got %d)", c->out_layers);
+  if (c->fusion < 0 || c->fusion > 2) return fail("unknown fusion %d", c->fusion);
+  if (c->descriptions_per_label < 1) return fail("descriptions_per_label must be >= 1");
+  return 0;
+}
+
+__global__ void combine_kernel(const float* __restrict__ a, const float* __restrict__ b, float sign, long long rows,
+                               int cols, long long lda, long long ldb, float* __restrict__ out) {
+  const long long total = rows * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols;
+    const int cidx = (int)(i % cols);
+    out[i] = a[r * lda + cidx] + sign * b[r * ldb + cidx];
+  }
+}
+
+__global__ void copy_floats_kernel(const float* __restrict__ src, float* __restrict__ dst, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i];
+}
+
+// One projection head (W_p or W_l) followed by its half of output layer 1.
+int run_projection(const pn_scorer_cfg& c, const ScorerLayout& L, const Arena& pk, bool protein, const float* in,
+                   long long n, float* emb_out, float* half_out, void* workspace, size_t workspace_bytes, int mode,
+                   cudaStream_t stream) {
+  const std::vector<PackedLinear>& head = protein ? L.wp : L.wl;
+  const int in_dim = protein ? c.protein_dim : c.label_dim;
+  const int ld_in = (int)round_up(in_dim, 64);
+  const int ld_h = (int)round_up(c.proj_hidden > c.latent_dim ? c.proj_hidden : c.latent_dim, 64);
+  const size_t per_row = (size_t)ld_in * 4 + (size_t)ld_h * 4 * 2 + 1024;
+  long long chunk = (long long)(workspace_bytes / per_row);
+  chunk = chunk / kBM * kBM;
+  if (chunk <= 0) return fail("projection workspace too small (%zu bytes)", workspace_bytes);
+  for (long long r0 = 0; r0 < n; r0 += chunk) {
+    const long long rows = (n - r0) < chunk ? (n - r0) : chunk;
+    Arena ws(workspace, workspace_bytes);
+    __half* in_hi = ws.at<__half>(ws.take((size_t)rows * ld_in * 2));
+    __half* in_lo = ws.at<__half>(ws.take((size_t)rows * ld_in * 2));
+    __half* buf_hi[2];
+    __half* buf_lo[2];
+    for (int q = 0; q < 2; ++q) {
+      buf_hi[q] = ws.at<__half>(ws.take((size_t)rows * ld_h * 2));
+      buf_lo[q] = ws.at<__half>(ws.take((size_t)rows * ld_h * 2));
+    }
+    if (!ws.ok()) return fail("projection workspace accounting error");
+    split_rows_kernel<<<ew_grid(rows * (ld_in / 8)), 256, 0, stream>>>(in + r0 * in_dim, rows, in_dim, in_dim, in_hi,
+                                                                       in_lo, ld_in);
+    g_launches++;
+    PN_CUDA(cudaGetLastError());
+    Planes A;
+    A.hi = in_hi; A.lo = in_lo; A.rows = rows; A.cols = in_dim; A.ld = ld_in;
+    int cur = 0;
+    for (size_t i = 0; i < head.size(); ++i) {
+      const PackedLinear& pl = head[i];
+      const bool last = i + 1 == head.size();
+      Epilogue e;
+      e.scale = pk.at<float>(pl.scale);
+      e.shift = pk.at<float>(pl.shift);
+      e.relu = last ? 0 : 1;
+      e.out_hi = buf_hi[cur]; e.out_lo = buf_lo[cur]; e.ld_split = ld_h;
+      if (last && emb_out) {
+        e.out_f32 = emb_out + r0 * c.latent_dim;
+        e.ld_out = c.latent_dim;
+      }
+      PN_TRY(launch_gemm(A, ConvView(), weight_planes(pk, pl), pl.N, e, mode, stream));
+      A.hi = buf_hi[cur]; A.lo = buf_lo[cur]; A.rows = rows; A.cols = pl.N; A.ld = ld_h;
+      cur ^= 1;
+    }
+    // half of output layer 1: protein side carries the folded BN1 shift, both sides carry its scale
+    const PackedLinear& pl = protein ? L.l1_p : L.l1_l;
+    Epilogue e;
+    e.scale = pk.at<float>(pl.scale);
+    e.shift = protein ? pk.at<float>(L.l1_shift) : nullptr;
+    e.out_f32 = half_out + r0 * c.out_hidden;
+    e.ld_out = c.out_hidden;
+    PN_TRY(launch_gemm(A, ConvView(), weight_planes(pk, pl), pl.N, e, mode, stream));
+  }
+  return 0;
+}
+
+size_t scorer_row_bytes(const pn_scorer_cfg& c) {
+  const size_t ld_h = (size_t)round_up(c.out_hidden, 64);
+  return ld_h * 2 /*bytes*/ * 2 /*planes*/ * 2 /*ping-pong*/ + (size_t)tiles_n_for(c.out_hidden) * 4;
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+int pn_version(void) { return 1; }
+
+const char* pn_last_error(void) { return g_err.c_str(); }
+
+long long pn_launch_count(void) { return g_launches.load(); }
+
+int pn_device_check(int device) {
+  cudaDeviceProp prop;
+  PN_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+  return 0;
+}
+
+int pn_set_option(const char* name, long long value) {
+  if (!name) return fail("null option name");
+  if (strcmp(name, "bk") == 0) {
+    if (value != 0 && value != 32 && value != 64) return fail("bk must be 0, 32 or 64");
+    g_bk_option = (int)value;
+    return 0;
+  }
+  if (strcmp(name, "chunk_rows") == 0) {
+    if (value < 0) return fail("chunk_rows must be >= 0");
+    g_chunk_rows = value;
+    return 0;
+  }
+  return fail("unknown option '%s'", name);
+}
+
+// ---------------------------------------------------------------------------------------- encoder
+size_t pn_encoder_packed_bytes(const pn_encoder_cfg* cfg) {
+  if (check_encoder_cfg(cfg)) return 0;
+  return encoder_layout(*cfg).bytes;
+}
+
+int pn_encoder_pack(const pn_encoder_cfg* cfg, const float* const* params, int num_params, void* packed,
+                    size_t packed_bytes, void* stream_) {
+  PN_TRY(check_encoder_cfg(cfg));
+  const pn_encoder_cfg& c = *cfg;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (num_params != 2 + 12 * c.num_blocks) return fail("encoder expects %d parameter pointers, got %d", 2 + 12 * c.num_blocks, num_params);
+  const EncoderLayout L = encoder_layout(c);
+  if (packed_bytes < L.bytes) return fail("packed buffer too small: %zu < %zu", packed_bytes, L.bytes);
+  Arena pk(packed, packed_bytes);
+  const int k = c.kernel_size;
+  // conv1 (C, Cin, k) + bias; no BatchNorm behind it
+  PN_TRY(pack_linear(pk, L.conv1, params[0], (long long)c.input_channels * k, k, 1, (long long)c.input_channels * k,
+                     params[1], nullptr, nullptr, nullptr, nullptr, 0.f, stream));
+  for (int i = 0; i < c.num_blocks; ++i) {
+    const float* const* q = params + 2 + 12 * i;
+    const EncoderLayout::Block& b = L.blocks[i];
+    // bn_activation_1: applied by the epilogue that PRODUCES this block's input
+    fold_affine_kernel<<<(c.channels + 255) / 256, 256, 0, stream>>>(c.channels, nullptr, q[0], q[1], q[2], q[3],
+                                                                     c.bn_eps, nullptr, pk.at<float>(b.bn1_scale),
+                                                                     pk.at<float>(b.bn1_shift));
+    g_launches++;
+    PN_CUDA(cudaGetLastError());
+    // dilated conv (Cb, C, k) + bias, then bn_activation_2 folded into its epilogue
+    PN_TRY(pack_linear(pk, b.conv_d, q[4], (long long)c.channels * k, k, 1, (long long)c.channels * k, q[5], q[6], q[7],
+                       q[8], q[9], c.bn_eps, stream));
+    // pointwise conv (C, Cb, 1) + bias
+    PN_TRY(pack_linear(pk, b.conv_p, q[10], c.bottleneck, 1, 0, c.bottleneck, q[11], nullptr, nullptr, nullptr, nullptr,
+                       0.f, stream));
+  }
+  return 0;
+}
+
+size_t pn_encoder_workspace_bytes(const pn_encoder_cfg* cfg, int batch, int T) {
+  if (check_encoder_cfg(cfg)) return 0;
+  return encoder_ws(*cfg, batch, T).bytes;
+}
+
+int pn_encoder_forward(const pn_encoder_cfg* cfg, const void* packed, const float* x, const int64_t* lengths,
+                       int batch, int T, float* out, void* workspace, size_t workspace_bytes, int mode,
+                       void* stream_) {
+  PN_TRY(check_encoder_cfg(cfg));
+  const pn_encoder_cfg& c = *cfg;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (batch <= 0 || T <= 0) return fail("empty encoder input (batch %d, T %d)", batch, T);
+  const EncoderLayout L = encoder_layout(c);
+  Arena pk(const_cast<void*>(packed), L.bytes);
+  const size_t per_seq = encoder_ws(c, 1, T).bytes + 4096;
+  int sub = (int)(workspace_bytes / per_seq);
+  if (sub <= 0) return fail("encoder workspace too small: %zu bytes < %zu for one sequence", workspace_bytes, per_seq);
+  if (sub > batch) sub = batch;
+  const long long* len64 = reinterpret_cast<const long long*>(lengths);
+  for (int b0 = 0; b0 < batch; b0 += sub) {
+    const int nb = batch - b0 < sub ? batch - b0 : sub;
+    const EncoderWs W = encoder_ws(c, nb, T);
+    if (W.bytes > workspace_bytes) return fail("encoder workspace accounting error");
+    Arena ws(workspace, workspace_bytes);
+    const long long* len = len64 + b0;
+    const long long pos = (long long)nb * T;
+    conv_input_kernel<<<ew_grid(pos), 256, 0, stream>>>(x + (long long)b0 * c.input_channels * T, len, nb,
+                                                        c.input_channels, T, W.cin_pad, ws.at<__half>(W.in_hi),
+                                                        ws.at<__half>(W.in_lo));
+    g_launches++;
+    PN_CUDA(cudaGetLastError());
+    float* X = ws.at<float>(W.x);
+    ConvView cv;
+    cv.batch = nb; cv.T = T; cv.lengths = len;
+    // conv1: x0 = mask(conv(x) + bias); act = mask(relu(bn1_0(x0)))
+    {
+      Planes A;
+      A.hi = ws.at<__half>(W.in_hi); A.lo = ws.at<__half>(W.in_lo);
+      A.rows = pos; A.cols = c.input_channels; A.ld = W.cin_pad;
+      cv.taps = c.kernel_size; cv.dil = 1; cv.cpad = L.conv1.cpad;
+      Epilogue e;
+      e.scale = pk.at<float>(L.conv1.scale); e.shift = pk.at<float>(L.conv1.shift);
+      e.out_f32 = X; e.ld_out = W.ldc;
+      if (c.num_blocks > 0) {
+        e.scale2 = pk.at<float>(L.blocks[0].bn1_scale); e.shift2 = pk.at<float>(L.blocks[0].bn1_shift);
+        e.relu = 1;
+        e.out_hi = ws.at<__half>(W.act_hi); e.out_lo = ws.at<__half>(W.act_lo); e.ld_split = W.ldc;
+      }
+      PN_TRY(launch_gemm(A, cv, weight_planes(pk, L.conv1), c.channels, e, mode, stream));
+    }
+    long long dil = 1;
+    for (int i = 0; i < c.num_blocks; ++i) {
+      const EncoderLayout::Block& b = L.blocks[i];
+      {   // hid = mask(relu(bn2(dilated_conv(act) + bias)))
+        Planes A;
+        A.hi = ws.at<__half>(W.act_hi); A.lo = ws.at<__half>(W.act_lo);
+        A.rows = pos; A.cols = c.channels; A.ld = W.ldc;
+        cv.taps = c.kernel_size; cv.dil = (int)dil; cv.cpad = b.conv_d.cpad;
+        Epilogue e;
+        e.scale = pk.at<float>(b.conv_d.scale); e.shift = pk.at<float>(b.conv_d.shift);
+        e.relu = 1;
+        e.out_hi = ws.at<__half>(W.hid_hi); e.out_lo = ws.at<__half>(W.hid_lo); e.ld_split = W.ldb;
+        PN_TRY(launch_gemm(A, cv, weight_planes(pk, b.conv_d), c.bottleneck, e, mode, stream));
+      }
+      {   // x = x + mask(conv1x1(hid) + bias); act = mask(relu(bn1_{i+1}(x)))
+        Planes A;
+        A.hi = ws.at<__half>(W.hid_hi); A.lo = ws.at<__half>(W.hid_lo);
+        A.rows = pos; A.cols = c.bottleneck; A.ld = W.ldb;
+        cv.taps = 1; cv.dil = 1; cv.cpad = b.conv_p.cpad;
+        Epilogue e;
+        e.scale = pk.at<float>(b.conv_p.scale); e.shift = pk.at<float>(b.conv_p.shift);
+        e.resid = X; e.ld_resid = W.ldc;
+        e.out_f32 = X; e.ld_out = W.ldc;
+        if (i + 1 < c.num_blocks) {
+          e.scale2 = pk.at<float>(L.blocks[i + 1].bn1_scale); e.shift2 = pk.at<float>(L.blocks[i + 1].bn1_shift);
+          e.relu = 1;
+          e.out_hi = ws.at<__half>(W.act_hi); e.out_lo = ws.at<__half>(W.act_lo); e.ld_split = W.ldc;
+        }
+        PN_TRY(launch_gemm(A, cv, weight_planes(pk, b.conv_p), c.channels, e, mode, stream));
+      }
+      dil *= c.dilation_base;
+      if (dil > (1 << 24)) return fail("dilation overflow");
+    }
+    pool_mean_kernel<<<dim3((c.channels + 31) / 32, nb), dim3(32, 8), 0, stream>>>(X, W.ldc, len, T, c.channels,
+                                                                                   out + (long long)b0 * c.channels,
+                                                                                   c.channels);
+    g_launches++;
+    PN_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------- scorer
+int pn_scorer_num_params(const pn_scorer_cfg* cfg) {
+  if (check_scorer_cfg(cfg)) return -1;
+  const int head = 5 * (cfg->proj_layers - 1) + 1;
+  const int out = cfg->out_layers * (cfg->out_batchnorm ? 5 : 2) + 2;
+  return 2 * head + out;
+}
+
+size_t pn_scorer_packed_bytes(const pn_scorer_cfg* cfg) {
+  if (check_scorer_cfg(cfg)) return 0;
+  return scorer_layout(*cfg).bytes;
+}
+
+int pn_scorer_pack(const pn_scorer_cfg* cfg, const float* const* params, int num_params, void* packed,
+                   size_t packed_bytes, void* stream_) {
+  PN_TRY(check_scorer_cfg(cfg));
+  const pn_scorer_cfg& c = *cfg;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (num_params != pn_scorer_num_params(cfg)) return fail("scorer expects %d parameter pointers, got %d", pn_scorer_num_params(cfg), num_params);
+  const ScorerLayout L = scorer_layout(c);
+  if (packed_bytes < L.bytes) return fail("packed buffer too small: %zu < %zu", packed_bytes, L.bytes);
+  Arena pk(packed, packed_bytes);
+  const float* const* q = params;
+  for (int head = 0; head < 2; ++head) {
+    const std::vector<PackedLinear>& H = head == 0 ? L.wp : L.wl;
+    for (size_t i = 0; i < H.size(); ++i) {
+      const bool last = i + 1 == H.size();
+      const float* w = *q++;
+      const float *g = nullptr, *bt = nullptr, *mu = nullptr, *var = nullptr;
+      if (!last) {
+        g = *q++; bt = *q++; mu = *q++; var = *q++;
+      }
+      PN_TRY(pack_linear(pk, H[i], w, H[i].cin, 1, 0, H[i].cin, nullptr, g, bt, mu, var, c.bn_eps, stream));
+    }
+  }
+  // output layer 1: weight (H, 2d or 3d), split by column block
+  const int d = c.latent_dim;
+  const int in1 = c.fusion == PN_FUSION_CONCAT ? 2 * d : 3 * d;
+  {
+    const float* w = *q++;
+    const float *bias = nullptr, *g = nullptr, *bt = nullptr, *mu = nullptr, *var = nullptr;
+    if (c.out_batchnorm) {
+      g = *q++; bt = *q++; mu = *q++; var = *q++;
+    } else {
+      bias = *q++;
+    }
+    const float* wp_src = w;
+    const float* wl_src = w + d;
+    long long src_ld = in1;
+    if (c.fusion == PN_FUSION_CONCAT_DIFF) {
+      // W [p; t; p - t] = (Wp + Wd) p + (Wl - Wd) t   (exact in real arithmetic)
+      float* tp = pk.at<float>(L.tmp);
+      float* tl = tp + (size_t)c.out_hidden * d;
+      combine_kernel<<<ew_grid((long long)c.out_hidden * d), 256, 0, stream>>>(w, w + 2 * d, 1.f, c.out_hidden, d, in1,
+                                                                               in1, tp);
+      combine_kernel<<<ew_grid((long long)c.out_hidden * d), 256, 0, stream>>>(w + d, w + 2 * d, -1.f, c.out_hidden, d,
+                                                                               in1, in1, tl);
+      g_launches += 2;
+      PN_CUDA(cudaGetLastError());
+      wp_src = tp;
+      wl_src = tl;
+      src_ld = d;
+    }
+    // scale = BN1 scale / wscale on every part; the shift (bias, mean, beta) goes to the protein side only
+    PN_TRY(pack_linear(pk, L.l1_p, wp_src, src_ld, 1, 0, d, bias, g, bt, mu, var, c.bn_eps, stream));
+    PN_TRY(pack_linear(pk, L.l1_l, wl_src, src_ld, 1, 0, d, nullptr, g, nullptr, nullptr, var, c.bn_eps, stream));
+    if (c.fusion == PN_FUSION_CONCAT_PROD)
+      PN_TRY(pack_linear(pk, L.l1_x, w + 2 * d, src_ld, 1, 0, d, nullptr, g, nullptr, nullptr, var, c.bn_eps, stream));
+    copy_floats_kernel<<<(c.out_hidden + 255) / 256, 256, 0, stream>>>(pk.at<float>(L.l1_p.shift), pk.at<float>(L.l1_shift),
+                                                                       c.out_hidden);
+    g_launches++;
+    PN_CUDA(cudaGetLastError());
+  }
+  for (size_t j = 0; j < L.hidden.size(); ++j) {
+    const float* w = *q++;
+    const float *bias = nullptr, *g = nullptr, *bt = nullptr, *mu = nullptr, *var = nullptr;
+    if (c.out_batchnorm) {
+      g = *q++; bt = *q++; mu = *q++; var = *q++;
+    } else {
+      bias = *q++;
+    }
+    PN_TRY(pack_linear(pk, L.hidden[j], w, c.out_hidden, 1, 0, c.out_hidden, bias, g, bt, mu, var, c.bn_eps, stream));
+  }
+  copy_floats_kernel<<<(c.out_hidden + 255) / 256, 256, 0, stream>>>(*q++, pk.at<float>(L.w_out), c.out_hidden);
+  copy_floats_kernel<<<1, 32, 0, stream>>>(*q++, pk.at<float>(L.b_out), 1);
+  g_launches += 2;
+  PN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+size_t pn_project_workspace_bytes(const pn_scorer_cfg* cfg, long long rows) {
+  if (check_scorer_cfg(cfg)) return 0;
+  const long long in_dim = cfg->protein_dim > cfg->label_dim ? cfg->protein_dim : cfg->label_dim;
+  const long long ld_in = round_up(in_dim, 64);
+  const long long ld_h = round_up(cfg->proj_hidden > cfg->latent_dim ? cfg->proj_hidden : cfg->latent_dim, 64);
+  const long long r = round_up(rows < 1 ? 1 : rows, kBM);
+  return (size_t)(r * (ld_in * 4 + ld_h * 4 * 2 + 1024) + 8192);
+}
+
+int pn_project_sequences(const pn_scorer_cfg* cfg, const void* packed, const float* P_f, long long n, float* P_e,
+                         float* a, void* workspace, size_t workspace_bytes, int mode, void* stream) {
+  PN_TRY(check_scorer_cfg(cfg));
+  if (n <= 0) return fail("no sequences to project");
+  const ScorerLayout L = scorer_layout(*cfg);
+  Arena pk(const_cast<void*>(packed), L.bytes);
+  return run_projection(*cfg, L, pk, true, P_f, n, P_e, a, workspace, workspace_bytes, mode,
+                        static_cast<cudaStream_t>(stream));
+}
+
+int pn_project_labels(const pn_scorer_cfg* cfg, const void* packed, const float* L_f, long long n, float* L_e,
+                      float* c_out, void* workspace, size_t workspace_bytes, int mode, void* stream) {
+  PN_TRY(check_scorer_cfg(cfg));
+  if (n <= 0) return fail("no label rows to project");
+  const ScorerLayout L = scorer_layout(*cfg);
+  Arena pk(const_cast<void*>(packed), L.bytes);
+  return run_projection(*cfg, L, pk, false, L_f, n, L_e, c_out, workspace, workspace_bytes, mode,
+                        static_cast<cudaStream_t>(stream));
+}
+
+size_t pn_scorer_min_workspace_bytes(const pn_scorer_cfg* cfg) {
+  if (check_scorer_cfg(cfg)) return 0;
+  const long long rows = round_up(1024, (long long)kBM * cfg->descriptions_per_label);
+  return scorer_row_bytes(*cfg) * (size_t)rows + 8192;
+}
+
+size_t pn_scorer_workspace_bytes(const pn_scorer_cfg* cfg, long long B, long long L) {
+  if (check_scorer_cfg(cfg)) return 0;
+  long long rows = B * L;
+  const long long cap = 1LL << 19;   // 512 Ki pairs per chunk is already > 20 ms of tensor work
+  if (rows > cap) rows = L <= cap ? cap / L * L : cap;
+  const size_t need = scorer_row_bytes(*cfg) * (size_t)round_up(rows, kBM) + 8192;
+  const size_t mn = pn_scorer_min_workspace_bytes(cfg);
+  return need > mn ? need : mn;
+}
+
+int pn_score_pairs(const pn_scorer_cfg* cfg, const void* packed, const float* a, const float* c_in, const float* P_e,
+                   const float* L_e, long long B, long long Lrows, float* logits, long long ld_logits, void* workspace,
+                   size_t workspace_bytes, int mode, void* stream_) {
+  PN_TRY(check_scorer_cfg(cfg));
+  const pn_scorer_cfg& c = *cfg;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int k = c.descriptions_per_label;
+  if (B <= 0 || Lrows <= 0) return fail("empty scorer input (B %lld, L %lld)", B, Lrows);
+  if (Lrows % k != 0) return fail("label rows (%lld) not a multiple of descriptions_per_label (%d)", Lrows, k);
+  if (c.fusion == PN_FUSION_CONCAT_PROD && (P_e == nullptr || L_e == nullptr))
+    return fail("concatenation_prod needs P_e and L_e");
+  const ScorerLayout L = scorer_layout(c);
+  Arena pk(const_cast<void*>(packed), L.bytes);
+  const int H = c.out_hidden;
+  const int ld_h = (int)round_up(H, 64);
+  const int parts = tiles_n_for(H);
+  const size_t per_row = scorer_row_bytes(c);
+  long long max_rows = (long long)((workspace_bytes > 8192 ? workspace_bytes - 8192 : 0) / per_row);
+  if (g_chunk_rows > 0 && g_chunk_rows < max_rows) max_rows = g_chunk_rows;
+  max_rows = max_rows / ((long long)kBM * k) * ((long long)kBM * k);
+  if (max_rows <= 0) return fail("scorer workspace too small: %zu bytes", workspace_bytes);
+  // chunk = nb whole proteins x all label rows when that fits, else one protein x a label range
+  long long nb_chunk = max_rows / Lrows, nl_chunk = Lrows;
+  if (nb_chunk == 0) {
+    nb_chunk = 1;
+    nl_chunk = max_rows;
+  }
+  for (long long b0 = 0; b0 < B; b0 += nb_chunk) {
+    const long long nb = B - b0 < nb_chunk ? B - b0 : nb_chunk;
+    for (long long l0 = 0; l0 < Lrows; l0 += nl_chunk) {
+      const long long nl = Lrows - l0 < nl_chunk ? Lrows - l0 : nl_chunk;
+      const long long rows = nb * nl;
+      Arena ws(workspace, workspace_bytes);
+      __half* buf_hi[2];
+      __half* buf_lo[2];
+      for (int q = 0; q < 2; ++q) {
+        buf_hi[q] = ws.at<__half>(ws.take((size_t)max_rows * ld_h * 2));
+        buf_lo[q] = ws.at<__half>(ws.take((size_t)max_rows * ld_h * 2));
+      }
+      float* partial = ws.at<float>(ws.take((size_t)max_rows * parts * 4));
+      if (!ws.ok()) return fail("scorer workspace accounting error (%zu > %zu)", ws.off, workspace_bytes);
+      int cur = 0;
+      if (c.fusion == PN_FUSION_CONCAT_PROD) {
+        // x = p * t into buffer 1, then h1 = relu(x W1x^T * s + a[b] + c[l]) into buffer 0
+        const int ld_d = (int)round_up(c.latent_dim, 64);
+        pair_product_kernel<<<ew_grid(rows * (ld_d / 8)), 256, 0, stream>>>(P_e, c.latent_dim, L_e, c.latent_dim, (int)b0,
+                                                                            (int)l0, (int)nl, rows, c.latent_dim,
+                                                                            buf_hi[1], buf_lo[1], ld_d);
+        g_launches++;
+        PN_CUDA(cudaGetLastError());
+        Planes A;
+        A.hi = buf_hi[1]; A.lo = buf_lo[1]; A.rows = rows; A.cols = c.latent_dim; A.ld = ld_d;
+        Epilogue e;
+        e.scale = pk.at<float>(L.l1_x.scale);
+        e.pair_nl = (int)nl;
+        e.add_p = a + b0 * H; e.ld_add_p = H;
+        e.add_l = c_in + l0 * H; e.ld_add_l = H;
+        e.relu = 1;
+        e.out_hi = buf_hi[0]; e.out_lo = buf_lo[0]; e.ld_split = ld_h;
+        PN_TRY(launch_gemm(A, ConvView(), weight_planes(pk, L.l1_x), H, e, mode, stream));
+      } else {
+        pair_features_kernel<<<ew_grid(rows * (ld_h / 8)), 256, 0, stream>>>(a, H, c_in, H, (int)b0, (int)l0, (int)nl, rows,
+                                                                             H, buf_hi[0], mode == PN_STRICT ? buf_lo[0] : nullptr,
+                                                                             ld_h);
+        g_launches++;
+        PN_CUDA(cudaGetLastError());
+      }
+      for (size_t j = 0; j < L.hidden.size(); ++j) {
+        const PackedLinear& pl = L.hidden[j];
+        const bool last = j + 1 == L.hidden.size();
+        Planes A;
+        A.hi = buf_hi[cur]; A.lo = buf_lo[cur]; A.rows = rows; A.cols = H; A.ld = ld_h;
+        Epilogue e;
+        e.scale = pk.at<float>(pl.scale); e.shift = pk.at<float>(pl.shift);
+        e.relu = 1;
+        if (last) {
+          e.dot_w = pk.at<float>(L.w_out);
+          e.dot_out = partial;
+        } else {
+          e.out_hi = buf_hi[cur ^ 1]; e.out_lo = buf_lo[cur ^ 1]; e.ld_split = ld_h;
+        }
+        PN_TRY(launch_gemm(A, ConvView(), weight_planes(pk, pl), H, e, mode, stream));
+        cur ^= 1;
+      }
+      finalize_logits_kernel<<<ew_grid(rows / k), 256, 0, stream>>>(partial, parts, pk.at<float>(L.b_out), (int)b0, (int)l0,
+                                                                    (int)nl, rows, k, logits, ld_logits);
+      g_launches++;
+      PN_CUDA(cudaGetLastError());
+    }
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------- plain layers
+size_t pn_linear_workspace_bytes(long long M, long long N, long long K) {
+  const long long ld = round_up(K, 64);
+  return (size_t)(round_up(M, kBM) * ld * 4 + N * ld * 4 + N * 8 + 8192);
+}
+
+int pn_linear(const float* x, long long M, long long K, long long ldx, const float* w, long long N, const float* bias,
+              float* y, long long ldy, void* workspace, size_t workspace_bytes, int mode, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (M <= 0 || N <= 0 || K <= 0) return fail("empty linear layer");
+  if (workspace_bytes < pn_linear_workspace_bytes(M, N, K)) return fail("linear workspace too small");
+  Arena ws(workspace, workspace_bytes);
+  const int ld = (int)round_up(K, 64);
+  __half* a_hi = ws.at<__half>(ws.take((size_t)M * ld * 2));
+  __half* a_lo = ws.at<__half>(ws.take((size_t)M * ld * 2));
+  PackedLinear pl = carve_linear(ws, (int)N, (int)K, 1);
+  if (!ws.ok()) return fail("linear workspace accounting error");
+  split_rows_kernel<<<ew_grid(M * (ld / 8)), 256, 0, stream>>>(x, M, (int)K, ldx, a_hi, a_lo, ld);
+  g_launches++;
+  PN_CUDA(cudaGetLastError());
+  PN_TRY(pack_linear(ws, pl, w, K, 1, 0, K, bias, nullptr, nullptr, nullptr, nullptr, 0.f, stream));
+  Planes A;
+  A.hi = a_hi; A.lo = a_lo; A.rows = M; A.cols = K; A.ld = ld;
+  Epilogue e;
+  e.scale = ws.at<float>(pl.scale); e.shift = ws.at<float>(pl.shift);
+  e.out_f32 = y; e.ld_out = ldy;
+  return launch_gemm(A, ConvView(), weight_planes(ws, pl), N, e, mode, stream);
+}
+
+size_t pn_conv1d_workspace_bytes(int batch, int T, int cin, int cout, int taps) {
+  const long long cpad = round_up(cin, 64);
+  return (size_t)((long long)batch * T * cpad * 4 + (long long)cout * cpad * taps * 4 + (long long)cout * 8 + 16384);
+}
+
+int pn_conv1d(const float* x, const int64_t* lengths, int batch, int cin, int T, const float* w, const float* bias,
+              int cout, int taps, int dilation, float* y, void* workspace, size_t workspace_bytes, int mode,
+              void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (batch <= 0 || T <= 0 || cin <= 0 || cout <= 0) return fail("empty conv");
+  if (taps < 1 || taps % 2 == 0) return fail("taps must be odd");
+  if (workspace_bytes < pn_conv1d_workspace_bytes(batch, T, cin, cout, taps)) return fail("conv workspace too small");
+  Arena ws(workspace, workspace_bytes);
+  const int cpad = (int)round_up(cin, 64);
+  const long long pos = (long long)batch * T;
+  __half* a_hi = ws.at<__half>(ws.take((size_t)pos * cpad * 2));
+  __half* a_lo = ws.at<__half>(ws.take((size_t)pos * cpad * 2));
+  PackedLinear pl = carve_linear(ws, cout, cin, taps);
+  if (!ws.ok()) return fail("conv workspace accounting error");
+  const long long* len = reinterpret_cast<const long long*>(lengths);
+  conv_input_kernel<<<ew_grid(pos), 256, 0, stream>>>(x, len, batch, cin, T, cpad, a_hi, a_lo);
+  g_launches++;
+  PN_CUDA(cudaGetLastError());
+  PN_TRY(pack_linear(ws, pl, w, (long long)cin * taps, taps, 1, (long long)cin * taps, bias, nullptr, nullptr, nullptr,
+                     nullptr, 0.f, stream));
+  Planes A;
+  A.hi = a_hi; A.lo = a_lo; A.rows = pos; A.cols = cin; A.ld = cpad;
+  ConvView cv;
+  cv.taps = taps; cv.dil = dilation; cv.T = T; cv.batch = batch; cv.cpad = pl.cpad; cv.lengths = len;
+  Epilogue e;
+  e.scale = ws.at<float>(pl.scale); e.shift = ws.at<float>(pl.shift);
+  e.out_f32 = y; e.ld_out = cout;
+  return launch_gemm(A, cv, weight_planes(ws, pl), cout, e, mode, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,243 @@
+// Element-wise / layout kernels around the tensor-core engine.  All of them are pure HBM streaming work:
+// one thread handles 8 consecutive elements of the fastest axis (two 16-byte loads, one or two 16-byte stores),
+// rows are 128-byte aligned, no shared memory is needed because nothing is re-read.
+#pragma once
+
+#include "pn_gemm.cuh"
+
+namespace pn {
+
+// ------------------------------------------------------------------------------------------------
+// weight packing (once per weight version)
+// ------------------------------------------------------------------------------------------------
+// max |w| over `rows` rows of `span` consecutive elements, row pitch `pitch`
+__global__ void absmax_kernel(const float* __restrict__ w, long long rows, long long span, long long pitch,
+                              unsigned* __restrict__ out) {
+  float m = 0.f;
+  const long long n = rows * span;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float a = fabsf(w[(i / span) * pitch + (i % span)]);
+    if (a == a) m = fmaxf(m, a);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));   // non-negative floats order like uints
+}
+
+// power-of-two scale that puts the largest |w| into [2^7, 2^8): hi AND lo fp16 planes stay normal for every
+// weight within 2^-11 of the largest one, and nothing overflows.
+__device__ __forceinline__ float weight_scale_from_absmax(unsigned bits) {
+  const float m = __uint_as_float(bits);
+  if (!(m > 0.f)) return 1.f;
+  int e;
+  frexpf(m, &e);   // m = f * 2^e, f in [0.5, 1)
+  return ldexpf(1.f, 8 - e);
+}
+
+// dst[n][tap*cpad + c] = split(w[n*sn + c*sc + tap*st] * s) ; zero elsewhere in [0, ld)
+// Linear (out,in):         taps=1, sn=in, sc=1, st=0, cin=in, cpad=ld
+// Conv1d (out,in,k):       taps=k, sn=in*k, sc=k, st=1
+__global__ void pack_weight_kernel(const float* __restrict__ w, int N, int cin, int taps, long long sn, long long sc,
+                                   long long st, int cpad, int ld, const unsigned* __restrict__ absmax,
+                                   float* __restrict__ scale_out, __half* __restrict__ hi, __half* __restrict__ lo) {
+  const float s = weight_scale_from_absmax(*absmax);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *scale_out = s;
+  const long long total = (long long)N * ld;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i / ld);
+    const int k = (int)(i % ld);
+    const int tap = k / cpad, c = k % cpad;
+    float v = 0.f;
+    if (tap < taps && c < cin) v = w[n * sn + c * sc + tap * st] * s;
+    __half h, l;
+    split_f16(v, h, l);
+    hi[i] = h;
+    lo[i] = l;
+  }
+}
+
+// Folds (conv/linear bias) + eval-mode BatchNorm + the weight scale into one per-column affine:
+//   y = (acc / s + bias - mean) * g / sqrt(var + eps) + beta  =  acc * scale + shift
+// Every pointer may be null (-> identity for that term).  BatchNorm eval: reference
+// protnote/models/protein_encoders.py:35-37,47-50 (eps 1e-3) and protnote/models/ProtNote.py:364-365 (eps 1e-5).
+__global__ void fold_affine_kernel(int n, const float* __restrict__ bias, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, const float* __restrict__ mean,
+                                   const float* __restrict__ var, float eps, const float* __restrict__ wscale,
+                                   float* __restrict__ scale, float* __restrict__ shift) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float gs = 1.f;
+  if (var) gs = 1.f / sqrtf(var[i] + eps);
+  if (gamma) gs *= gamma[i];
+  const float inv_s = wscale ? 1.f / *wscale : 1.f;
+  scale[i] = gs * inv_s;
+  shift[i] = ((bias ? bias[i] : 0.f) - (mean ? mean[i] : 0.f)) * gs + (beta ? beta[i] : 0.f);
+}
+
+// ------------------------------------------------------------------------------------------------
+// activations: fp32 -> fp16 hi/lo planes
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void split8_store(const float (&v)[8], __half* hi, __half* lo) {
+  __align__(16) __half2 h2[4];
+  __align__(16) __half2 l2[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    __half h0, l0, h1, l1;
+    split_f16(fmaxf(fminf(v[2 * j], 65504.f), -65504.f), h0, l0);
+    split_f16(fmaxf(fminf(v[2 * j + 1], 65504.f), -65504.f), h1, l1);
+    h2[j] = __halves2half2(h0, h1);
+    l2[j] = __halves2half2(l0, l1);
+  }
+  *reinterpret_cast<uint4*>(hi) = *reinterpret_cast<const uint4*>(h2);
+  if (lo) *reinterpret_cast<uint4*>(lo) = *reinterpret_cast<const uint4*>(l2);
+}
+
+// x [M][ldx] fp32 -> hi/lo [M][ld] (ld multiple of 8, columns >= K zero-filled)
+__global__ void split_rows_kernel(const float* __restrict__ x, long long M, int K, long long ldx,
+                                  __half* __restrict__ hi, __half* __restrict__ lo, int ld) {
+  const int chunks = ld / 8;
+  const long long total = M * chunks;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long m = i / chunks;
+    const int k0 = (int)(i % chunks) * 8;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (k0 + j < K) ? x[m * ldx + k0 + j] : 0.f;
+    split8_store(v, hi + m * ld + k0, lo ? lo + m * ld + k0 : nullptr);
+  }
+}
+
+// Sequence input [B][Cin][T] fp32 (reference layout, collators.py:123-133) -> channels-last [B][T][cpad] planes,
+// with positions >= length zeroed (MaskedConv1D masks its input, protein_encoders.py:14).
+__global__ void conv_input_kernel(const float* __restrict__ x, const long long* __restrict__ lengths, int B, int cin,
+                                  int T, int cpad, __half* __restrict__ hi, __half* __restrict__ lo) {
+  const long long total = (long long)B * T;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / T);
+    const int t = (int)(i % T);
+    const bool valid = (long long)t < lengths[b];
+    for (int c0 = 0; c0 < cpad; c0 += 8) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = c0 + j;
+        v[j] = (valid && c < cin) ? x[((long long)b * cin + c) * T + t] : 0.f;   // coalesced over t per channel
+      }
+      split8_store(v, hi + i * cpad + c0, lo ? lo + i * cpad + c0 : nullptr);
+    }
+  }
+}
+
+// Layer 1 of the pair scorer after the exact split of Linear(2d -> H) over [p; t]
+// (reference protnote/models/ProtNote.py:112-126,293 materialises [B*L, 2d]; here it never exists):
+//   h1[(b,l)][k] = relu(a[b][k] + c[l][k])      a = BN1-folded protein half, c = BN1-scaled label half
+// rows of the chunk are pairs (b0 + r / nl, l0 + r % nl); output fp16 planes [nb*nl][ld].
+__global__ void pair_features_kernel(const float* __restrict__ a, long long lda, const float* __restrict__ c,
+                                     long long ldc, int b0, int l0, int nl, long long rows, int H,
+                                     __half* __restrict__ hi, __half* __restrict__ lo, int ld) {
+  const int chunks = ld / 8;
+  const long long total = rows * chunks;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / chunks;
+    const int k0 = (int)(i % chunks) * 8;
+    const float* ap = a + (b0 + r / nl) * lda + k0;
+    const float* cp = c + (l0 + r % nl) * ldc + k0;
+    float v[8];
+    if (k0 + 8 <= H && ((lda | ldc) & 3) == 0) {
+      const float4 a0 = *reinterpret_cast<const float4*>(ap), a1 = *reinterpret_cast<const float4*>(ap + 4);
+      const float4 c0 = *reinterpret_cast<const float4*>(cp), c1 = *reinterpret_cast<const float4*>(cp + 4);
+      v[0] = a0.x + c0.x; v[1] = a0.y + c0.y; v[2] = a0.z + c0.z; v[3] = a0.w + c0.w;
+      v[4] = a1.x + c1.x; v[5] = a1.y + c1.y; v[6] = a1.z + c1.z; v[7] = a1.w + c1.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = (k0 + j < H) ? ap[j] + cp[j] : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+    split8_store(v, hi + r * ld + k0, lo ? lo + r * ld + k0 : nullptr);
+  }
+}
+
+// [p * t] block of the concatenation_prod fusion (ProtNote.py:139-150): x[(b,l)][k] = P_e[b][k] * L_e[l][k]
+__global__ void pair_product_kernel(const float* __restrict__ p, long long ldp, const float* __restrict__ t,
+                                    long long ldt, int b0, int l0, int nl, long long rows, int D,
+                                    __half* __restrict__ hi, __half* __restrict__ lo, int ld) {
+  const int chunks = ld / 8;
+  const long long total = rows * chunks;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / chunks;
+    const int k0 = (int)(i % chunks) * 8;
+    const float* pp = p + (b0 + r / nl) * ldp + k0;
+    const float* tp = t + (l0 + r % nl) * ldt + k0;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (k0 + j < D) ? pp[j] * tp[j] : 0.f;
+    split8_store(v, hi + r * ld + k0, lo ? lo + r * ld + k0 : nullptr);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// reductions at the two ends of the path
+// ------------------------------------------------------------------------------------------------
+// Masked mean pool (protein_encoders.py:114-117): out[b][c] = sum_{t < len[b]} x[b][t][c] / len[b].
+// grid (ceil(C/32), B), block (32, 8): lanes span channels (coalesced), the 8 rows stride over t.
+__global__ void pool_mean_kernel(const float* __restrict__ x, long long ldx, const long long* __restrict__ lengths,
+                                 int T, int C, float* __restrict__ out, long long ldo) {
+  __shared__ float part[8][33];
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  long long len = lengths[b];
+  const int n = (int)(len < T ? len : T);
+  float s = 0.f;
+  if (c < C)
+    for (int t = threadIdx.y; t < n; t += 8) s += x[((long long)b * T + t) * ldx + c];
+  part[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float tot = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) tot += part[j][threadIdx.x];
+    out[(long long)b * ldo + c] = tot / (float)len;
+  }
+}
+
+// logits = sum of the per-N-tile partial dots + output bias; k consecutive description rows of one label are
+// ensembled in probability space, logit(mean_k sigmoid(x), eps=1e-7)  (ProtNote.py:308-322).
+// partial rows are the chunk's pairs (b0 + r / nl, l0 + r % nl); nl and l0 are multiples of k.
+__global__ void finalize_logits_kernel(const float* __restrict__ partial, int parts, const float* __restrict__ bias,
+                                       int b0, int l0, int nl, long long rows, int k, float* __restrict__ logits,
+                                       long long ld_logits) {
+  const long long groups = rows / k;
+  for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < groups;
+       g += (long long)gridDim.x * blockDim.x) {
+    const long long r0 = g * k;
+    const long long b = b0 + r0 / nl;
+    const long long l = (l0 + r0 % nl) / k;
+    float acc = 0.f;
+    for (int j = 0; j < k; ++j) {
+      const float* pp = partial + (r0 + j) * parts;
+      float x = 0.f;
+      for (int q = 0; q < parts; ++q) x += pp[q];
+      x += bias ? *bias : 0.f;
+      if (k == 1) {
+        acc = x;
+      } else {
+        acc += 1.f / (1.f + expf(-x));
+      }
+    }
+    if (k > 1) {
+      float pm = acc / (float)k;
+      const float lo = 1e-7f, hi = 1.f - 1e-7f;
+      pm = fminf(fmaxf(pm, lo), hi);
+      acc = logf(pm / (1.f - pm));
+    }
+    logits[b * ld_logits + l] = acc;
+  }
+}
+
+}  // namespace pn

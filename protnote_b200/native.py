@@ -1,0 +1,219 @@
+"""Thin torch-tensor wrappers over the C ABI (include/protnote_b200.h).
+
+PyTorch is used here for exactly three things: owning device memory (torch.empty), naming the current CUDA stream,
+and handing data pointers to the library.  No arithmetic on tensor data happens in this file.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import PN_FAST, PN_STRICT, EncoderCfg, ScorerCfg, check, pointer_array, ptr, stream_ptr
+
+MODES = {"strict": PN_STRICT, "fast": PN_FAST}
+
+# scratch memory is cached per (device, purpose) and only ever grows: the caching allocator would do the same,
+# but keeping one buffer makes the pointers stable for CUDA-graph capture.
+_scratch = {}
+
+
+def scratch(device: torch.device, key: str, nbytes: int) -> torch.Tensor:
+    k = (device.index, key)
+    buf = _scratch.get(k)
+    if buf is None or buf.numel() < nbytes:
+        buf = None
+        _scratch.pop(k, None)
+        buf = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        _scratch[k] = buf
+    return buf
+
+
+def release_scratch():
+    _scratch.clear()
+
+
+def _require_cuda(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise _lib.ProtnoteB200Error(
+            f"{name} is on {t.device}: protnote_b200 computes on a CUDA sm_100a device only (no CPU path)")
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def set_option(name: str, value: int):
+    check(_lib.load().pn_set_option(name.encode(), int(value)))
+
+
+def launch_count() -> int:
+    return int(_lib.load().pn_launch_count())
+
+
+class PackedEncoder:
+    """Device-resident packed weights of one ProteInfer encoder + the forward call."""
+
+    def __init__(self, input_channels: int, channels: int, bottleneck: int, kernel_size: int, dilation_base: int,
+                 num_blocks: int, bn_eps: float = 1e-3):
+        self.lib = _lib.load()
+        self.cfg = EncoderCfg(input_channels, channels, bottleneck, kernel_size, dilation_base, num_blocks, bn_eps)
+        self.packed: Optional[torch.Tensor] = None
+
+    def pack(self, params: Sequence[torch.Tensor]):
+        """params: fp32 CUDA tensors in the order include/protnote_b200.h documents for pn_encoder_pack."""
+        dev = params[0].device
+        for p in params:
+            _require_cuda(p, "encoder parameter")
+        keep = [_f32c(p.detach()) for p in params]
+        nbytes = self.lib.pn_encoder_packed_bytes(C.byref(self.cfg))
+        if nbytes == 0:
+            check(1)
+        if self.packed is None or self.packed.numel() < nbytes or self.packed.device != dev:
+            self.packed = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            check(self.lib.pn_encoder_pack(C.byref(self.cfg), pointer_array(keep), len(keep), ptr(self.packed),
+                                           self.packed.numel(), stream_ptr()))
+        del keep  # stream-ordered: the caching allocator keeps the memory alive until the kernels have run
+
+    def forward(self, x: torch.Tensor, lengths: torch.Tensor, mode: int = PN_STRICT,
+                max_workspace_bytes: int = 6 << 30) -> torch.Tensor:
+        if self.packed is None:
+            raise _lib.ProtnoteB200Error("encoder weights have not been packed")
+        _require_cuda(x, "sequence_onehots")
+        dev = self.packed.device
+        x = _f32c(x)
+        lengths = lengths.to(device=dev, dtype=torch.int64).contiguous()
+        B, cin, T = x.shape
+        if cin != self.cfg.input_channels:
+            raise ValueError(f"expected {self.cfg.input_channels} input channels, got {cin}")
+        out = torch.empty(B, self.cfg.channels, dtype=torch.float32, device=dev)
+        if B == 0:
+            return out
+        need = self.lib.pn_encoder_workspace_bytes(C.byref(self.cfg), B, T)
+        one = self.lib.pn_encoder_workspace_bytes(C.byref(self.cfg), 1, T) + 4096
+        ws = scratch(dev, "encoder", max(min(need + 4096 * B, max_workspace_bytes), one))
+        with torch.cuda.device(dev):
+            check(self.lib.pn_encoder_forward(C.byref(self.cfg), ptr(self.packed), ptr(x), ptr(lengths), B, T, ptr(out),
+                                              ptr(ws), ws.numel(), mode, stream_ptr()))
+        return out
+
+
+class PackedScorer:
+    """Device-resident packed weights of W_p, W_l and the output MLP + the three calls of the scorer."""
+
+    def __init__(self, protein_dim: int, label_dim: int, latent_dim: int, proj_hidden: int, proj_layers: int,
+                 out_hidden: int, out_layers: int, out_batchnorm: bool, fusion: str, descriptions_per_label: int,
+                 bn_eps: float = 1e-5):
+        self.lib = _lib.load()
+        if fusion not in _lib.FUSIONS:
+            raise ValueError(f"feature fusion '{fusion}' is not handled by the fused pair scorer")
+        self.cfg = ScorerCfg(protein_dim, label_dim, latent_dim, proj_hidden, proj_layers, out_hidden, out_layers,
+                             int(bool(out_batchnorm)), _lib.FUSIONS[fusion], descriptions_per_label, bn_eps)
+        self.packed: Optional[torch.Tensor] = None
+
+    def num_params(self) -> int:
+        n = self.lib.pn_scorer_num_params(C.byref(self.cfg))
+        if n < 0:
+            check(1)
+        return n
+
+    def pack(self, params: Sequence[torch.Tensor]):
+        dev = params[0].device
+        for p in params:
+            _require_cuda(p, "scorer parameter")
+        keep = [_f32c(p.detach()) for p in params]
+        nbytes = self.lib.pn_scorer_packed_bytes(C.byref(self.cfg))
+        if nbytes == 0:
+            check(1)
+        if self.packed is None or self.packed.numel() < nbytes or self.packed.device != dev:
+            self.packed = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            check(self.lib.pn_scorer_pack(C.byref(self.cfg), pointer_array(keep), len(keep), ptr(self.packed),
+                                          self.packed.numel(), stream_ptr()))
+        del keep
+
+    def _project(self, fn, x: torch.Tensor, want_embedding: bool, mode: int):
+        dev = self.packed.device
+        x = _f32c(x)
+        n = x.shape[0]
+        emb = torch.empty(n, self.cfg.latent_dim, dtype=torch.float32, device=dev) if want_embedding else None
+        half = torch.empty(n, self.cfg.out_hidden, dtype=torch.float32, device=dev)
+        if n == 0:
+            return emb, half
+        rows = min(n, 1 << 15)
+        ws = scratch(dev, "project", self.lib.pn_project_workspace_bytes(C.byref(self.cfg), rows))
+        with torch.cuda.device(dev):
+            check(fn(C.byref(self.cfg), ptr(self.packed), ptr(x), n, ptr(emb), ptr(half), ptr(ws), ws.numel(), mode,
+                     stream_ptr()))
+        return emb, half
+
+    def project_sequences(self, P_f: torch.Tensor, mode: int = PN_STRICT, want_embedding: bool = False):
+        """P_f [n, protein_dim] -> (P_e [n, latent] or None, a [n, out_hidden])"""
+        _require_cuda(P_f, "sequence embeddings")
+        return self._project(self.lib.pn_project_sequences, P_f, want_embedding, mode)
+
+    def project_labels(self, L_f: torch.Tensor, mode: int = PN_STRICT, want_embedding: bool = False):
+        """L_f [n, label_dim] -> (L_e [n, latent] or None, c [n, out_hidden])"""
+        _require_cuda(L_f, "label embeddings")
+        return self._project(self.lib.pn_project_labels, L_f, want_embedding, mode)
+
+    def score(self, a: torch.Tensor, c: torch.Tensor, P_e: Optional[torch.Tensor] = None,
+              L_e: Optional[torch.Tensor] = None, mode: int = PN_STRICT, out: Optional[torch.Tensor] = None,
+              max_workspace_bytes: int = 8 << 30) -> torch.Tensor:
+        """a [B, H], c [L, H] -> logits [B, L / k] fp32"""
+        dev = self.packed.device
+        B, L = a.shape[0], c.shape[0]
+        k = self.cfg.descriptions_per_label
+        if L % k != 0:
+            raise ValueError(f"{L} label rows is not a multiple of inference_descriptions_per_label={k}")
+        if out is None:
+            out = torch.empty(B, L // k, dtype=torch.float32, device=dev)
+        if B == 0 or L == 0:
+            return out
+        need = self.lib.pn_scorer_workspace_bytes(C.byref(self.cfg), B, L)
+        floor = self.lib.pn_scorer_min_workspace_bytes(C.byref(self.cfg))
+        ws = scratch(dev, "scorer", max(min(need, max_workspace_bytes), floor))
+        with torch.cuda.device(dev):
+            check(self.lib.pn_score_pairs(C.byref(self.cfg), ptr(self.packed), ptr(a), ptr(c), ptr(P_e), ptr(L_e), B, L,
+                                          ptr(out), out.stride(0), ptr(ws), ws.numel(), mode, stream_ptr()))
+        return out
+
+
+def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], mode: int = PN_STRICT) -> torch.Tensor:
+    """y = x w^T + bias on the tensor-core engine (ProteInfer.output_layer, protein_encoders.py:120-123)."""
+    lib = _lib.load()
+    _require_cuda(x, "input")
+    x, w = _f32c(x), _f32c(w.detach())
+    b = _f32c(bias.detach()) if bias is not None else None
+    M, K = x.shape
+    N = w.shape[0]
+    y = torch.empty(M, N, dtype=torch.float32, device=x.device)
+    if M == 0:
+        return y
+    ws = scratch(x.device, "linear", lib.pn_linear_workspace_bytes(M, N, K))
+    with torch.cuda.device(x.device):
+        check(lib.pn_linear(ptr(x), M, K, K, ptr(w), N, ptr(b), ptr(y), N, ptr(ws), ws.numel(), mode, stream_ptr()))
+    return y
+
+
+def conv1d_channels_last(x: torch.Tensor, lengths: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor],
+                         dilation: int, mode: int = PN_STRICT) -> torch.Tensor:
+    """Masked 'same' Conv1d (MaskedConv1D, protein_encoders.py:8-17): x [B,Cin,T] -> y [B,T,Cout]."""
+    lib = _lib.load()
+    _require_cuda(x, "input")
+    x, w = _f32c(x), _f32c(w.detach())
+    b = _f32c(bias.detach()) if bias is not None else None
+    lengths = lengths.to(device=x.device, dtype=torch.int64).contiguous()
+    B, cin, T = x.shape
+    cout, _, taps = w.shape
+    y = torch.empty(B, T, cout, dtype=torch.float32, device=x.device)
+    ws = scratch(x.device, "conv1d", lib.pn_conv1d_workspace_bytes(B, T, cin, cout, taps))
+    with torch.cuda.device(x.device):
+        check(lib.pn_conv1d(ptr(x), ptr(lengths), B, cin, T, ptr(w), ptr(b), cout, taps, dilation, ptr(y), ptr(ws),
+                            ws.numel(), mode, stream_ptr()))
+    return y

@@ -1,0 +1,126 @@
+"""B200-native mirror of the reference's `protnote/models/protein_encoders.py`.
+
+Same class names, constructor arguments, parameter names / registration order and call signatures as the reference
+(protein_encoders.py:8-153), so `state_dict()`, `load_state_dict(strict=True)`, `transfer_tf_weights_to_torch`
+(protnote/utils/proteinfer.py:7-41, positional) and every caller (`bin/main.py:383-405`,
+`bin/test_proteinfer.py:221-303`, `ProtNote.forward`) work unchanged.  The parameters live in ordinary torch modules;
+the arithmetic of `get_embeddings` / `forward` runs in the sm_100a library (csrc/) through the C ABI.  There is no
+PyTorch or CPU implementation of the forward pass in this file.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import native
+from ._lib import ProtnoteB200Error
+
+
+def _versions(tensors):
+    return tuple((t.data_ptr(), t._version, tuple(t.shape), t.device.index) for t in tensors)
+
+
+class MaskedConv1D(torch.nn.Conv1d):
+    """Parameter holder + single-layer entry point.  Reference: protein_encoders.py:8-17
+    (mask input, Conv1d(padding='same'), mask output)."""
+
+    def forward(self, x, sequence_lengths):
+        if isinstance(self.padding, str) and self.padding != "same":
+            raise ProtnoteB200Error("MaskedConv1D supports padding='same' only")
+        y = native.conv1d_channels_last(x, sequence_lengths, self.weight, self.bias, self.dilation[0])
+        return y.permute(0, 2, 1)   # a [B, C, T] view of the channels-last result
+
+
+class Residual(torch.nn.Module):
+    """ResNet-v2 pre-activation bottleneck block (protein_encoders.py:23-67).  Holds parameters only; the block is
+    executed as part of ProteInfer.get_embeddings (two tensor-core kernels with BatchNorm/ReLU/mask/residual fused)."""
+
+    def __init__(self, input_channels: int, kernel_size: int, dilation: int, bottleneck_factor: float,
+                 activation=torch.nn.ReLU):
+        super().__init__()
+        if activation is not torch.nn.ReLU:
+            raise ProtnoteB200Error("the fused encoder kernels implement ReLU activations only")
+        bottleneck_out_channels = int(math.floor(input_channels * bottleneck_factor))
+        self.bn_activation_1 = torch.nn.Sequential(
+            torch.nn.BatchNorm1d(input_channels, eps=0.001, momentum=0.01), activation())
+        self.masked_conv1 = MaskedConv1D(in_channels=input_channels, out_channels=bottleneck_out_channels,
+                                         padding="same", kernel_size=kernel_size, stride=1, dilation=dilation)
+        self.bn_activation_2 = torch.nn.Sequential(
+            torch.nn.BatchNorm1d(bottleneck_out_channels, eps=0.001, momentum=0.01), activation())
+        self.masked_conv2 = MaskedConv1D(in_channels=bottleneck_out_channels, out_channels=input_channels,
+                                         padding="same", kernel_size=1, stride=1, dilation=1)
+
+    def forward(self, x, sequence_lengths):
+        raise ProtnoteB200Error("Residual blocks run fused inside ProteInfer.get_embeddings; "
+                                "there is no stand-alone PyTorch forward")
+
+
+class ProteInfer(torch.nn.Module):
+    """protein_encoders.py:70-153.  `precision`: 'strict' (fp32-grade, default) or 'fast' (fp16 operands)."""
+
+    def __init__(self, num_labels: int, input_channels: int, output_channels: int, kernel_size: int, activation,
+                 dilation_base: int, num_resnet_blocks: int, bottleneck_factor: float, precision: str = "strict"):
+        super().__init__()
+        self.conv1 = MaskedConv1D(in_channels=input_channels, out_channels=output_channels, padding="same",
+                                  kernel_size=kernel_size, stride=1, dilation=1)
+        self.resnet_blocks = torch.nn.ModuleList()
+        for i in range(num_resnet_blocks):
+            self.resnet_blocks.append(Residual(input_channels=output_channels, kernel_size=kernel_size,
+                                               dilation=dilation_base ** i, bottleneck_factor=bottleneck_factor,
+                                               activation=activation))
+        self.output_layer = torch.nn.Linear(in_features=output_channels, out_features=num_labels)
+        self.precision = precision
+        self._dilation_base = dilation_base
+        self._packed = None
+        self._packed_key = None
+
+    # ------------------------------------------------------------------ packed-weight cache
+    def _pack_sources(self):
+        srcs = [self.conv1.weight, self.conv1.bias]
+        for blk in self.resnet_blocks:
+            bn1, bn2 = blk.bn_activation_1[0], blk.bn_activation_2[0]
+            srcs += [bn1.weight, bn1.bias, bn1.running_mean, bn1.running_var,
+                     blk.masked_conv1.weight, blk.masked_conv1.bias,
+                     bn2.weight, bn2.bias, bn2.running_mean, bn2.running_var,
+                     blk.masked_conv2.weight, blk.masked_conv2.bias]
+        return srcs
+
+    def _ensure_packed(self):
+        srcs = self._pack_sources()
+        key = _versions(srcs)
+        if self._packed is None or key != self._packed_key:
+            bottleneck = self.resnet_blocks[0].masked_conv1.out_channels if len(self.resnet_blocks) else 1
+            enc = native.PackedEncoder(self.conv1.in_channels, self.conv1.out_channels, bottleneck,
+                                       self.conv1.kernel_size[0], self._dilation_base, len(self.resnet_blocks),
+                                       bn_eps=self.resnet_blocks[0].bn_activation_1[0].eps if len(self.resnet_blocks) else 1e-3)
+            enc.pack(srcs)
+            self._packed, self._packed_key = enc, key
+        return self._packed
+
+    # ------------------------------------------------------------------ reference interface
+    def get_embeddings(self, x, sequence_lengths):
+        """[B, Cin, T] float + [B] lengths -> [B, C] masked mean of the residual stream (protein_encoders.py:109-118)."""
+        if self.training:
+            raise ProtnoteB200Error("the sm_100a encoder implements eval-mode BatchNorm only (the reference freezes the "
+                                    "sequence encoder: TRAIN_SEQUENCE_ENCODER False, base_config.yaml:71); call .eval()")
+        dev = self.conv1.weight.device
+        x = x.to(dev, non_blocking=True)
+        sequence_lengths = sequence_lengths.to(dev, non_blocking=True)
+        return self._ensure_packed().forward(x, sequence_lengths, native.MODES[self.precision])
+
+    def forward(self, x, sequence_lengths):
+        features = self.get_embeddings(x, sequence_lengths)
+        return native.linear(features, self.output_layer.weight, self.output_layer.bias, native.MODES[self.precision])
+
+    @classmethod
+    def from_pretrained(cls, weights_path: str, num_labels: int, input_channels: int, output_channels: int,
+                        kernel_size: int, activation, dilation_base: int, num_resnet_blocks: int,
+                        bottleneck_factor: float):
+        """protein_encoders.py:125-153.  The TF->torch weight transfer is the reference's own utility
+        (protnote/utils/proteinfer.py:7-41); it zips TF variables onto state_dict() order, which this class preserves."""
+        model = cls(num_labels, input_channels, output_channels, kernel_size, activation, dilation_base,
+                    num_resnet_blocks, bottleneck_factor)
+        from protnote.utils.proteinfer import transfer_tf_weights_to_torch  # reference package (caller's environment)
+        transfer_tf_weights_to_torch(model, weights_path)
+        return model

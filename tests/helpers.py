@@ -49,3 +49,29 @@ def topk_agree(ref: torch.Tensor, got: torch.Tensor, k: int, tol: float) -> bool
     ok_rank[:, :gaps.shape[1]] &= gaps > 2 * tol
     ok_rank[:, 1:gaps.shape[1] + 1] &= (gaps > 2 * tol)[:, :ok_rank.shape[1] - 1]
     return bool(((ri == gi) | ~ok_rank).all())
+
+
+def build_b200_model(ecfg, scfg, sd, device="cuda", precision="strict"):
+    """protnote_b200 modules built exactly the way bin/main.py:383-446 builds the reference's, strict-loaded with `sd`."""
+    from protnote_b200.ProtNote import ProtNote
+    from protnote_b200.protein_encoders import ProteInfer
+    enc = ProteInfer(num_labels=sd["sequence_encoder.output_layer.weight"].shape[0],
+                     input_channels=ecfg.input_channels, output_channels=ecfg.output_channels,
+                     kernel_size=ecfg.kernel_size, activation=torch.nn.ReLU, dilation_base=ecfg.dilation_base,
+                     num_resnet_blocks=ecfg.num_resnet_blocks, bottleneck_factor=ecfg.bottleneck_factor,
+                     precision=precision)
+    model = ProtNote(protein_embedding_dim=scfg.protein_embedding_dim, label_embedding_dim=scfg.label_embedding_dim,
+                     latent_dim=scfg.latent_dim, label_embedding_pooling_method="mean", label_encoder=None,
+                     sequence_encoder=enc,
+                     inference_descriptions_per_label=scfg.inference_descriptions_per_label,
+                     output_mlp_hidden_dim_scale_factor=scfg.output_mlp_hidden_dim_scale_factor,
+                     output_mlp_num_layers=scfg.output_mlp_num_layers,
+                     outout_mlp_add_batchnorm=scfg.output_mlp_batchnorm,
+                     projection_head_num_layers=scfg.projection_head_num_layers,
+                     projection_head_hidden_dim_scale_factor=scfg.projection_head_hidden_dim_scale_factor,
+                     label_encoder_num_trainable_layers=0, train_sequence_encoder=False,
+                     sequence_embedding_dropout=scfg.sequence_embedding_dropout,
+                     label_embedding_dropout=scfg.label_embedding_dropout,
+                     feature_fusion=scfg.feature_fusion, temperature=scfg.temperature, precision=precision)
+    model.load_state_dict(sd, strict=True)
+    return model.to(device).eval()

@@ -23,8 +23,16 @@ def test_fresh_inputs_match_reference(name):
         ref_logits, _ = model(sequence_onehots=onehots, sequence_lengths=lengths, label_embeddings=labels)
         emb = proteinfer_embeddings(sd, onehots, lengths, ecfg, "sequence_encoder.")
         logits = protnote_forward(sd, onehots, lengths, labels, ecfg, scfg)
-    assert (emb - ref_emb).abs().max() < 2e-5
-    assert (logits - ref_logits).abs().max() < 2e-5
+    # fp32 vs fp32: same operators, different association order -> agreement to the fp32 noise floor
+    assert (emb - ref_emb).abs().max() < 2e-6
+    assert (logits - ref_logits).abs().max() < 1e-4
+    # fp64 vs fp64: the algorithm itself is pinned to ~1e-12
+    model = model.double()
+    with torch.no_grad():
+        ref64, _ = model(sequence_onehots=onehots.double(), sequence_lengths=lengths,
+                         label_embeddings=labels.double())
+        got64 = protnote_forward(sd, onehots, lengths, labels, ecfg, scfg, dtype=torch.float64)
+    assert (got64 - ref64).abs().max() < 1e-9
 
 
 def test_non_onehot_float_input_and_similarity_fusion():
@@ -39,4 +47,4 @@ def test_non_onehot_float_input_and_similarity_fusion():
     with torch.no_grad():
         ref_logits, _ = model(sequence_onehots=x, sequence_lengths=lengths, label_embeddings=labels)
         logits = protnote_forward(sd, x, lengths, labels, ecfg, scfg)
-    assert (logits - ref_logits).abs().max() < 2e-5
+    assert (logits - ref_logits).abs().max() < 1e-4
