@@ -37,7 +37,9 @@ int pn_version(void);
 const char* pn_last_error(void);
 /* 0 if `device` is a compute-capability 10.x GPU this library can run on. */
 int pn_device_check(int device);
-/* Engine knobs: "bk" = 32 | 64 (k-block / swizzle width), "chunk_rows" (pairs per scorer chunk, 0 = auto). */
+/* Engine knobs: "bk" = 32 | 64 (k-block / swizzle width, 0 = auto); "promote_k_encoder" | "promote_k_heads" |
+ * "promote_k_scorer" | "promote_k" (all): strict mode, K elements summed in TMEM between fp32 promotions
+ * (0 = never); "chunk_rows" (pairs per scorer chunk, 0 = auto). */
 int pn_set_option(const char* name, long long value);
 /* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
 long long pn_launch_count(void);

@@ -77,12 +77,12 @@ class ScorerCfg:
 
 def pad_mask(lengths: Tensor, T: int) -> Tensor:
     """True where position >= length.  protnote/data/datasets.py:559-563."""
-    return torch.arange(T)[None, :] >= lengths.reshape(-1, 1)
+    return torch.arange(T, device=lengths.device)[None, :] >= lengths.reshape(-1, 1)
 
 
 def zero_padding(x: Tensor, lengths: Tensor) -> Tensor:
     """set_padding_to_sentinel(x, lengths, 0) - protnote/data/datasets.py:535-569."""
-    return torch.where(pad_mask(lengths, x.shape[-1])[:, None, :], torch.zeros((), dtype=x.dtype), x)
+    return torch.where(pad_mask(lengths, x.shape[-1])[:, None, :], torch.zeros((), dtype=x.dtype, device=x.device), x)
 
 
 def masked_conv(x: Tensor, lengths: Tensor, w: Tensor, b: Tensor, dilation: int) -> Tensor:

@@ -20,6 +20,9 @@ thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
 int g_bk_option = 0;             // 0 = auto (strict: 32, fast: 64)
 long long g_chunk_rows = 0;      // 0 = auto
+// strict mode: K elements accumulated in TMEM between fp32 promotions, per stage of the path
+enum { kStageEncoder = 0, kStageHeads = 1, kStageScorer = 2, kStageOther = 3 };
+int g_promote_k[4] = {32, 32, 256, 64};
 
 int fail(const char* fmt, ...) {
   char buf[1024];
@@ -163,7 +166,7 @@ int launch_gemm_t(const GemmParams& p, cudaStream_t stream) {
 
 // D = A * B^T with the fused epilogue.  A: plain [M][K] or conv view; B: packed weights [N][K_total].
 int launch_gemm(const Planes& A, const ConvView& cv, const Planes& B, long long N, const Epilogue& e, int mode,
-                cudaStream_t stream) {
+                cudaStream_t stream, int stage_kind = kStageOther) {
   if (mode != PN_STRICT && mode != PN_FAST) return fail("mode must be PN_STRICT or PN_FAST");
   const int bk = pick_bk(mode);
   GemmParams p;
@@ -201,6 +204,12 @@ int launch_gemm(const Planes& A, const ConvView& cv, const Planes& B, long long 
     if (need_lo) PN_TRY(make_map(&p.tm_a_lo, A.lo, 2, dims, strides, box, bk * 2));
   }
   if (A.rows >= (1LL << 31) || p.tiles_m <= 0 || p.num_kblocks <= 0) return fail("bad GEMM shape");
+  p.chunk_kblocks = p.num_kblocks;
+  const int promote_k = g_promote_k[stage_kind];
+  if (mode == PN_STRICT && promote_k > 0) {
+    p.chunk_kblocks = promote_k / bk > 0 ? promote_k / bk : 1;
+    if (p.chunk_kblocks > p.num_kblocks) p.chunk_kblocks = p.num_kblocks;
+  }
   {
     const cuuint64_t dims[2] = {(cuuint64_t)B.cols, (cuuint64_t)B.rows};
     const cuuint64_t strides[1] = {(cuuint64_t)B.ld * 2};
@@ -473,7 +482,7 @@ int run_projection(const pn_scorer_cfg& c, const ScorerLayout& L, const Arena& p
         e.out_f32 = emb_out + r0 * c.latent_dim;
         e.ld_out = c.latent_dim;
       }
-      PN_TRY(launch_gemm(A, ConvView(), weight_planes(pk, pl), pl.N, e, mode, stream));
+      PN_TRY(launch_gemm(A, ConvView(), weight_planes(pk, pl), pl.N, e, mode, stream, kStageHeads));
       A.hi = buf_hi[cur]; A.lo = buf_lo[cur]; A.rows = rows; A.cols = pl.N; A.ld = ld_h;
       cur ^= 1;
     }
@@ -484,14 +493,14 @@ int run_projection(const pn_scorer_cfg& c, const ScorerLayout& L, const Arena& p
     e.shift = protein ? pk.at<float>(L.l1_shift) : nullptr;
     e.out_f32 = half_out + r0 * c.out_hidden;
     e.ld_out = c.out_hidden;
-    PN_TRY(launch_gemm(A, ConvView(), weight_planes(pk, pl), pl.N, e, mode, stream));
+    PN_TRY(launch_gemm(A, ConvView(), weight_planes(pk, pl), pl.N, e, mode, stream, kStageHeads));
   }
   return 0;
 }
 
 size_t scorer_row_bytes(const pn_scorer_cfg& c) {
   const size_t ld_h = (size_t)round_up(c.out_hidden, 64);
-  return ld_h * 2 /*bytes*/ * 2 /*planes*/ * 2 /*ping-pong*/ + (size_t)tiles_n_for(c.out_hidden) * 4;
+  return ld_h * 2 /*bytes*/ * 2 /*planes*/ * 2 /*ping-pong*/ + (size_t)tiles_n_for(c.out_hidden) * 2 * 4;
 }
 
 }  // namespace
@@ -519,6 +528,22 @@ int pn_set_option(const char* name, long long value) {
   if (strcmp(name, "bk") == 0) {
     if (value != 0 && value != 32 && value != 64) return fail("bk must be 0, 32 or 64");
     g_bk_option = (int)value;
+    return 0;
+  }
+  if (strncmp(name, "promote_k", 9) == 0) {
+    if (value < 0) return fail("promote_k must be >= 0 (0 = never promote)");
+    const char* which = name + 9;
+    if (*which == 0) {
+      for (int i = 0; i < 4; ++i) g_promote_k[i] = (int)value;
+    } else if (strcmp(which, "_encoder") == 0) {
+      g_promote_k[kStageEncoder] = (int)value;
+    } else if (strcmp(which, "_heads") == 0) {
+      g_promote_k[kStageHeads] = (int)value;
+    } else if (strcmp(which, "_scorer") == 0) {
+      g_promote_k[kStageScorer] = (int)value;
+    } else {
+      return fail("unknown option '%s'", name);
+    }
     return 0;
   }
   if (strcmp(name, "chunk_rows") == 0) {
@@ -615,7 +640,7 @@ int pn_encoder_forward(const pn_encoder_cfg* cfg, const void* packed, const floa
         e.relu = 1;
         e.out_hi = ws.at<__half>(W.act_hi); e.out_lo = ws.at<__half>(W.act_lo); e.ld_split = W.ldc;
       }
-      PN_TRY(launch_gemm(A, cv, weight_planes(pk, L.conv1), c.channels, e, mode, stream));
+      PN_TRY(launch_gemm(A, cv, weight_planes(pk, L.conv1), c.channels, e, mode, stream, kStageEncoder));
     }
     long long dil = 1;
     for (int i = 0; i < c.num_blocks; ++i) {
@@ -629,7 +654,7 @@ int pn_encoder_forward(const pn_encoder_cfg* cfg, const void* packed, const floa
         e.scale = pk.at<float>(b.conv_d.scale); e.shift = pk.at<float>(b.conv_d.shift);
         e.relu = 1;
         e.out_hi = ws.at<__half>(W.hid_hi); e.out_lo = ws.at<__half>(W.hid_lo); e.ld_split = W.ldb;
-        PN_TRY(launch_gemm(A, cv, weight_planes(pk, b.conv_d), c.bottleneck, e, mode, stream));
+        PN_TRY(launch_gemm(A, cv, weight_planes(pk, b.conv_d), c.bottleneck, e, mode, stream, kStageEncoder));
       }
       {   // x = x + mask(conv1x1(hid) + bias); act = mask(relu(bn1_{i+1}(x)))
         Planes A;
@@ -645,7 +670,7 @@ int pn_encoder_forward(const pn_encoder_cfg* cfg, const void* packed, const floa
           e.relu = 1;
           e.out_hi = ws.at<__half>(W.act_hi); e.out_lo = ws.at<__half>(W.act_lo); e.ld_split = W.ldc;
         }
-        PN_TRY(launch_gemm(A, cv, weight_planes(pk, b.conv_p), c.channels, e, mode, stream));
+        PN_TRY(launch_gemm(A, cv, weight_planes(pk, b.conv_p), c.channels, e, mode, stream, kStageEncoder));
       }
       dil *= c.dilation_base;
       if (dil > (1 << 24)) return fail("dilation overflow");
@@ -809,7 +834,7 @@ int pn_score_pairs(const pn_scorer_cfg* cfg, const void* packed, const float* a,
   Arena pk(const_cast<void*>(packed), L.bytes);
   const int H = c.out_hidden;
   const int ld_h = (int)round_up(H, 64);
-  const int parts = tiles_n_for(H);
+  const int parts = 2 * tiles_n_for(H);   // one partial dot per (N tile, column half)
   const size_t per_row = scorer_row_bytes(c);
   long long max_rows = (long long)((workspace_bytes > 8192 ? workspace_bytes - 8192 : 0) / per_row);
   if (g_chunk_rows > 0 && g_chunk_rows < max_rows) max_rows = g_chunk_rows;
@@ -853,7 +878,7 @@ int pn_score_pairs(const pn_scorer_cfg* cfg, const void* packed, const float* a,
         e.add_l = c_in + l0 * H; e.ld_add_l = H;
         e.relu = 1;
         e.out_hi = buf_hi[0]; e.out_lo = buf_lo[0]; e.ld_split = ld_h;
-        PN_TRY(launch_gemm(A, ConvView(), weight_planes(pk, L.l1_x), H, e, mode, stream));
+        PN_TRY(launch_gemm(A, ConvView(), weight_planes(pk, L.l1_x), H, e, mode, stream, kStageScorer));
       } else {
         pair_features_kernel<<<ew_grid(rows * (ld_h / 8)), 256, 0, stream>>>(a, H, c_in, H, (int)b0, (int)l0, (int)nl, rows,
                                                                              H, buf_hi[0], mode == PN_STRICT ? buf_lo[0] : nullptr,
@@ -875,7 +900,7 @@ int pn_score_pairs(const pn_scorer_cfg* cfg, const void* packed, const float* a,
         } else {
           e.out_hi = buf_hi[cur ^ 1]; e.out_lo = buf_lo[cur ^ 1]; e.ld_split = ld_h;
         }
-        PN_TRY(launch_gemm(A, ConvView(), weight_planes(pk, pl), H, e, mode, stream));
+        PN_TRY(launch_gemm(A, ConvView(), weight_planes(pk, pl), H, e, mode, stream, kStageScorer));
         cur ^= 1;
       }
       finalize_logits_kernel<<<ew_grid(rows / k), 256, 0, stream>>>(partial, parts, pk.at<float>(L.b_out), (int)b0, (int)l0,

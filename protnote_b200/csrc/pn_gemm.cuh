@@ -1,21 +1,30 @@
 // The one tensor-core engine every dense contraction of the scoring path runs on (sm_100a only).
 //
-//   D[M,N] = sum over K of A[M,K] * B[N,K]        (both operands K-major, fp32 accumulate in TMEM)
+//   D[M,N] = sum over K of A[M,K] * B[N,K]        (both operands K-major, fp32 accumulate)
 //
 // Operands are fp32 values carried as TWO fp16 planes (hi = fp16(x), lo = fp16(x - hi)).  In `strict`
 // mode (NPASS == 3) every k-step issues three tcgen05.mma into the same accumulator,
 //   A_lo*B_hi + A_hi*B_lo + A_hi*B_hi,
-// which reproduces an fp32 GEMM to ~2^-22 relative (the dropped lo*lo term); `fast` mode (NPASS == 1) issues
-// A_hi*B_hi only.  Weights are pre-scaled by a power of two at pack time so that their lo plane stays in
+// which reproduces an fp32 product sum to ~2^-22 relative (the dropped lo*lo term); `fast` mode (NPASS == 1)
+// issues A_hi*B_hi only.  Weights are pre-scaled by a power of two at pack time so that their lo plane stays in
 // fp16's normal range; the epilogue's per-column `scale` undoes it (and carries the folded BatchNorm).
 //
-// Structure: persistent CTAs (grid = #SMs), 8 warps, warp-specialised
-//   warp 0   TMA producer   (cp.async.bulk.tensor 2D for plain matrices, 3D for dilated-conv taps)
-//   warp 1   MMA issuer     (one elected lane, tcgen05.mma cta_group::1, M=128, N=bn<=256, K=16)
-//   warp 2   TMEM allocator (512 columns = two accumulator buffers)
-//   warps 4-7 epilogue      (tcgen05.ld 32x32b, one accumulator row per thread)
-// with an smem ring (full/empty mbarriers) between 0 and 1 and a two-deep TMEM ring between 1 and 4-7,
-// so the epilogue of tile i overlaps the main loop of tile i+1.
+// Accumulator promotion.  The tcgen05 accumulator add rounds toward zero, so a long accumulation chain picks up a
+// bias proportional to its length (measured on B200: K=3072 strict, relative error 3e-5; K=9900, 9e-5 - see
+// tools/accum_probe.py and profiles/).  The K loop is therefore cut into chunks of `chunk_kblocks` k-blocks
+// (256 K-elements in strict mode); each chunk accumulates from zero into one of the two TMEM buffers and the
+// epilogue warps add it into fp32 running sums held in registers (round-to-nearest).  With 256-element chunks the
+// result is as accurate as an fp32 SIMT GEMM (rms 6e-7 vs 5e-7 for cuBLAS fp32 at K=3072).  The two TMEM buffers
+// alternate, so the tensor core never waits for a drain; in fast mode a chunk is the whole K loop and the scheme
+// degenerates to the usual "epilogue of tile i overlaps main loop of tile i+1".
+//
+// Structure: persistent CTAs (grid = #SMs), 12 warps, warp-specialised
+//   warp 0     TMA producer   (cp.async.bulk.tensor 2D for plain matrices, 3D for dilated-conv taps)
+//   warp 1     MMA issuer     (one elected lane, tcgen05.mma cta_group::1, M=128, N=bn<=256, K=16)
+//   warp 2     TMEM allocator (512 columns = two accumulator buffers)
+//   warps 4-11 epilogue       (tcgen05.ld 32x32b; warp w owns TMEM lanes 32*(w%4).. and column half (w-4)/4)
+// Registers are re-balanced with setmaxnreg: the four control warps give theirs to the epilogue warps, whose
+// running sums (128 fp32 per thread) live in registers.
 //
 // A-operand addressing modes
 //   plain : A is a [M][K] matrix, tile rows = 128 consecutive rows.
@@ -32,8 +41,10 @@ namespace pn {
 
 constexpr int kBM = 128;          // accumulator rows per tile (UMMA M)
 constexpr int kMaxBN = 256;       // accumulator columns per tile (UMMA N), runtime bn <= kMaxBN
-constexpr int kGemmThreads = 256;
+constexpr int kGemmThreads = 384; // 4 control warps + 8 epilogue warps
 constexpr int kSmemBudget = 200 * 1024;
+constexpr int kCtrlRegs = 40;     // setmaxnreg targets: 128*40 + 256*232 = 64512 <= 65536
+constexpr int kEpiRegs = 232;
 
 struct alignas(64) GemmParams {
   CUtensorMap tm_a_hi, tm_a_lo, tm_b_hi, tm_b_lo;
@@ -41,6 +52,7 @@ struct alignas(64) GemmParams {
   int bn;                // tile width, multiple of 32, <= 256
   int tiles_m, tiles_n;
   int num_kblocks;       // K / BK (conv: taps * cblocks)
+  int chunk_kblocks;     // k-blocks per accumulator chunk (promotion period), >= 1
   // conv addressing (conv_taps == 0 -> plain)
   int conv_taps, conv_cblocks, conv_cpad, conv_dil, conv_T, conv_tiles_per_seq;
   const long long* lengths;      // [B] valid positions per sequence (conv) or nullptr
@@ -56,9 +68,18 @@ struct alignas(64) GemmParams {
   const float* scale2; const float* shift2; // [N] (nullable)
   int relu;
   __half* out_hi; __half* out_lo; long long ld_split;   // z as fp16 planes (nullable; out_lo nullable)
-  const float* dot_w; float* dot_out;       // dot_out[row*tiles_n + n_tile] = sum_n z*dot_w[n] (nullable)
+  const float* dot_w; float* dot_out;       // dot_out[(row*tiles_n + n_tile)*2 + half] = sum_n z*dot_w[n] (nullable)
   int vec_out, vec_resid, vec_split;        // 16-byte vector access is legal for that tensor (host-checked)
 };
+
+// Per-tile copies of the per-column epilogue vectors in shared memory (all 128 rows of a tile use the same
+// values: a broadcast LDS.128 fetches four columns at once instead of four global loads per thread).
+struct EpiConsts {
+  float scale[kMaxBN], shift[kMaxBN], scale2[kMaxBN], shift2[kMaxBN], dotw[kMaxBN];
+};
+constexpr int kStageRowBytes = 80;                       // 64 B of halves + 16 B pad (conflict-free 16 B accesses)
+constexpr int kStageBytesPerWarp = 32 * kStageRowBytes;  // one 32x32 fp16 block per epilogue warp
+constexpr int kEpiSmemBytes = (int)sizeof(EpiConsts) + 8 * kStageBytesPerWarp;
 
 template <int BK, int NPASS>
 struct GemmCfg {
@@ -68,13 +89,149 @@ struct GemmCfg {
   static constexpr int kBTile = kMaxBN * BK * 2;
   static constexpr int kStageBytes = kPlanes * (kATile + kBTile);
   static constexpr int kStages = kSmemBudget / kStageBytes;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kEpiSmemBytes;
   static_assert(kStages >= 2, "pipeline too shallow");
 };
 
 __device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
   hi = __float2half_rn(x);
   lo = __float2half_rn(x - __half2float(hi));
+}
+
+template <int REGS>
+__device__ __forceinline__ void reg_dealloc() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS));
+}
+template <int REGS>
+__device__ __forceinline__ void reg_alloc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS));
+}
+
+// fp32 pair -> packed fp16 hi pair and lo pair (3 instructions per element)
+__device__ __forceinline__ void split_pack(float a, float b, uint32_t& hi, uint32_t& lo) {
+  a = fmaxf(fminf(a, 65504.f), -65504.f);
+  b = fmaxf(fminf(b, 65504.f), -65504.f);
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// A warp's 32 rows x 32 halves: transpose through shared memory so that four consecutive lanes write 64
+// contiguous bytes of one row (8 rows per store instruction instead of 32 scattered 16-byte pieces).
+__device__ __forceinline__ void store_halves_coalesced(const uint32_t (&v)[16], uint8_t* stage, __half* row0_ptr,
+                                                       long long ld, uint32_t row_mask, int lane) {
+  uint4* mine = reinterpret_cast<uint4*>(stage + lane * kStageRowBytes);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) mine[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  __syncwarp();
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int rr = it * 8 + (lane >> 2);
+    const int ch = lane & 3;
+    const uint4 val = *reinterpret_cast<const uint4*>(stage + rr * kStageRowBytes + ch * 16);
+    if ((row_mask >> rr) & 1u) *reinterpret_cast<uint4*>(row0_ptr + rr * ld + ch * 8) = val;
+  }
+  __syncwarp();
+}
+
+// Epilogue math for one group of 32 consecutive columns of one row; `y` holds the raw accumulator sums on entry.
+// c0 = column offset of the group inside the tile (index into EpiConsts), n0 = global column.
+__device__ __forceinline__ void epilogue_group(const GemmParams& p, const EpiConsts& ec, uint8_t* stage, float (&y)[32],
+                                               int c0, int n0, long long row, bool valid, uint32_t row_mask, int lane,
+                                               const float* addp, const float* addl, float& dot) {
+  const bool full = (n0 + 32 <= p.N);
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    const float4 s4 = *reinterpret_cast<const float4*>(&ec.scale[c0 + j]);
+    const float4 h4 = *reinterpret_cast<const float4*>(&ec.shift[c0 + j]);
+    y[j] = fmaf(y[j], s4.x, h4.x);
+    y[j + 1] = fmaf(y[j + 1], s4.y, h4.y);
+    y[j + 2] = fmaf(y[j + 2], s4.z, h4.z);
+    y[j + 3] = fmaf(y[j + 3], s4.w, h4.w);
+  }
+  if (addp || addl) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (full || n0 + j < p.N) {
+        if (addp) y[j] += __ldg(addp + n0 + j);
+        if (addl) y[j] += __ldg(addl + n0 + j);
+      }
+  }
+  if (p.resid && valid) {
+    const float* rp = p.resid + row * p.ld_resid + n0;
+    if (full && p.vec_resid) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 r4 = *reinterpret_cast<const float4*>(rp + j);
+        y[j] += r4.x; y[j + 1] += r4.y; y[j + 2] += r4.z; y[j + 3] += r4.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (n0 + j < p.N) y[j] += rp[j];
+    }
+  }
+  if (!valid) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) y[j] = 0.f;
+  }
+  if (p.out_f32 && ((row_mask >> lane) & 1u)) {
+    float* op = p.out_f32 + row * p.ld_out + n0;
+    if (full && p.vec_out) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(op + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (n0 + j < p.N) op[j] = y[j];
+    }
+  }
+  if (p.out_hi || p.dot_w) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      if (p.scale2) {
+        const float4 s4 = *reinterpret_cast<const float4*>(&ec.scale2[c0 + j]);
+        const float4 h4 = *reinterpret_cast<const float4*>(&ec.shift2[c0 + j]);
+        y[j] = fmaf(y[j], s4.x, h4.x);
+        y[j + 1] = fmaf(y[j + 1], s4.y, h4.y);
+        y[j + 2] = fmaf(y[j + 2], s4.z, h4.z);
+        y[j + 3] = fmaf(y[j + 3], s4.w, h4.w);
+      }
+      if (p.relu) {
+        y[j] = fmaxf(y[j], 0.f); y[j + 1] = fmaxf(y[j + 1], 0.f);
+        y[j + 2] = fmaxf(y[j + 2], 0.f); y[j + 3] = fmaxf(y[j + 3], 0.f);
+      }
+      if (!valid) y[j] = y[j + 1] = y[j + 2] = y[j + 3] = 0.f;
+      if (p.dot_w) {   // columns >= N carry dotw == 0
+        const float4 w4 = *reinterpret_cast<const float4*>(&ec.dotw[c0 + j]);
+        dot = fmaf(y[j], w4.x, dot);
+        dot = fmaf(y[j + 1], w4.y, dot);
+        dot = fmaf(y[j + 2], w4.z, dot);
+        dot = fmaf(y[j + 3], w4.w, dot);
+      }
+    }
+    if (p.out_hi) {
+      uint32_t hi2[16], lo2[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) split_pack(y[2 * j], y[2 * j + 1], hi2[j], lo2[j]);
+      __half* hp = p.out_hi + row * p.ld_split + n0;
+      __half* lp = p.out_lo ? p.out_lo + row * p.ld_split + n0 : nullptr;
+      if (full && p.vec_split) {   // warp-uniform
+        store_halves_coalesced(hi2, stage, hp - lane * p.ld_split, p.ld_split, row_mask, lane);
+        if (lp) store_halves_coalesced(lo2, stage, lp - lane * p.ld_split, p.ld_split, row_mask, lane);
+      } else if ((row_mask >> lane) & 1u) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (n0 + j < p.N) {
+            hp[j] = __ushort_as_half((unsigned short)((hi2[j >> 1] >> ((j & 1) * 16)) & 0xffffu));
+            if (lp) lp[j] = __ushort_as_half((unsigned short)((lo2[j >> 1] >> ((j & 1) * 16)) & 0xffffu));
+          }
+      }
+    }
+  }
 }
 
 template <int BK, int NPASS>
@@ -91,11 +248,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
   const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::kStages + 4);
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  uint8_t* epi_smem = smem_raw + (bar_base + 256u - smem_u32(smem_raw));   // EpiConsts, then 8 warp staging blocks
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const bool conv = p.conv_taps > 0;
   const int total_tiles = p.tiles_m * p.tiles_n;
+  const int num_chunks = (p.num_kblocks + p.chunk_kblocks - 1) / p.chunk_kblocks;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tm_a_hi);
@@ -112,7 +271,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);
+      mbar_init(tempty_bar(a), 8);   // one arrive per epilogue warp
     }
     fence_mbar_init();
   }
@@ -134,9 +293,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
     return (long long)t0 >= p.lengths[b];
   };
 
-  if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+  if (warp < 4) {
+    reg_dealloc<kCtrlRegs>();
+    if (warp == 0 && lane == 0) {
+      // ---------------------------------------------------------------- TMA producer
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t tx_bytes = Cfg::kPlanes * (Cfg::kATile + (uint32_t)p.bn * BK * 2);
@@ -173,10 +333,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
           }
         }
       }
-    }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    } else if (warp == 1 && lane == 0) {
+      // ---------------------------------------------------------------- MMA issuer
       const uint32_t idesc = make_idesc_f16(kBM, p.bn, /*fp16*/ 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -185,46 +343,62 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int m_tile = tile / p.tiles_n;
         if (tile_is_padding(m_tile)) continue;
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * kMaxBN;
-        for (int kb = 0; kb < p.num_kblocks; ++kb) {
-          mbar_wait(full_bar(stage), phase);
+        int kb = 0;
+        for (int chunk = 0; chunk < num_chunks; ++chunk) {
+          mbar_wait(tempty_bar(acc), acc_phase ^ 1);   // the epilogue has drained this buffer
           tc_fence_after();
-          const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
-          const uint32_t sb = sa + Cfg::kPlanes * Cfg::kATile;
-#pragma unroll
-          for (int ks = 0; ks < BK / 16; ++ks) {
-            const uint64_t a_hi = make_kmajor_desc<Cfg::kSwizzle>(sa + ks * 32);
-            const uint64_t b_hi = make_kmajor_desc<Cfg::kSwizzle>(sb + ks * 32);
-            const uint32_t first = (kb | ks) != 0;
+          const uint32_t d_tmem = tmem_base + acc * kMaxBN;
+          const int kb_end = min(kb + p.chunk_kblocks, p.num_kblocks);
+          bool first = true;
+          for (; kb < kb_end; ++kb) {
+            mbar_wait(full_bar(stage), phase);
+            tc_fence_after();
+            const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+            const uint32_t sb = sa + Cfg::kPlanes * Cfg::kATile;
+            // Within a k-block the small hi*lo / lo*hi products go first: the accumulator add truncates relative
+            // to the accumulator's magnitude, so every tiny term added before the hi*hi terms is added exactly.
             if (NPASS == 3) {
-              const uint64_t a_lo = make_kmajor_desc<Cfg::kSwizzle>(sa + Cfg::kATile + ks * 32);
-              const uint64_t b_lo = make_kmajor_desc<Cfg::kSwizzle>(sb + Cfg::kBTile + ks * 32);
-              umma_f16(d_tmem, a_lo, b_hi, idesc, first);   // small terms first
-              umma_f16(d_tmem, a_hi, b_lo, idesc, 1);
-              umma_f16(d_tmem, a_hi, b_hi, idesc, 1);
-            } else {
-              umma_f16(d_tmem, a_hi, b_hi, idesc, first);
+#pragma unroll
+              for (int ks = 0; ks < BK / 16; ++ks) {
+                const uint64_t a_hi = make_kmajor_desc<Cfg::kSwizzle>(sa + ks * 32);
+                const uint64_t b_hi = make_kmajor_desc<Cfg::kSwizzle>(sb + ks * 32);
+                const uint64_t a_lo = make_kmajor_desc<Cfg::kSwizzle>(sa + Cfg::kATile + ks * 32);
+                const uint64_t b_lo = make_kmajor_desc<Cfg::kSwizzle>(sb + Cfg::kBTile + ks * 32);
+                umma_f16(d_tmem, a_lo, b_hi, idesc, first ? 0u : 1u);
+                umma_f16(d_tmem, a_hi, b_lo, idesc, 1);
+                first = false;
+              }
+            }
+#pragma unroll
+            for (int ks = 0; ks < BK / 16; ++ks) {
+              const uint64_t a_hi = make_kmajor_desc<Cfg::kSwizzle>(sa + ks * 32);
+              const uint64_t b_hi = make_kmajor_desc<Cfg::kSwizzle>(sb + ks * 32);
+              umma_f16(d_tmem, a_hi, b_hi, idesc, first ? 0u : 1u);
+              first = false;
+            }
+            umma_commit(empty_bar(stage));   // frees the smem slot once these MMAs have read it
+            if (++stage == Cfg::kStages) {
+              stage = 0;
+              phase ^= 1;
             }
           }
-          umma_commit(empty_bar(stage));   // frees the smem slot once these MMAs have read it
-          if (++stage == Cfg::kStages) {
-            stage = 0;
-            phase ^= 1;
+          umma_commit(tfull_bar(acc));       // chunk complete -> epilogue warps promote it
+          if (++acc == 2) {
+            acc = 0;
+            acc_phase ^= 1;
           }
-        }
-        umma_commit(tfull_bar(acc));       // accumulator complete -> epilogue
-        if (++acc == 2) {
-          acc = 0;
-          acc_phase ^= 1;
         }
       }
     }
-  } else if (warp >= 4) {
-    // ------------------------------------------------------------------ epilogue
-    const int ew = warp - 4;                  // == warp % 4: the TMEM lane quarter this warp may read
-    const int r_in_tile = ew * 32 + lane;
+  } else {
+    // ------------------------------------------------------------------ epilogue (8 warps)
+    reg_alloc<kEpiRegs>();
+    const int q = warp & 3;                   // TMEM lane quarter this warp may read
+    const int half = (warp - 4) >> 2;         // which half of the tile's column groups
+    const int ngroups = p.bn >> 5;            // 32-column groups in a tile (<= 8)
+    const int g_lo = half == 0 ? 0 : (ngroups + 1) >> 1;
+    const int g_hi = half == 0 ? (ngroups + 1) >> 1 : ngroups;
+    const int r_in_tile = q * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -250,118 +424,59 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
         if (p.add_p) addp = p.add_p + (row / p.pair_nl) * p.ld_add_p;
         if (p.add_l) addl = p.add_l + (row % p.pair_nl) * p.ld_add_l;
       }
+      // per-tile epilogue vectors -> shared memory (one column per epilogue thread)
+      EpiConsts& ec = *reinterpret_cast<EpiConsts*>(epi_smem);
+      uint8_t* stage = epi_smem + sizeof(EpiConsts) + (warp - 4) * kStageBytesPerWarp;
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // everyone is done with the previous tile's vectors
+      {
+        const int cc = threadIdx.x - 128;
+        const int n = n_tile * p.bn + cc;
+        const bool ok = cc < p.bn && n < p.N;
+        ec.scale[cc] = (ok && p.scale) ? __ldg(p.scale + n) : 1.f;
+        ec.shift[cc] = (ok && p.shift) ? __ldg(p.shift + n) : 0.f;
+        ec.scale2[cc] = (ok && p.scale2) ? __ldg(p.scale2 + n) : 1.f;
+        ec.shift2[cc] = (ok && p.shift2) ? __ldg(p.shift2 + n) : 0.f;
+        ec.dotw[cc] = (ok && p.dot_w) ? __ldg(p.dot_w + n) : 0.f;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const uint32_t row_mask = __ballot_sync(0xffffffffu, in_range);
+      float sums[4][32];
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sums[g][j] = 0.f;
       if (!padding_tile) {
-        mbar_wait(tfull_bar(acc), acc_phase);
-        tc_fence_after();
+        for (int chunk = 0; chunk < num_chunks; ++chunk) {
+          mbar_wait(tfull_bar(acc), acc_phase);
+          tc_fence_after();
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (g_lo + g < g_hi) {   // warp-uniform
+              uint32_t v[32];
+              tmem_ld32(tmem_base + acc * kMaxBN + (g_lo + g) * 32 + ((uint32_t)(q * 32) << 16), v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) sums[g][j] += __uint_as_float(v[j]);
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(acc));
+          if (++acc == 2) {
+            acc = 0;
+            acc_phase ^= 1;
+          }
+        }
       }
       float dot = 0.f;
-      for (int c0 = 0; c0 < p.bn; c0 += 32) {
-        uint32_t v[32];
-        if (!padding_tile) {
-          tmem_ld32(tmem_base + acc * kMaxBN + c0 + ((uint32_t)(ew * 32) << 16), v);
-          tmem_ld_wait();
-        } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = 0u;
-        }
+      for (int g = 0; g < 4; ++g) {
+        const int c0 = (g_lo + g) * 32;
         const int n0 = n_tile * p.bn + c0;
-        if (!in_range || n0 >= p.N) continue;
-        const bool full = (n0 + 32 <= p.N);
-        float y[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int n = n0 + j;
-          float a = __uint_as_float(v[j]);
-          if (full || n < p.N) {
-            const float s = p.scale ? __ldg(p.scale + n) : 1.f;
-            const float h = p.shift ? __ldg(p.shift + n) : 0.f;
-            a = fmaf(a, s, h);
-            if (addp) a += __ldg(addp + n);
-            if (addl) a += __ldg(addl + n);
-          }
-          y[j] = a;
-        }
-        if (p.resid && valid) {
-          const float* rp = p.resid + row * p.ld_resid + n0;
-          if (full && p.vec_resid) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 r4 = *reinterpret_cast<const float4*>(rp + j);
-              y[j] += r4.x; y[j + 1] += r4.y; y[j + 2] += r4.z; y[j + 3] += r4.w;
-            }
-          } else {
-            for (int j = 0; j < 32; ++j)
-              if (n0 + j < p.N) y[j] += rp[j];
-          }
-        }
-        if (!valid) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) y[j] = 0.f;
-        }
-        if (p.out_f32) {
-          float* op = p.out_f32 + row * p.ld_out + n0;
-          if (full && p.vec_out) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(op + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
-          } else {
-            for (int j = 0; j < 32; ++j)
-              if (n0 + j < p.N) op[j] = y[j];
-          }
-        }
-        if (p.out_hi || p.dot_w) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int n = n0 + j;
-            float z = y[j];
-            if (full || n < p.N) {
-              if (p.scale2) z = fmaf(z, __ldg(p.scale2 + n), p.shift2 ? __ldg(p.shift2 + n) : 0.f);
-              if (p.relu) z = fmaxf(z, 0.f);
-              if (!valid) z = 0.f;
-              if (p.dot_w) dot = fmaf(z, __ldg(p.dot_w + n), dot);
-            } else {
-              z = 0.f;
-            }
-            y[j] = z;
-          }
-          if (p.out_hi) {
-            uint32_t hi2[16], lo2[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              __half h0, l0, h1, l1;
-              split_f16(fmaxf(fminf(y[2 * j], 65504.f), -65504.f), h0, l0);
-              split_f16(fmaxf(fminf(y[2 * j + 1], 65504.f), -65504.f), h1, l1);
-              hi2[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-              lo2[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
-            }
-            __half* hp = p.out_hi + row * p.ld_split + n0;
-            __half* lp = p.out_lo ? p.out_lo + row * p.ld_split + n0 : nullptr;
-            if (full && p.vec_split) {
-#pragma unroll
-              for (int j = 0; j < 16; j += 4) {
-                *reinterpret_cast<uint4*>(hp + 2 * j) = make_uint4(hi2[j], hi2[j + 1], hi2[j + 2], hi2[j + 3]);
-                if (lp) *reinterpret_cast<uint4*>(lp + 2 * j) = make_uint4(lo2[j], lo2[j + 1], lo2[j + 2], lo2[j + 3]);
-              }
-            } else {
-              for (int j = 0; j < 32; ++j)
-                if (n0 + j < p.N) {
-                  hp[j] = __ushort_as_half((unsigned short)((hi2[j >> 1] >> ((j & 1) * 16)) & 0xffffu));
-                  if (lp) lp[j] = __ushort_as_half((unsigned short)((lo2[j >> 1] >> ((j & 1) * 16)) & 0xffffu));
-                }
-            }
-          }
-        }
+        if (g_lo + g < g_hi && n0 < p.N)   // warp-uniform (rows out of range are masked inside)
+          epilogue_group(p, ec, stage, sums[g], c0, n0, row, valid, row_mask, lane, addp, addl, dot);
       }
-      if (p.dot_w && in_range) p.dot_out[row * p.tiles_n + n_tile] = dot;
-      if (!padding_tile) {
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(acc));
-        if (++acc == 2) {
-          acc = 0;
-          acc_phase ^= 1;
-        }
-      }
+      if (p.dot_w && in_range) p.dot_out[(row * p.tiles_n + n_tile) * 2 + half] = dot;
     }
   }
 

@@ -188,21 +188,21 @@ __global__ void pair_product_kernel(const float* __restrict__ p, long long ldp, 
 // grid (ceil(C/32), B), block (32, 8): lanes span channels (coalesced), the 8 rows stride over t.
 __global__ void pool_mean_kernel(const float* __restrict__ x, long long ldx, const long long* __restrict__ lengths,
                                  int T, int C, float* __restrict__ out, long long ldo) {
-  __shared__ float part[8][33];
+  __shared__ double part[8][33];
   const int b = blockIdx.y;
   const int c = blockIdx.x * 32 + threadIdx.x;
   long long len = lengths[b];
   const int n = (int)(len < T ? len : T);
-  float s = 0.f;
+  double s = 0.0;   // fp64 accumulation: the sum over up to T positions is then exact to fp32 rounding
   if (c < C)
-    for (int t = threadIdx.y; t < n; t += 8) s += x[((long long)b * T + t) * ldx + c];
+    for (int t = threadIdx.y; t < n; t += 8) s += (double)x[((long long)b * T + t) * ldx + c];
   part[threadIdx.y][threadIdx.x] = s;
   __syncthreads();
   if (threadIdx.y == 0 && c < C) {
-    float tot = 0.f;
+    double tot = 0.0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) tot += part[j][threadIdx.x];
-    out[(long long)b * ldo + c] = tot / (float)len;
+    out[(long long)b * ldo + c] = (float)(tot / (double)len);
   }
 }
 
@@ -221,9 +221,10 @@ __global__ void finalize_logits_kernel(const float* __restrict__ partial, int pa
     float acc = 0.f;
     for (int j = 0; j < k; ++j) {
       const float* pp = partial + (r0 + j) * parts;
-      float x = 0.f;
-      for (int q = 0; q < parts; ++q) x += pp[q];
-      x += bias ? *bias : 0.f;
+      double xs = 0.0;
+      for (int q = 0; q < parts; ++q) xs += (double)pp[q];
+      xs += bias ? (double)*bias : 0.0;
+      const float x = (float)xs;
       if (k == 1) {
         acc = x;
       } else {

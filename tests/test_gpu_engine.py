@@ -18,8 +18,8 @@ def test_linear_strict(bk, shape):
         b = torch.randn(N, generator=g).cuda()
         y = native.linear(x, w, b)
         ref = x.double() @ w.double().T + b.double()
-        # fp32-grade: error budget = fp32 accumulation over K terms of O(1) magnitude
-        assert (y.double() - ref).abs().max().item() <= 2e-7 * K + 2e-6
+        # fp32-grade: same error level as an fp32 SIMT GEMM (cuBLAS fp32 measures 5e-6 max at K=3072 on this data)
+        assert (y.double() - ref).abs().max().item() <= 1e-5
     finally:
         native.set_option("bk", 0)
 
@@ -41,5 +41,5 @@ def test_masked_dilated_conv_strict(cfg):
     mask = torch.arange(T, device="cuda")[None, :] < lengths[:, None]
     ref = torch.nn.functional.conv1d((x * mask[:, None, :]).double(), w.double(), b.double(), padding="same", dilation=dil)
     ref = (ref * mask[:, None, :]).permute(0, 2, 1)
-    assert (y.double() - ref).abs().max().item() <= 2e-7 * cin * taps + 2e-6
+    assert (y.double() - ref).abs().max().item() <= 1e-5
     assert y[~mask].abs().max().item() == 0.0 if (~mask).any() else True
