@@ -43,6 +43,11 @@ int pn_device_check(int device);
 int pn_set_option(const char* name, long long value);
 /* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
 long long pn_launch_count(void);
+/* Measurement hook: while enabled, every GEMM launch of the pair scorer is bracketed by CUDA events on its stream.
+ * pn_gemm_timing(enable) clears earlier records; pn_gemm_timing_read waits for the recorded events and returns
+ * the summed launch durations, the number of launches and their algorithmic FLOPs (2*M*N*K each). */
+int pn_gemm_timing(int enable);
+int pn_gemm_timing_read(double* total_ms, long long* launches, double* algorithmic_flops);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Sequence encoder: ProteInfer dilated ResNet, eval mode.

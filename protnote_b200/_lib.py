@@ -38,6 +38,8 @@ SIGNATURES = {
     "pn_device_check": (_I, [_I]),
     "pn_set_option": (_I, [C.c_char_p, _LL]),
     "pn_launch_count": (_LL, []),
+    "pn_gemm_timing": (_I, [_I]),
+    "pn_gemm_timing_read": (_I, [C.POINTER(C.c_double), C.POINTER(_LL), C.POINTER(C.c_double)]),
     "pn_encoder_packed_bytes": (_SZ, [C.POINTER(EncoderCfg)]),
     "pn_encoder_pack": (_I, [C.POINTER(EncoderCfg), C.POINTER(_P), _I, _P, _SZ, _P]),
     "pn_encoder_workspace_bytes": (_SZ, [C.POINTER(EncoderCfg), _I, _I]),

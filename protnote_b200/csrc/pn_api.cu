@@ -24,6 +24,14 @@ long long g_chunk_rows = 0;      // 0 = auto
 enum { kStageEncoder = 0, kStageHeads = 1, kStageScorer = 2, kStageOther = 3 };
 int g_promote_k[4] = {32, 32, 256, 64};
 
+// optional per-launch CUDA-event timing of the pair scorer's GEMM launches (bench.py's roofline numbers)
+struct TimedLaunch {
+  cudaEvent_t start, stop;
+  double flops;
+};
+bool g_timing = false;
+std::vector<TimedLaunch> g_timed;
+
 int fail(const char* fmt, ...) {
   char buf[1024];
   va_list ap;
@@ -158,8 +166,20 @@ int launch_gemm_t(const GemmParams& p, cudaStream_t stream) {
   }
   const int total = p.tiles_m * p.tiles_n;
   const int grid = total < num_sms() ? total : num_sms();
+  TimedLaunch tl;
+  const bool timed = g_timing && p.timed_flops > 0;
+  if (timed) {
+    PN_CUDA(cudaEventCreate(&tl.start));
+    PN_CUDA(cudaEventCreate(&tl.stop));
+    tl.flops = p.timed_flops;
+    PN_CUDA(cudaEventRecord(tl.start, stream));
+  }
   gemm_kernel<BK, NPASS><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(p);
   PN_CUDA(cudaGetLastError());
+  if (timed) {
+    PN_CUDA(cudaEventRecord(tl.stop, stream));
+    g_timed.push_back(tl);
+  }
   g_launches++;
   return 0;
 }
@@ -205,6 +225,8 @@ int launch_gemm(const Planes& A, const ConvView& cv, const Planes& B, long long 
   }
   if (A.rows >= (1LL << 31) || p.tiles_m <= 0 || p.num_kblocks <= 0) return fail("bad GEMM shape");
   p.chunk_kblocks = p.num_kblocks;
+  // algorithmic FLOPs of this launch (2*M*N*K), recorded only for the pair scorer's GEMMs
+  p.timed_flops = stage_kind == kStageScorer ? 2.0 * (double)A.rows * (double)N * (double)A.cols : 0.0;
   const int promote_k = g_promote_k[stage_kind];
   if (mode == PN_STRICT && promote_k > 0) {
     p.chunk_kblocks = promote_k / bk > 0 ? promote_k / bk : 1;
@@ -520,6 +542,31 @@ int pn_device_check(int device) {
   cudaDeviceProp prop;
   PN_CUDA(cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10) return fail("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+  return 0;
+}
+
+int pn_gemm_timing(int enable) {
+  for (TimedLaunch& t : g_timed) {
+    cudaEventDestroy(t.start);
+    cudaEventDestroy(t.stop);
+  }
+  g_timed.clear();
+  g_timing = enable != 0;
+  return 0;
+}
+
+int pn_gemm_timing_read(double* total_ms, long long* launches, double* algorithmic_flops) {
+  double ms = 0.0, fl = 0.0;
+  for (TimedLaunch& t : g_timed) {
+    PN_CUDA(cudaEventSynchronize(t.stop));
+    float e = 0.f;
+    PN_CUDA(cudaEventElapsedTime(&e, t.start, t.stop));
+    ms += e;
+    fl += t.flops;
+  }
+  if (total_ms) *total_ms = ms;
+  if (launches) *launches = (long long)g_timed.size();
+  if (algorithmic_flops) *algorithmic_flops = fl;
   return 0;
 }
 

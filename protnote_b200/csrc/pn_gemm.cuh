@@ -70,6 +70,7 @@ struct alignas(64) GemmParams {
   __half* out_hi; __half* out_lo; long long ld_split;   // z as fp16 planes (nullable; out_lo nullable)
   const float* dot_w; float* dot_out;       // dot_out[(row*tiles_n + n_tile)*2 + half] = sum_n z*dot_w[n] (nullable)
   int vec_out, vec_resid, vec_split;        // 16-byte vector access is legal for that tensor (host-checked)
+  double timed_flops;                       // host-side bookkeeping only (algorithmic FLOPs of this launch)
 };
 
 // Per-tile copies of the per-column epilogue vectors in shared memory (all 128 rows of a tile use the same

@@ -55,6 +55,17 @@ def launch_count() -> int:
     return int(_lib.load().pn_launch_count())
 
 
+def gemm_timing(enable: bool):
+    check(_lib.load().pn_gemm_timing(int(enable)))
+
+
+def gemm_timing_read():
+    """(summed launch ms, launches, algorithmic FLOPs) of the scorer GEMM launches since gemm_timing(True)."""
+    ms, n, fl = C.c_double(), C.c_longlong(), C.c_double()
+    check(_lib.load().pn_gemm_timing_read(C.byref(ms), C.byref(n), C.byref(fl)))
+    return ms.value, n.value, fl.value
+
+
 class PackedEncoder:
     """Device-resident packed weights of one ProteInfer encoder + the forward call."""
 
