@@ -1,0 +1,133 @@
+"""Edge cases and size-independent properties of the sm_100a path (through the C ABI), checked against the oracle."""
+import dataclasses
+
+import pytest
+import torch
+
+from oracle.cases import CASES
+from oracle.protnote_oracle import (EncoderCfg, ScorerCfg, proteinfer_embeddings, proteinfer_logits, protnote_forward,
+                                    synth_inputs, synth_state_dict)
+from tests.helpers import build_b200_model, load_case
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+TINY_E = CASES["tiny_concat"][0]
+TINY_S = CASES["tiny_concat"][1]
+
+
+def run(model, onehots, lengths, labels):
+    with torch.no_grad():
+        out, _ = model(sequence_onehots=onehots.cuda(), sequence_lengths=lengths.cuda(), label_embeddings=labels.cuda())
+    torch.cuda.synchronize()
+    return out.cpu()
+
+
+@pytest.mark.parametrize("B,T,L", [(1, 1, 1), (1, 9, 3), (2, 129, 33), (3, 128, 1), (2, 257, 130), (1, 1500, 5)])
+def test_ragged_shapes_against_oracle(B, T, L):
+    """Single residue / single label / tile-boundary lengths / sequences longer than the widest dilation's reach."""
+    ecfg = dataclasses.replace(TINY_E, num_resnet_blocks=5) if T > 1000 else TINY_E
+    sd = synth_state_dict(ecfg, TINY_S, seed=100 + B + T + L)
+    onehots, lengths, labels = synth_inputs(B, T, L, ecfg, TINY_S, ragged=True, seed=7 * T + L)
+    if T > 1:
+        lengths[-1] = 1                      # a one-residue protein next to a full-length one
+        onehots[-1, :, 1:] = 0
+    model = build_b200_model(ecfg, TINY_S, sd)
+    got = run(model, onehots, lengths, labels)
+    ref = protnote_forward(sd, onehots, lengths, labels, ecfg, TINY_S)
+    assert got.shape == ref.shape == (B, L)
+    assert (got - ref).abs().max().item() <= TOL
+
+
+def test_padding_content_and_batch_position_do_not_matter():
+    """set_padding_to_sentinel semantics (datasets.py:535-569): garbage beyond `length` is ignored, and a protein scored
+    alone (unpadded) gets bit-identical logits to the same protein inside a padded batch."""
+    ecfg, scfg, sd, onehots, lengths, labels, g = load_case("tiny_concat")
+    model = build_b200_model(ecfg, scfg, sd)
+    base = run(model, onehots, lengths, labels)
+    noisy = onehots.clone()
+    for b in range(onehots.shape[0]):
+        noisy[b, :, int(lengths[b]):] = 123.0
+    assert torch.equal(run(model, noisy, lengths, labels), base)
+    for b in (1, onehots.shape[0] - 1):
+        n = int(lengths[b])
+        solo = run(model, onehots[b:b + 1, :, :n].contiguous(), lengths[b:b + 1], labels)
+        assert torch.equal(solo[0], base[b])
+
+
+def test_permutation_equivariance_and_chunking_are_bitwise():
+    """Pairs are independent: permuting proteins / label rows permutes the logits bit for bit, and so does forcing the
+    scorer to work in small chunks (workspace-limited path)."""
+    from protnote_b200 import native
+    ecfg, scfg, sd, onehots, lengths, labels, g = load_case("base_small")
+    model = build_b200_model(ecfg, scfg, sd)
+    base = run(model, onehots, lengths, labels)
+    gen = torch.Generator().manual_seed(3)
+    pl = torch.randperm(labels.shape[0], generator=gen)
+    pb = torch.randperm(onehots.shape[0], generator=gen)
+    assert torch.equal(run(model, onehots, lengths, labels[pl]), base[:, pl])
+    assert torch.equal(run(model, onehots[pb], lengths[pb], labels), base[pb])
+    native.set_option("chunk_rows", 128)
+    try:
+        model._label_cache = None
+        assert torch.equal(run(model, onehots, lengths, labels), base)
+    finally:
+        native.set_option("chunk_rows", 0)
+
+
+@pytest.mark.parametrize("variant", ["diff", "no_batchnorm", "two_layers", "dropout_wrappers", "k3"])
+def test_config_variants_against_oracle(variant):
+    """Constructor options that change the arithmetic or the state_dict layout (ProtNote.py:83-102,128-138,337-378)."""
+    scfg = {
+        "diff": dataclasses.replace(TINY_S, feature_fusion="concatenation_diff"),
+        "no_batchnorm": dataclasses.replace(TINY_S, output_mlp_batchnorm=False),
+        "two_layers": dataclasses.replace(TINY_S, output_mlp_num_layers=2, projection_head_num_layers=1),
+        "dropout_wrappers": dataclasses.replace(TINY_S, sequence_embedding_dropout=0.1, label_embedding_dropout=0.2),
+        "k3": dataclasses.replace(TINY_S, inference_descriptions_per_label=3),
+    }[variant]
+    sd = synth_state_dict(TINY_E, scfg, seed=900 + len(variant))
+    onehots, lengths, labels = synth_inputs(4, 77, 21, TINY_E, scfg, ragged=True, seed=55)
+    model = build_b200_model(TINY_E, scfg, sd)
+    got = run(model, onehots, lengths, labels)
+    ref = protnote_forward(sd, onehots, lengths, labels, TINY_E, scfg)
+    assert got.shape == ref.shape
+    # the k-row ensemble maps a logit error e to e / (p (1 - p)) at most; the synthetic logits keep p away from 0/1
+    assert (got - ref).abs().max().item() <= TOL
+
+
+def test_float_inputs_and_encoder_logits():
+    """Any float [B,Cin,T] is accepted, and ProteInfer.forward = output_layer(get_embeddings)
+    (protein_encoders.py:120-123, the path bin/test_proteinfer.py:303 uses)."""
+    ecfg, scfg, sd, onehots, lengths, labels, g = load_case("tiny_concat")
+    model = build_b200_model(ecfg, scfg, sd)
+    x = onehots + 0.25 * torch.randn(onehots.shape, generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        emb = model.sequence_encoder.get_embeddings(x.cuda(), lengths.cuda()).cpu()
+        enc_logits = model.sequence_encoder(x.cuda(), lengths.cuda()).cpu()
+    ref_emb = proteinfer_embeddings(sd, x, lengths, ecfg, "sequence_encoder.")
+    ref_logits = proteinfer_logits(sd, x, lengths, ecfg, "sequence_encoder.")
+    assert (emb - ref_emb).abs().max().item() <= 2e-5
+    assert (enc_logits - ref_logits).abs().max().item() <= 2e-5
+
+
+def test_headline_shape_spot_check():
+    """BASELINE.json's shape (1024 aa x 32768 label rows, published architecture) on a slice of the protein axis: a random
+    subset of the [B, L] logits must equal the oracle's scores of exactly those (protein, label) pairs."""
+    ecfg, scfg = EncoderCfg(), ScorerCfg()
+    sd = synth_state_dict(ecfg, scfg, seed=46, calib_T=256)
+    B, T, L = 24, 1024, 32768
+    onehots, lengths, labels = synth_inputs(B, T, L, ecfg, scfg, ragged=True, seed=99)
+    model = build_b200_model(ecfg, scfg, sd)
+    got = run(model, onehots, lengths, labels)
+    assert got.shape == (B, L) and torch.isfinite(got).all()
+    gen = torch.Generator().manual_seed(5)
+    rows = torch.tensor([0, 7, 23])
+    cols = torch.cat([torch.tensor([0, 127, 128, L - 1]), torch.randint(0, L, (28,), generator=gen)])
+    torch.set_num_threads(8)
+    ref = protnote_forward(sd, onehots[rows], lengths[rows], labels[cols], ecfg, scfg)
+    sub = got[rows][:, cols]
+    assert (sub - ref).abs().max().item() <= TOL
+    # top-k identity on the full label axis for one protein, against the oracle on the labels that matter
+    top = got[0].topk(10).indices
+    ref_top = protnote_forward(sd, onehots[:1], lengths[:1], labels[top], ecfg, scfg)[0]
+    assert (got[0, top] - ref_top).abs().max().item() <= TOL
