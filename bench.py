@@ -287,7 +287,15 @@ def run_ours(args, rank, world, local_rank):
         "clocks": clocks,
         "roofline": {"kernel": "pn::gemm_kernel<32,3> (pair-scorer output-MLP layers 2 and 3)" if passes == 3
                      else "pn::gemm_kernel<64,1>", "bound": "tensor", "achieved": achieved, "peak": peak,
-                     "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": None,
+                     "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
+                     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full`
+                     # capture (profiles/r01_ncu_full_gemm_scorer_encoder.txt): 31.5 KB/row for the layer that stores its
+                     # activations, 13.2 KB/row for the dot-epilogue layer -> 22.4 KB per row per launch on average;
+                     # algorithmic: 12 KB/row of A planes read (+12 KB/row written by the storing layer) = 18 KB/row
+                     "traffic": (22.4e3 * gemm_flops / (2.0 * 3072 * 3072) / gemm_launches) if gemm_launches else None,
+                     "traffic_unit": "bytes per launch (ncu dram bytes, scaled by the rows of the timed launches)",
+                     "algorithmic_bytes_per_launch": (18.0e3 * gemm_flops / (2.0 * 3072 * 3072) / gemm_launches)
+                     if gemm_launches else None,
                      "peak_source": peak_src, "launches": int(gemm_launches),
                      "avg_launch_ms": gemm_ms / gemm_launches if gemm_launches else None,
                      "share_of_step": gemm_ms / (ms_step * args.steps) if ms_step > 0 else None,

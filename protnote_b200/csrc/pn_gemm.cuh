@@ -43,8 +43,8 @@ constexpr int kBM = 128;          // accumulator rows per tile (UMMA M)
 constexpr int kMaxBN = 256;       // accumulator columns per tile (UMMA N), runtime bn <= kMaxBN
 constexpr int kGemmThreads = 384; // 4 control warps + 8 epilogue warps
 constexpr int kSmemBudget = 200 * 1024;
-constexpr int kCtrlRegs = 40;     // setmaxnreg targets: 128*40 + 256*232 = 64512 <= 65536
-constexpr int kEpiRegs = 232;
+constexpr int kCtrlRegs = 24;     // setmaxnreg: 128*24 + 256*240 = 64512 = the 384*168 registers the CTA owns at launch
+constexpr int kEpiRegs = 240;
 
 struct alignas(64) GemmParams {
   CUtensorMap tm_a_hi, tm_a_lo, tm_b_hi, tm_b_lo;
@@ -450,19 +450,42 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
         for (int chunk = 0; chunk < num_chunks; ++chunk) {
           mbar_wait(tfull_bar(acc), acc_phase);
           tc_fence_after();
+          // Drain this warp's (up to four) 32-column groups two at a time; the TMEM buffer is handed back to the MMA
+          // issuer as soon as the last load has landed in registers, BEFORE the additions, so the round trip
+          // commit -> drain -> release that bounds short chunks stays as short as possible.
+          const uint32_t t_addr = tmem_base + acc * kMaxBN + g_lo * 32 + ((uint32_t)(q * 32) << 16);
+          const int ng = g_hi - g_lo;   // warp-uniform
+          uint32_t v0[32], v1[32];
+          if (ng > 0) tmem_ld32(t_addr, v0);
+          if (ng > 1) tmem_ld32(t_addr + 32, v1);
+          tmem_ld_wait();
+          if (ng <= 2) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+          }
+          if (ng > 0) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            if (g_lo + g < g_hi) {   // warp-uniform
-              uint32_t v[32];
-              tmem_ld32(tmem_base + acc * kMaxBN + (g_lo + g) * 32 + ((uint32_t)(q * 32) << 16), v);
-              tmem_ld_wait();
+            for (int j = 0; j < 32; ++j) sums[0][j] += __uint_as_float(v0[j]);
+          }
+          if (ng > 1) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) sums[g][j] += __uint_as_float(v[j]);
+            for (int j = 0; j < 32; ++j) sums[1][j] += __uint_as_float(v1[j]);
+          }
+          if (ng > 2) {
+            tmem_ld32(t_addr + 64, v0);
+            if (ng > 3) tmem_ld32(t_addr + 96, v1);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sums[2][j] += __uint_as_float(v0[j]);
+            if (ng > 3) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) sums[3][j] += __uint_as_float(v1[j]);
             }
           }
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar(acc));
           if (++acc == 2) {
             acc = 0;
             acc_phase ^= 1;
