@@ -31,6 +31,7 @@ extern "C" {
 #define PN_FUSION_CONCAT 0      /* [p; t]        configs/base_config.yaml:44 (default)      */
 #define PN_FUSION_CONCAT_DIFF 1 /* [p; t; p - t] protnote/models/ProtNote.py:128-138        */
 #define PN_FUSION_CONCAT_PROD 2 /* [p; t; p * t] protnote/models/ProtNote.py:139-150        */
+#define PN_FUSION_SIMILARITY 3  /* cosine(p, t) / temperature, no output MLP (ProtNote.py:281-284) */
 
 int pn_version(void);
 /* Thread-local description of the last error on this thread ("" if none). */
@@ -105,6 +106,7 @@ typedef struct pn_scorer_cfg {
  *   W_l: same
  *   output_layer: for each hidden layer: Linear.weight, then (out_batchnorm ? BN x4 : Linear.bias);
  *                 final Linear.weight (1,H), final Linear.bias (1)
+ *   (PN_FUSION_SIMILARITY: the module has no output_layer; only the W_p and W_l parameters are passed)
  */
 int pn_scorer_num_params(const pn_scorer_cfg* cfg);
 size_t pn_scorer_packed_bytes(const pn_scorer_cfg* cfg);
@@ -131,6 +133,14 @@ size_t pn_scorer_workspace_bytes(const pn_scorer_cfg* cfg, long long B, long lon
 int pn_score_pairs(const pn_scorer_cfg* cfg, const void* packed, const float* a, const float* c, const float* P_e,
                    const float* L_e, long long B, long long L, float* logits, long long ld_logits, void* workspace,
                    size_t workspace_bytes, int mode, void* stream);
+
+/* PN_FUSION_SIMILARITY: logits[b][l/k] = <P_e[b]/|P_e[b]|, L_e[l]/|L_e[l]|> / temperature (F.normalize eps 1e-12,
+ * ProtNote.py:281-284), then the same k-row ensembling.  P_e / L_e are the fp32 embeddings returned by the two
+ * projection calls (their `a` / `c` outputs may be NULL for this fusion). */
+size_t pn_similarity_workspace_bytes(const pn_scorer_cfg* cfg, long long B, long long L);
+int pn_score_similarity(const pn_scorer_cfg* cfg, const float* P_e, const float* L_e, long long B, long long L,
+                        float temperature, float* logits, long long ld_logits, void* workspace, size_t workspace_bytes,
+                        int mode, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Plain dense layer on the same engine: y[M][N] = x[M][K] * w[N][K]^T + bias   (ProteInfer.output_layer,

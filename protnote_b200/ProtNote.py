@@ -149,6 +149,8 @@ class ProtNote(nn.Module):
 
     def _pack_sources(self):
         srcs = self._head_sources(self.W_p) + self._head_sources(self.W_l)
+        if self.feature_fusion == "similarity":
+            return srcs
         mods = list(self.output_layer)
         for i, m in enumerate(mods[:-1]):
             if isinstance(m, nn.Linear):
@@ -165,7 +167,8 @@ class ProtNote(nn.Module):
         srcs = self._pack_sources()
         key = _versions(srcs) + (self.feature_fusion, self.inference_descriptions_per_label)
         if self._packed is None or key != self._packed_key:
-            bn_eps = next((m.eps for m in self.output_layer if isinstance(m, nn.BatchNorm1d)), 1e-5)
+            own = [self.W_p, self.W_l] + ([self.output_layer] if hasattr(self, "output_layer") else [])
+            bn_eps = next((m.eps for part in own for m in part.modules() if isinstance(m, nn.BatchNorm1d)), 1e-5)
             sc = native.PackedScorer(fusion=self.feature_fusion,
                                      descriptions_per_label=self.inference_descriptions_per_label, bn_eps=bn_eps,
                                      **self._cfg)
@@ -196,14 +199,12 @@ class ProtNote(nn.Module):
         if self.label_embedding_pooling_method == "all":
             raise ProtnoteB200Error("LABEL_EMBEDDING_POOLING_METHOD 'all' (token-level attention pooling, "
                                     "ProtNote.py:154-166) is not on the cached-embedding path")
-        if not self.feature_fusion.startswith("concatenation"):
-            if self.feature_fusion == "similarity":
-                raise ProtnoteB200Error("FEATURE_FUSION 'similarity' has no fused kernel yet")
+        if not (self.feature_fusion.startswith("concatenation") or self.feature_fusion == "similarity"):
             raise ValueError("feature fusion method not implemented")
         if save_embeddings:
             raise ProtnoteB200Error("save_embeddings=True would materialise the [B*L, 2d] joint tensor the fused "
                                     "scorer exists to avoid; not supported")
-        dev = self.output_layer[-1].weight.device
+        dev = next(self.W_p.parameters()).device
         mode = native.MODES[self.precision]
         scorer = self._ensure_packed()
         # ---- sequence embeddings (ProtNote.py:243-264)
@@ -217,9 +218,12 @@ class ProtNote(nn.Module):
         else:
             raise ValueError("Incompatible sequence parameters passed to forward method.")
         L_f = L_f.to(dev, non_blocking=True)
-        need_emb = self.feature_fusion == "concatenation_prod"
+        need_emb = self.feature_fusion in ("concatenation_prod", "similarity")
         P_e, a = scorer.project_sequences(P_f, mode, want_embedding=need_emb)
         L_e, c = self._projected_labels(scorer, L_f, mode, need_emb)
-        logits = scorer.score(a, c, P_e, L_e, mode)
+        if self.feature_fusion == "similarity":
+            logits = scorer.score_similarity(P_e, L_e, self.temperature, mode)
+        else:
+            logits = scorer.score(a, c, P_e, L_e, mode)
         embeddings = {"output_layer_embeddings": [], "joint_embeddings": []}
         return logits, embeddings

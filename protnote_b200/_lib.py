@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(PKG_DIR, "lib", "libprotnote_b200.so")
 
 PN_STRICT = 3
 PN_FAST = 1
-FUSIONS = {"concatenation": 0, "concatenation_diff": 1, "concatenation_prod": 2}
+FUSIONS = {"concatenation": 0, "concatenation_diff": 1, "concatenation_prod": 2, "similarity": 3}
 
 
 class EncoderCfg(C.Structure):
@@ -53,6 +53,8 @@ SIGNATURES = {
     "pn_scorer_min_workspace_bytes": (_SZ, [C.POINTER(ScorerCfg)]),
     "pn_scorer_workspace_bytes": (_SZ, [C.POINTER(ScorerCfg), _LL, _LL]),
     "pn_score_pairs": (_I, [C.POINTER(ScorerCfg), _P, _P, _P, _P, _P, _LL, _LL, _P, _LL, _P, _SZ, _I, _P]),
+    "pn_similarity_workspace_bytes": (_SZ, [C.POINTER(ScorerCfg), _LL, _LL]),
+    "pn_score_similarity": (_I, [C.POINTER(ScorerCfg), _P, _P, _LL, _LL, C.c_float, _P, _LL, _P, _SZ, _I, _P]),
     "pn_linear_workspace_bytes": (_SZ, [_LL, _LL, _LL]),
     "pn_linear": (_I, [_P, _LL, _LL, _LL, _P, _LL, _P, _P, _LL, _P, _SZ, _I, _P]),
     "pn_conv1d_workspace_bytes": (_SZ, [_I, _I, _I, _I, _I]),

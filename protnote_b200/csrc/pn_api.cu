@@ -422,6 +422,10 @@ ScorerLayout scorer_layout(const pn_scorer_cfg& c) {
       in_dim = out_dim;
     }
   }
+  if (c.fusion == PN_FUSION_SIMILARITY) {
+    L.bytes = ar.off;
+    return L;
+  }
   L.l1_p = carve_linear(ar, c.out_hidden, c.latent_dim, 1);
   L.l1_l = carve_linear(ar, c.out_hidden, c.latent_dim, 1);
   if (c.fusion == PN_FUSION_CONCAT_PROD) L.l1_x = carve_linear(ar, c.out_hidden, c.latent_dim, 1);
@@ -436,11 +440,12 @@ ScorerLayout scorer_layout(const pn_scorer_cfg& c) {
 
 int check_scorer_cfg(const pn_scorer_cfg* c) {
   if (!c) return fail("null scorer cfg");
-  if (c->protein_dim < 1 || c->label_dim < 1 || c->latent_dim < 1 || c->proj_hidden < 1 || c->out_hidden < 1)
+  if (c->protein_dim < 1 || c->label_dim < 1 || c->latent_dim < 1 || c->proj_hidden < 1 ||
+      (c->fusion != PN_FUSION_SIMILARITY && c->out_hidden < 1))
     return fail("bad scorer dims");
   if (c->proj_layers < 1) return fail("proj_layers must be >= 1");
-  if (c->out_layers < 2) return fail("out_layers must be >= 2 (got %d)", c->out_layers);
-  if (c->fusion < 0 || c->fusion > 2) return fail("unknown fusion %d", c->fusion);
+  if (c->fusion < 0 || c->fusion > 3) return fail("unknown fusion %d", c->fusion);
+  if (c->fusion != PN_FUSION_SIMILARITY && c->out_layers < 2) return fail("out_layers must be >= 2 (got %d)", c->out_layers);
   if (c->descriptions_per_label < 1) return fail("descriptions_per_label must be >= 1");
   return 0;
 }
@@ -508,6 +513,7 @@ int run_projection(const pn_scorer_cfg& c, const ScorerLayout& L, const Arena& p
       A.hi = buf_hi[cur]; A.lo = buf_lo[cur]; A.rows = rows; A.cols = pl.N; A.ld = ld_h;
       cur ^= 1;
     }
+    if (half_out == nullptr) continue;
     // half of output layer 1: protein side carries the folded BN1 shift, both sides carry its scale
     const PackedLinear& pl = protein ? L.l1_p : L.l1_l;
     Epilogue e;
@@ -735,6 +741,7 @@ int pn_encoder_forward(const pn_encoder_cfg* cfg, const void* packed, const floa
 int pn_scorer_num_params(const pn_scorer_cfg* cfg) {
   if (check_scorer_cfg(cfg)) return -1;
   const int head = 5 * (cfg->proj_layers - 1) + 1;
+  if (cfg->fusion == PN_FUSION_SIMILARITY) return 2 * head;
   const int out = cfg->out_layers * (cfg->out_batchnorm ? 5 : 2) + 2;
   return 2 * head + out;
 }
@@ -766,6 +773,7 @@ int pn_scorer_pack(const pn_scorer_cfg* cfg, const float* const* params, int num
       PN_TRY(pack_linear(pk, H[i], w, H[i].cin, 1, 0, H[i].cin, nullptr, g, bt, mu, var, c.bn_eps, stream));
     }
   }
+  if (c.fusion == PN_FUSION_SIMILARITY) return 0;
   // output layer 1: weight (H, 2d or 3d), split by column block
   const int d = c.latent_dim;
   const int in1 = c.fusion == PN_FUSION_CONCAT ? 2 * d : 3 * d;
@@ -834,6 +842,7 @@ int pn_project_sequences(const pn_scorer_cfg* cfg, const void* packed, const flo
                          float* a, void* workspace, size_t workspace_bytes, int mode, void* stream) {
   PN_TRY(check_scorer_cfg(cfg));
   if (n <= 0) return fail("no sequences to project");
+  if (a == nullptr && cfg->fusion != PN_FUSION_SIMILARITY) return fail("the layer-1 half output is required for this fusion");
   const ScorerLayout L = scorer_layout(*cfg);
   Arena pk(const_cast<void*>(packed), L.bytes);
   return run_projection(*cfg, L, pk, true, P_f, n, P_e, a, workspace, workspace_bytes, mode,
@@ -844,6 +853,7 @@ int pn_project_labels(const pn_scorer_cfg* cfg, const void* packed, const float*
                       float* c_out, void* workspace, size_t workspace_bytes, int mode, void* stream) {
   PN_TRY(check_scorer_cfg(cfg));
   if (n <= 0) return fail("no label rows to project");
+  if (c_out == nullptr && cfg->fusion != PN_FUSION_SIMILARITY) return fail("the layer-1 half output is required for this fusion");
   const ScorerLayout L = scorer_layout(*cfg);
   Arena pk(const_cast<void*>(packed), L.bytes);
   return run_projection(*cfg, L, pk, false, L_f, n, L_e, c_out, workspace, workspace_bytes, mode,
@@ -873,6 +883,7 @@ int pn_score_pairs(const pn_scorer_cfg* cfg, const void* packed, const float* a,
   const pn_scorer_cfg& c = *cfg;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int k = c.descriptions_per_label;
+  if (c.fusion == PN_FUSION_SIMILARITY) return fail("use pn_score_similarity for PN_FUSION_SIMILARITY");
   if (B <= 0 || Lrows <= 0) return fail("empty scorer input (B %lld, L %lld)", B, Lrows);
   if (Lrows % k != 0) return fail("label rows (%lld) not a multiple of descriptions_per_label (%d)", Lrows, k);
   if (c.fusion == PN_FUSION_CONCAT_PROD && (P_e == nullptr || L_e == nullptr))
@@ -955,6 +966,56 @@ int pn_score_pairs(const pn_scorer_cfg* cfg, const void* packed, const float* a,
       g_launches++;
       PN_CUDA(cudaGetLastError());
     }
+  }
+  return 0;
+}
+
+size_t pn_similarity_workspace_bytes(const pn_scorer_cfg* cfg, long long B, long long L) {
+  if (check_scorer_cfg(cfg)) return 0;
+  const long long ld = round_up(cfg->latent_dim, 64);
+  return (size_t)((round_up(B, kBM) + L) * ld * 4 + L * 4 + (cfg->descriptions_per_label > 1 ? B * L * 4 : 0) + 16384);
+}
+
+int pn_score_similarity(const pn_scorer_cfg* cfg, const float* P_e, const float* L_e, long long B, long long Lrows,
+                        float temperature, float* logits, long long ld_logits, void* workspace, size_t workspace_bytes,
+                        int mode, void* stream_) {
+  PN_TRY(check_scorer_cfg(cfg));
+  const pn_scorer_cfg& c = *cfg;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int k = c.descriptions_per_label;
+  if (B <= 0 || Lrows <= 0) return fail("empty scorer input (B %lld, L %lld)", B, Lrows);
+  if (Lrows % k != 0) return fail("label rows (%lld) not a multiple of descriptions_per_label (%d)", Lrows, k);
+  if (!(temperature > 0.f)) return fail("temperature must be positive");
+  if (workspace_bytes < pn_similarity_workspace_bytes(cfg, B, Lrows)) return fail("similarity workspace too small");
+  const int d = c.latent_dim;
+  const int ld = (int)round_up(d, 64);
+  Arena ws(workspace, workspace_bytes);
+  __half* p_hi = ws.at<__half>(ws.take((size_t)B * ld * 2));
+  __half* p_lo = ws.at<__half>(ws.take((size_t)B * ld * 2));
+  __half* l_hi = ws.at<__half>(ws.take((size_t)Lrows * ld * 2));
+  __half* l_lo = ws.at<__half>(ws.take((size_t)Lrows * ld * 2));
+  float* scale = ws.at<float>(ws.take((size_t)Lrows * 4));
+  float* raw = k > 1 ? ws.at<float>(ws.take((size_t)B * Lrows * 4)) : logits;
+  if (!ws.ok()) return fail("similarity workspace accounting error");
+  const float pow2 = 128.f;   // keeps the lo planes of unit vectors in fp16's normal range; undone in the epilogue
+  normalize_split_kernel<<<(int)((B * 32 + 255) / 256), 256, 0, stream>>>(P_e, B, d, pow2, p_hi, p_lo, ld);
+  normalize_split_kernel<<<(int)((Lrows * 32 + 255) / 256), 256, 0, stream>>>(L_e, Lrows, d, pow2, l_hi, l_lo, ld);
+  fill_kernel<<<ew_grid(Lrows), 256, 0, stream>>>(scale, Lrows, 1.f / (pow2 * pow2) / temperature);
+  g_launches += 3;
+  PN_CUDA(cudaGetLastError());
+  Planes A, Bm;
+  A.hi = p_hi; A.lo = p_lo; A.rows = B; A.cols = d; A.ld = ld;
+  Bm.hi = l_hi; Bm.lo = l_lo; Bm.rows = Lrows; Bm.cols = d; Bm.ld = ld;
+  Epilogue e;
+  e.scale = scale;
+  e.out_f32 = raw;
+  e.ld_out = k > 1 ? Lrows : ld_logits;
+  PN_TRY(launch_gemm(A, ConvView(), Bm, Lrows, e, mode, stream, kStageHeads));
+  if (k > 1) {
+    finalize_logits_kernel<<<ew_grid(B * Lrows / k), 256, 0, stream>>>(raw, 1, nullptr, 0, 0, (int)Lrows, B * Lrows, k, logits,
+                                                                     ld_logits);
+    g_launches++;
+    PN_CUDA(cudaGetLastError());
   }
   return 0;
 }

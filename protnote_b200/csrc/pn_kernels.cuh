@@ -181,6 +181,32 @@ __global__ void pair_product_kernel(const float* __restrict__ p, long long ldp, 
   }
 }
 
+// F.normalize(x, dim=-1, p=2) (eps 1e-12) of every row, times a power of two, as fp16 planes (one warp per row).
+// Used by the 'similarity' fusion (ProtNote.py:281-284).
+__global__ void normalize_split_kernel(const float* __restrict__ x, long long n, int d, float pow2,
+                                       __half* __restrict__ hi, __half* __restrict__ lo, int ld) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  if (row >= n) return;
+  const float* xr = x + row * d;
+  float ss = 0.f;
+  for (int k = lane; k < d; k += 32) ss = fmaf(xr[k], xr[k], ss);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float denom = fmaxf(sqrtf(ss), 1e-12f);
+  for (int k = lane; k < ld; k += 32) {
+    __half h, l;
+    split_f16(k < d ? xr[k] / denom * pow2 : 0.f, h, l);
+    hi[row * ld + k] = h;
+    if (lo) lo[row * ld + k] = l;
+  }
+}
+
+__global__ void fill_kernel(float* __restrict__ dst, long long n, float v) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = v;
+}
+
 // ------------------------------------------------------------------------------------------------
 // reductions at the two ends of the path
 // ------------------------------------------------------------------------------------------------

@@ -152,8 +152,9 @@ class PackedScorer:
         dev = self.packed.device
         x = _f32c(x)
         n = x.shape[0]
-        emb = torch.empty(n, self.cfg.latent_dim, dtype=torch.float32, device=dev) if want_embedding else None
-        half = torch.empty(n, self.cfg.out_hidden, dtype=torch.float32, device=dev)
+        similarity = self.cfg.fusion == _lib.FUSIONS["similarity"]
+        emb = torch.empty(n, self.cfg.latent_dim, dtype=torch.float32, device=dev) if (want_embedding or similarity) else None
+        half = None if similarity else torch.empty(n, self.cfg.out_hidden, dtype=torch.float32, device=dev)
         if n == 0:
             return emb, half
         rows = min(n, 1 << 15)
@@ -193,6 +194,26 @@ class PackedScorer:
             check(self.lib.pn_score_pairs(C.byref(self.cfg), ptr(self.packed), ptr(a), ptr(c), ptr(P_e), ptr(L_e), B, L,
                                           ptr(out), out.stride(0), ptr(ws), ws.numel(), mode, stream_ptr()))
         return out
+
+
+def _score_similarity(self, P_e: torch.Tensor, L_e: torch.Tensor, temperature: float, mode: int = PN_STRICT):
+    """cosine similarity / temperature for every pair, [B, L / k] fp32 (ProtNote.py:281-284)."""
+    dev = self.packed.device
+    B, L = P_e.shape[0], L_e.shape[0]
+    k = self.cfg.descriptions_per_label
+    if L % k != 0:
+        raise ValueError(f"{L} label rows is not a multiple of inference_descriptions_per_label={k}")
+    out = torch.empty(B, L // k, dtype=torch.float32, device=dev)
+    if B == 0 or L == 0:
+        return out
+    ws = scratch(dev, "similarity", self.lib.pn_similarity_workspace_bytes(C.byref(self.cfg), B, L))
+    with torch.cuda.device(dev):
+        check(self.lib.pn_score_similarity(C.byref(self.cfg), ptr(P_e), ptr(L_e), B, L, C.c_float(temperature), ptr(out),
+                                           out.stride(0), ptr(ws), ws.numel(), mode, stream_ptr()))
+    return out
+
+
+PackedScorer.score_similarity = _score_similarity
 
 
 def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], mode: int = PN_STRICT) -> torch.Tensor:

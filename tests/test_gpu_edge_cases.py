@@ -131,3 +131,16 @@ def test_headline_shape_spot_check():
     top = got[0].topk(10).indices
     ref_top = protnote_forward(sd, onehots[:1], lengths[:1], labels[top], ecfg, scfg)[0]
     assert (got[0, top] - ref_top).abs().max().item() <= TOL
+
+
+@pytest.mark.parametrize("k", [1, 2])
+def test_similarity_fusion_against_oracle(k):
+    """FEATURE_FUSION 'similarity' (ProtNote.py:281-284): cosine of the projected embeddings / temperature."""
+    scfg = dataclasses.replace(TINY_S, feature_fusion="similarity", inference_descriptions_per_label=k, temperature=0.07)
+    sd = synth_state_dict(TINY_E, scfg, seed=31 + k)
+    onehots, lengths, labels = synth_inputs(5, 90, 26, TINY_E, scfg, ragged=True, seed=77)
+    model = build_b200_model(TINY_E, scfg, sd)
+    got = run(model, onehots, lengths, labels)
+    ref = protnote_forward(sd, onehots, lengths, labels, TINY_E, scfg)
+    assert got.shape == ref.shape == (5, 26 // k)
+    assert (got - ref).abs().max().item() <= TOL
