@@ -134,6 +134,13 @@ int pn_score_pairs(const pn_scorer_cfg* cfg, const void* packed, const float* a,
                    const float* L_e, long long B, long long L, float* logits, long long ld_logits, void* workspace,
                    size_t workspace_bytes, int mode, void* stream);
 
+/* Same, and additionally stores the last hidden layer's activations relu(BN(z_n)) for every pair, fp32
+ * [B*L][out_hidden] in pair order b*L + l (the "output_layer_embeddings" of ProtNote.forward(save_embeddings=True),
+ * ProtNote.py:294-303).  hidden_out may be NULL. */
+int pn_score_pairs_ex(const pn_scorer_cfg* cfg, const void* packed, const float* a, const float* c, const float* P_e,
+                      const float* L_e, long long B, long long L, float* logits, long long ld_logits, float* hidden_out,
+                      void* workspace, size_t workspace_bytes, int mode, void* stream);
+
 /* PN_FUSION_SIMILARITY: logits[b][l/k] = <P_e[b]/|P_e[b]|, L_e[l]/|L_e[l]|> / temperature (F.normalize eps 1e-12,
  * ProtNote.py:281-284), then the same k-row ensembling.  P_e / L_e are the fp32 embeddings returned by the two
  * projection calls (their `a` / `c` outputs may be NULL for this fusion). */

@@ -201,9 +201,6 @@ class ProtNote(nn.Module):
                                     "ProtNote.py:154-166) is not on the cached-embedding path")
         if not (self.feature_fusion.startswith("concatenation") or self.feature_fusion == "similarity"):
             raise ValueError("feature fusion method not implemented")
-        if save_embeddings:
-            raise ProtnoteB200Error("save_embeddings=True would materialise the [B*L, 2d] joint tensor the fused "
-                                    "scorer exists to avoid; not supported")
         dev = next(self.W_p.parameters()).device
         mode = native.MODES[self.precision]
         scorer = self._ensure_packed()
@@ -218,12 +215,28 @@ class ProtNote(nn.Module):
         else:
             raise ValueError("Incompatible sequence parameters passed to forward method.")
         L_f = L_f.to(dev, non_blocking=True)
-        need_emb = self.feature_fusion in ("concatenation_prod", "similarity")
+        need_emb = self.feature_fusion in ("concatenation_prod", "similarity") or save_embeddings
         P_e, a = scorer.project_sequences(P_f, mode, want_embedding=need_emb)
         L_e, c = self._projected_labels(scorer, L_f, mode, need_emb)
+        embeddings = {"output_layer_embeddings": [], "joint_embeddings": []}
         if self.feature_fusion == "similarity":
             logits = scorer.score_similarity(P_e, L_e, self.temperature, mode)
-        else:
+        elif not save_embeddings:
             logits = scorer.score(a, c, P_e, L_e, mode)
-        embeddings = {"output_layer_embeddings": [], "joint_embeddings": []}
+        else:
+            # Diagnostics contract of the reference (ProtNote.py:294-303,324-334): the joint features and the last hidden
+            # layer for every pair, on the CPU.  The hidden layer comes out of the scorer kernel's epilogue; the joint
+            # tensor is a pure gather of P_e / L_e rows (it is only materialised here, never on the scoring path).
+            B, L = P_e.shape[0], L_e.shape[0]
+            hidden = torch.empty(B * L, self._cfg["out_hidden"], dtype=torch.float32, device=dev)
+            logits = scorer.score(a, c, P_e, L_e, mode, hidden_out=hidden)
+            p = P_e[:, None, :].expand(B, L, P_e.shape[1])
+            t = L_e[None, :, :].expand(B, L, L_e.shape[1])
+            parts = [p, t]
+            if self.feature_fusion == "concatenation_diff":
+                parts.append(p - t)
+            elif self.feature_fusion == "concatenation_prod":
+                parts.append(p * t)
+            embeddings["joint_embeddings"] = torch.cat(parts, dim=2).reshape(B * L, -1).detach().cpu()
+            embeddings["output_layer_embeddings"] = hidden.cpu()
         return logits, embeddings

@@ -53,6 +53,7 @@ SIGNATURES = {
     "pn_scorer_min_workspace_bytes": (_SZ, [C.POINTER(ScorerCfg)]),
     "pn_scorer_workspace_bytes": (_SZ, [C.POINTER(ScorerCfg), _LL, _LL]),
     "pn_score_pairs": (_I, [C.POINTER(ScorerCfg), _P, _P, _P, _P, _P, _LL, _LL, _P, _LL, _P, _SZ, _I, _P]),
+    "pn_score_pairs_ex": (_I, [C.POINTER(ScorerCfg), _P, _P, _P, _P, _P, _LL, _LL, _P, _LL, _P, _P, _SZ, _I, _P]),
     "pn_similarity_workspace_bytes": (_SZ, [C.POINTER(ScorerCfg), _LL, _LL]),
     "pn_score_similarity": (_I, [C.POINTER(ScorerCfg), _P, _P, _LL, _LL, C.c_float, _P, _LL, _P, _SZ, _I, _P]),
     "pn_linear_workspace_bytes": (_SZ, [_LL, _LL, _LL]),

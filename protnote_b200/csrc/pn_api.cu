@@ -114,6 +114,7 @@ struct Epilogue {
   const float* scale = nullptr; const float* shift = nullptr;
   const float* resid = nullptr; long long ld_resid = 0;
   float* out_f32 = nullptr; long long ld_out = 0;
+  float* out_z = nullptr; long long ld_z = 0;
   const float* scale2 = nullptr; const float* shift2 = nullptr;
   int relu = 0;
   __half* out_hi = nullptr; __half* out_lo = nullptr; long long ld_split = 0;
@@ -242,6 +243,7 @@ int launch_gemm(const Planes& A, const ConvView& cv, const Planes& B, long long 
   p.scale = e.scale; p.shift = e.shift;
   p.resid = e.resid; p.ld_resid = e.ld_resid;
   p.out_f32 = e.out_f32; p.ld_out = e.ld_out;
+  p.out_z = e.out_z; p.ld_z = e.ld_z;
   p.scale2 = e.scale2; p.shift2 = e.shift2;
   p.relu = e.relu;
   p.out_hi = e.out_hi; p.out_lo = need_lo ? e.out_lo : nullptr; p.ld_split = e.ld_split;
@@ -251,6 +253,7 @@ int launch_gemm(const Planes& A, const ConvView& cv, const Planes& B, long long 
   p.add_l = e.add_l; p.ld_add_l = e.ld_add_l;
   auto aligned16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   p.vec_out = e.out_f32 && aligned16(e.out_f32) && e.ld_out % 4 == 0;
+  p.vec_z = e.out_z && aligned16(e.out_z) && e.ld_z % 4 == 0;
   p.vec_resid = e.resid && aligned16(e.resid) && e.ld_resid % 4 == 0;
   p.vec_split = e.out_hi && aligned16(e.out_hi) && (!p.out_lo || aligned16(p.out_lo)) && e.ld_split % 8 == 0;
   if (bk == 32) return mode == PN_STRICT ? launch_gemm_t<32, 3>(p, stream) : launch_gemm_t<32, 1>(p, stream);
@@ -879,6 +882,13 @@ size_t pn_scorer_workspace_bytes(const pn_scorer_cfg* cfg, long long B, long lon
 int pn_score_pairs(const pn_scorer_cfg* cfg, const void* packed, const float* a, const float* c_in, const float* P_e,
                    const float* L_e, long long B, long long Lrows, float* logits, long long ld_logits, void* workspace,
                    size_t workspace_bytes, int mode, void* stream_) {
+  return pn_score_pairs_ex(cfg, packed, a, c_in, P_e, L_e, B, Lrows, logits, ld_logits, nullptr, workspace, workspace_bytes,
+                           mode, stream_);
+}
+
+int pn_score_pairs_ex(const pn_scorer_cfg* cfg, const void* packed, const float* a, const float* c_in, const float* P_e,
+                      const float* L_e, long long B, long long Lrows, float* logits, long long ld_logits,
+                      float* hidden_out, void* workspace, size_t workspace_bytes, int mode, void* stream_) {
   PN_TRY(check_scorer_cfg(cfg));
   const pn_scorer_cfg& c = *cfg;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -955,6 +965,11 @@ int pn_score_pairs(const pn_scorer_cfg* cfg, const void* packed, const float* a,
         if (last) {
           e.dot_w = pk.at<float>(L.w_out);
           e.dot_out = partial;
+          if (hidden_out) {   // output_layer_embeddings of save_embeddings=True: rows in pair order (b*L + l)
+            if (nl != Lrows) return fail("hidden_out needs a workspace that holds whole proteins (L rows) per chunk");
+            e.out_z = hidden_out + b0 * Lrows * H;
+            e.ld_z = H;
+          }
         } else {
           e.out_hi = buf_hi[cur ^ 1]; e.out_lo = buf_lo[cur ^ 1]; e.ld_split = ld_h;
         }

@@ -64,11 +64,13 @@ struct alignas(64) GemmParams {
   const float* scale; const float* shift;   // [N] (nullable -> 1 / 0)
   const float* resid; long long ld_resid;   // fp32 [M][ld] (nullable)
   float* out_f32; long long ld_out;         // y stored here (nullable)
+  float* out_z; long long ld_z;             // z stored here as fp32 (nullable)
   // z = relu?(y*scale2 + shift2) ; masked rows -> 0
   const float* scale2; const float* shift2; // [N] (nullable)
   int relu;
   __half* out_hi; __half* out_lo; long long ld_split;   // z as fp16 planes (nullable; out_lo nullable)
   const float* dot_w; float* dot_out;       // dot_out[(row*tiles_n + n_tile)*2 + half] = sum_n z*dot_w[n] (nullable)
+  int vec_z;
   int vec_out, vec_resid, vec_split;        // 16-byte vector access is legal for that tensor (host-checked)
   double timed_flops;                       // host-side bookkeeping only (algorithmic FLOPs of this launch)
 };
@@ -190,7 +192,7 @@ __device__ __forceinline__ void epilogue_group(const GemmParams& p, const EpiCon
         if (n0 + j < p.N) op[j] = y[j];
     }
   }
-  if (p.out_hi || p.dot_w) {
+  if (p.out_hi || p.dot_w || p.out_z) {
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
       if (p.scale2) {
@@ -212,6 +214,18 @@ __device__ __forceinline__ void epilogue_group(const GemmParams& p, const EpiCon
         dot = fmaf(y[j + 1], w4.y, dot);
         dot = fmaf(y[j + 2], w4.z, dot);
         dot = fmaf(y[j + 3], w4.w, dot);
+      }
+    }
+    if (p.out_z && ((row_mask >> lane) & 1u)) {
+      float* zp = p.out_z + row * p.ld_z + n0;
+      if (full && p.vec_z) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(zp + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (n0 + j < p.N) zp[j] = y[j];
       }
     }
     if (p.out_hi) {

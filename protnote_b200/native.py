@@ -176,8 +176,8 @@ class PackedScorer:
 
     def score(self, a: torch.Tensor, c: torch.Tensor, P_e: Optional[torch.Tensor] = None,
               L_e: Optional[torch.Tensor] = None, mode: int = PN_STRICT, out: Optional[torch.Tensor] = None,
-              max_workspace_bytes: int = 8 << 30) -> torch.Tensor:
-        """a [B, H], c [L, H] -> logits [B, L / k] fp32"""
+              max_workspace_bytes: int = 8 << 30, hidden_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """a [B, H], c [L, H] -> logits [B, L / k] fp32; hidden_out [B*L, H] optionally receives the last hidden layer"""
         dev = self.packed.device
         B, L = a.shape[0], c.shape[0]
         k = self.cfg.descriptions_per_label
@@ -191,8 +191,9 @@ class PackedScorer:
         floor = self.lib.pn_scorer_min_workspace_bytes(C.byref(self.cfg))
         ws = scratch(dev, "scorer", max(min(need, max_workspace_bytes), floor))
         with torch.cuda.device(dev):
-            check(self.lib.pn_score_pairs(C.byref(self.cfg), ptr(self.packed), ptr(a), ptr(c), ptr(P_e), ptr(L_e), B, L,
-                                          ptr(out), out.stride(0), ptr(ws), ws.numel(), mode, stream_ptr()))
+            check(self.lib.pn_score_pairs_ex(C.byref(self.cfg), ptr(self.packed), ptr(a), ptr(c), ptr(P_e), ptr(L_e), B, L,
+                                             ptr(out), out.stride(0), ptr(hidden_out), ptr(ws), ws.numel(), mode,
+                                             stream_ptr()))
         return out
 
 

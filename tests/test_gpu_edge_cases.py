@@ -144,3 +144,26 @@ def test_similarity_fusion_against_oracle(k):
     ref = protnote_forward(sd, onehots, lengths, labels, TINY_E, scfg)
     assert got.shape == ref.shape == (5, 26 // k)
     assert (got - ref).abs().max().item() <= TOL
+
+
+def test_save_embeddings_contract():
+    """forward(save_embeddings=True) returns the joint features and the last hidden layer of every pair on the CPU
+    (ProtNote.py:294-303,324-334) and the same logits as the plain call."""
+    from oracle.protnote_oracle import joint_features, output_mlp, projection_head
+    ecfg, scfg, sd, onehots, lengths, labels, g = load_case("tiny_prod")
+    model = build_b200_model(ecfg, scfg, sd)
+    with torch.no_grad():
+        plain, empty = model(sequence_onehots=onehots.cuda(), sequence_lengths=lengths.cuda(), label_embeddings=labels.cuda())
+        logits, emb = model(sequence_onehots=onehots.cuda(), sequence_lengths=lengths.cuda(), label_embeddings=labels.cuda(),
+                            save_embeddings=True)
+    assert empty == {"output_layer_embeddings": [], "joint_embeddings": []}
+    assert torch.equal(plain, logits)
+    P_f = proteinfer_embeddings(sd, onehots, lengths, ecfg, "sequence_encoder.")
+    P_e = projection_head(sd, "W_p", P_f, scfg, torch.float32)
+    L_e = projection_head(sd, "W_l", labels, scfg, torch.float32)
+    joint = joint_features(P_e, L_e, scfg.feature_fusion)
+    hidden = output_mlp(sd, "output_layer", joint, scfg, torch.float32, return_hidden=True)
+    assert emb["joint_embeddings"].device.type == "cpu" and emb["joint_embeddings"].shape == joint.shape
+    assert (emb["joint_embeddings"] - joint).abs().max().item() <= 2e-5
+    assert emb["output_layer_embeddings"].shape == hidden.shape
+    assert (emb["output_layer_embeddings"] - hidden).abs().max().item() <= 1e-4
