@@ -20,6 +20,11 @@ thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
 int g_bk_option = 0;             // 0 = auto (strict: 32, fast: 64)
 long long g_chunk_rows = 0;      // 0 = auto
+// 1: build layer 1 of the pair scorer inside the first GEMM's operand producer (no HBM round trip of h1).
+// Measured on B200 (profiles/r01_fused_generator_probe.txt): correct, but 18 % SLOWER than the separate kernel, because
+// the generator's extra shared-memory traffic (+32 KB per k-block on top of ~120 KB) competes with the tensor core's
+// operand reads; it needs the 2-CTA operand sharing planned for the next round to pay off.  Off by default.
+int g_fuse_features = 0;
 // strict mode: K elements accumulated in TMEM between fp32 promotions, per stage of the path
 enum { kStageEncoder = 0, kStageHeads = 1, kStageScorer = 2, kStageOther = 3 };
 int g_promote_k[4] = {32, 32, 256, 64};
@@ -75,7 +80,7 @@ int resolve_encode() {
 
 // fp16 tensor, dims fastest-first.  strides_bytes[i] = stride of dim i+1.
 int make_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-             const cuuint32_t* box, int swizzle_bytes) {
+             const cuuint32_t* box, int swizzle_bytes, CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_FLOAT16) {
   PN_TRY(resolve_encode());
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   const CUtensorMapSwizzle sw = swizzle_bytes == 128  ? CU_TENSOR_MAP_SWIZZLE_128B
@@ -84,7 +89,7 @@ int make_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dim
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return fail("TMA base %p not 16-byte aligned", base);
   for (int i = 0; i + 1 < rank; ++i)
     if (strides_bytes[i] % 16 != 0) return fail("TMA stride %llu not a multiple of 16", (unsigned long long)strides_bytes[i]);
-  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims,
+  CUresult r = g_encode(map, dtype, (cuuint32_t)rank, const_cast<void*>(base), dims,
                         strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
@@ -122,6 +127,9 @@ struct Epilogue {
   int pair_nl = 0;
   const float* add_p = nullptr; long long ld_add_p = 0;
   const float* add_l = nullptr; long long ld_add_l = 0;
+  // fused pair-feature A operand (A.hi may be null then): relu(gen_a[r / pair_nl] + gen_c[r % pair_nl])
+  const float* gen_a = nullptr; long long ld_gen_a = 0;
+  const float* gen_c = nullptr; long long ld_gen_c = 0;
 };
 
 int choose_bn(long long N) {
@@ -157,12 +165,12 @@ int num_sms() {
   return g_num_sms;
 }
 
-template <int BK, int NPASS>
+template <int BK, int NPASS, bool GEN = false>
 int launch_gemm_t(const GemmParams& p, cudaStream_t stream) {
-  using Cfg = GemmCfg<BK, NPASS>;
+  using Cfg = GemmCfg<BK, NPASS, GEN>;
   static bool configured = false;
   if (!configured) {
-    PN_CUDA(cudaFuncSetAttribute(gemm_kernel<BK, NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    PN_CUDA(cudaFuncSetAttribute(gemm_kernel<BK, NPASS, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured = true;
   }
   const int total = p.tiles_m * p.tiles_n;
@@ -175,7 +183,7 @@ int launch_gemm_t(const GemmParams& p, cudaStream_t stream) {
     tl.flops = p.timed_flops;
     PN_CUDA(cudaEventRecord(tl.start, stream));
   }
-  gemm_kernel<BK, NPASS><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(p);
+  gemm_kernel<BK, NPASS, GEN><<<grid, GEN ? kGenThreads : kGemmThreads, Cfg::kSmemBytes, stream>>>(p);
   PN_CUDA(cudaGetLastError());
   if (timed) {
     PN_CUDA(cudaEventRecord(tl.stop, stream));
@@ -189,14 +197,15 @@ int launch_gemm_t(const GemmParams& p, cudaStream_t stream) {
 int launch_gemm(const Planes& A, const ConvView& cv, const Planes& B, long long N, const Epilogue& e, int mode,
                 cudaStream_t stream, int stage_kind = kStageOther) {
   if (mode != PN_STRICT && mode != PN_FAST) return fail("mode must be PN_STRICT or PN_FAST");
-  const int bk = pick_bk(mode);
+  const bool gen = e.gen_a != nullptr;
+  const int bk = gen ? 32 : pick_bk(mode);
   GemmParams p;
   memset(&p, 0, sizeof(p));
   p.N = (int)N;
   p.bn = choose_bn(N);
   p.tiles_n = (int)((N + p.bn - 1) / p.bn);
   const bool need_lo = mode == PN_STRICT;
-  if (need_lo && (A.lo == nullptr || B.lo == nullptr)) return fail("strict mode needs lo planes");
+  if (need_lo && ((!gen && A.lo == nullptr) || B.lo == nullptr)) return fail("strict mode needs lo planes");
   if (cv.taps > 0) {
     const int cblocks = (int)((A.cols + bk - 1) / bk);
     p.conv_taps = cv.taps;
@@ -218,11 +227,13 @@ int launch_gemm(const Planes& A, const ConvView& cv, const Planes& B, long long 
     p.M = (int)A.rows;
     p.tiles_m = (int)((A.rows + kBM - 1) / kBM);
     p.num_kblocks = (int)((A.cols + bk - 1) / bk);
-    const cuuint64_t dims[2] = {(cuuint64_t)A.cols, (cuuint64_t)A.rows};
-    const cuuint64_t strides[1] = {(cuuint64_t)A.ld * 2};
-    const cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)kBM};
-    PN_TRY(make_map(&p.tm_a_hi, A.hi, 2, dims, strides, box, bk * 2));
-    if (need_lo) PN_TRY(make_map(&p.tm_a_lo, A.lo, 2, dims, strides, box, bk * 2));
+    if (!gen) {
+      const cuuint64_t dims[2] = {(cuuint64_t)A.cols, (cuuint64_t)A.rows};
+      const cuuint64_t strides[1] = {(cuuint64_t)A.ld * 2};
+      const cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)kBM};
+      PN_TRY(make_map(&p.tm_a_hi, A.hi, 2, dims, strides, box, bk * 2));
+      if (need_lo) PN_TRY(make_map(&p.tm_a_lo, A.lo, 2, dims, strides, box, bk * 2));
+    }
   }
   if (A.rows >= (1LL << 31) || p.tiles_m <= 0 || p.num_kblocks <= 0) return fail("bad GEMM shape");
   p.chunk_kblocks = p.num_kblocks;
@@ -251,11 +262,23 @@ int launch_gemm(const Planes& A, const ConvView& cv, const Planes& B, long long 
   p.pair_nl = e.pair_nl;
   p.add_p = e.add_p; p.ld_add_p = e.ld_add_p;
   p.add_l = e.add_l; p.ld_add_l = e.ld_add_l;
+  p.gen_a = e.gen_a; p.ld_gen_a = e.ld_gen_a;
+  if (gen) {
+    if (e.pair_nl % kBM != 0 || A.cols % 32 != 0) return fail("generated A operand needs pair_nl %% 128 == 0 and K %% 32 == 0");
+    const cuuint64_t dims[2] = {(cuuint64_t)A.cols, (cuuint64_t)e.pair_nl};
+    const cuuint64_t strides[1] = {(cuuint64_t)e.ld_gen_c * 4};
+    const cuuint32_t box[2] = {32, (cuuint32_t)kBM};
+    PN_TRY(make_map(&p.tm_gen_c, e.gen_c, 2, dims, strides, box, 128, CU_TENSOR_MAP_DATA_TYPE_FLOAT32));
+  }
   auto aligned16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   p.vec_out = e.out_f32 && aligned16(e.out_f32) && e.ld_out % 4 == 0;
   p.vec_z = e.out_z && aligned16(e.out_z) && e.ld_z % 4 == 0;
   p.vec_resid = e.resid && aligned16(e.resid) && e.ld_resid % 4 == 0;
   p.vec_split = e.out_hi && aligned16(e.out_hi) && (!p.out_lo || aligned16(p.out_lo)) && e.ld_split % 8 == 0;
+  if (gen) {
+    if (cv.taps > 0 || e.pair_nl <= 0) return fail("generated A operand needs plain addressing and pair_nl");
+    return mode == PN_STRICT ? launch_gemm_t<32, 3, true>(p, stream) : launch_gemm_t<32, 1, true>(p, stream);
+  }
   if (bk == 32) return mode == PN_STRICT ? launch_gemm_t<32, 3>(p, stream) : launch_gemm_t<32, 1>(p, stream);
   return mode == PN_STRICT ? launch_gemm_t<64, 3>(p, stream) : launch_gemm_t<64, 1>(p, stream);
 }
@@ -602,6 +625,10 @@ int pn_set_option(const char* name, long long value) {
     }
     return 0;
   }
+  if (strcmp(name, "fuse_features") == 0) {
+    g_fuse_features = value != 0;
+    return 0;
+  }
   if (strcmp(name, "chunk_rows") == 0) {
     if (value < 0) return fail("chunk_rows must be >= 0");
     g_chunk_rows = value;
@@ -902,6 +929,9 @@ int pn_score_pairs_ex(const pn_scorer_cfg* cfg, const void* packed, const float*
   Arena pk(const_cast<void*>(packed), L.bytes);
   const int H = c.out_hidden;
   const int ld_h = (int)round_up(H, 64);
+  // the fused generator reads a / c with 16-byte loads over whole 32-wide k-blocks
+  const bool fuse_ok = g_fuse_features && c.fusion != PN_FUSION_CONCAT_PROD && H % 32 == 0 &&
+                       (reinterpret_cast<uintptr_t>(a) & 15) == 0 && (reinterpret_cast<uintptr_t>(c_in) & 15) == 0;
   const int parts = 2 * tiles_n_for(H);   // one partial dot per (N tile, column half)
   const size_t per_row = scorer_row_bytes(c);
   long long max_rows = (long long)((workspace_bytes > 8192 ? workspace_bytes - 8192 : 0) / per_row);
@@ -947,7 +977,9 @@ int pn_score_pairs_ex(const pn_scorer_cfg* cfg, const void* packed, const float*
         e.relu = 1;
         e.out_hi = buf_hi[0]; e.out_lo = buf_lo[0]; e.ld_split = ld_h;
         PN_TRY(launch_gemm(A, ConvView(), weight_planes(pk, L.l1_x), H, e, mode, stream, kStageScorer));
-      } else {
+      }
+      const bool fuse_features = fuse_ok && nl % kBM == 0;   // a tile = one protein x 128 consecutive label rows
+      if (c.fusion != PN_FUSION_CONCAT_PROD && !fuse_features) {
         pair_features_kernel<<<ew_grid(rows * (ld_h / 8)), 256, 0, stream>>>(a, H, c_in, H, (int)b0, (int)l0, (int)nl, rows,
                                                                              H, buf_hi[0], mode == PN_STRICT ? buf_lo[0] : nullptr,
                                                                              ld_h);
@@ -962,6 +994,12 @@ int pn_score_pairs_ex(const pn_scorer_cfg* cfg, const void* packed, const float*
         Epilogue e;
         e.scale = pk.at<float>(pl.scale); e.shift = pk.at<float>(pl.shift);
         e.relu = 1;
+        if (j == 0 && fuse_features) {
+          // layer 1 is built inside this GEMM's A-producer: h1 never touches HBM
+          e.pair_nl = (int)nl;
+          e.gen_a = a + b0 * H; e.ld_gen_a = H;
+          e.gen_c = c_in + l0 * H; e.ld_gen_c = H;
+        }
         if (last) {
           e.dot_w = pk.at<float>(L.w_out);
           e.dot_out = partial;

@@ -45,9 +45,14 @@ constexpr int kGemmThreads = 384; // 4 control warps + 8 epilogue warps
 constexpr int kSmemBudget = 200 * 1024;
 constexpr int kCtrlRegs = 24;     // setmaxnreg: 128*24 + 256*240 = 64512 = the 384*168 registers the CTA owns at launch
 constexpr int kEpiRegs = 240;
+// fused pair-feature variant (GEN): 4 more warps generate the A operand; 512 threads x 128 registers at launch
+constexpr int kGenThreads = 512;
+constexpr int kGenWarpRegs = 56;   // 128*24 + 128*56 + 256*216 = 65536
+constexpr int kGenEpiRegs = 216;
 
 struct alignas(64) GemmParams {
   CUtensorMap tm_a_hi, tm_a_lo, tm_b_hi, tm_b_lo;
+  CUtensorMap tm_gen_c;  // GEN: fp32 [L][H] label halves, box 32 x 128, SWIZZLE_128B
   int M, N;              // logical extents of D (conv: M = B*T rows addressed as (b,t))
   int bn;                // tile width, multiple of 32, <= 256
   int tiles_m, tiles_n;
@@ -72,6 +77,9 @@ struct alignas(64) GemmParams {
   const float* dot_w; float* dot_out;       // dot_out[(row*tiles_n + n_tile)*2 + half] = sum_n z*dot_w[n] (nullable)
   int vec_z;
   int vec_out, vec_resid, vec_split;        // 16-byte vector access is legal for that tensor (host-checked)
+  // GEN kernels only: A[r][k] = relu(gen_a[r / pair_nl][k] + gen_c[r % pair_nl][k]) is built in shared memory by the
+  // generator warps instead of being read through tm_a_* (layer 1 of the pair scorer, ProtNote.py:112-126,293)
+  const float* gen_a; long long ld_gen_a;   // protein halves [B][ld]; the label halves come through tm_gen_c
   double timed_flops;                       // host-side bookkeeping only (algorithmic FLOPs of this launch)
 };
 
@@ -84,15 +92,19 @@ constexpr int kStageRowBytes = 80;                       // 64 B of halves + 16 
 constexpr int kStageBytesPerWarp = 32 * kStageRowBytes;  // one 32x32 fp16 block per epilogue warp
 constexpr int kEpiSmemBytes = (int)sizeof(EpiConsts) + 8 * kStageBytesPerWarp;
 
-template <int BK, int NPASS>
+constexpr int kGenStages = 3;                       // GEN: depth of the fp32 label-half staging ring
+constexpr int kGenTileBytes = kBM * 32 * 4;         // GEN: one 128-row x 32-float tile of c (SWIZZLE_128B)
+
+template <int BK, int NPASS, bool GEN = false>
 struct GemmCfg {
   static constexpr int kSwizzle = BK * 2;                    // bytes per smem row
   static constexpr int kPlanes = NPASS == 3 ? 2 : 1;
   static constexpr int kATile = kBM * BK * 2;
   static constexpr int kBTile = kMaxBN * BK * 2;
   static constexpr int kStageBytes = kPlanes * (kATile + kBTile);
-  static constexpr int kStages = kSmemBudget / kStageBytes;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kEpiSmemBytes;
+  static constexpr int kGenBytes = GEN ? kGenStages * kGenTileBytes : 0;
+  static constexpr int kStages = (kSmemBudget - kGenBytes) / kStageBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kGenBytes + 1024 /*align*/ + 256 /*barriers*/ + kEpiSmemBytes;
   static_assert(kStages >= 2, "pipeline too shallow");
 };
 
@@ -114,6 +126,17 @@ __device__ __forceinline__ void reg_alloc() {
 __device__ __forceinline__ void split_pack(float a, float b, uint32_t& hi, uint32_t& lo) {
   a = fmaxf(fminf(a, 65504.f), -65504.f);
   b = fmaxf(fminf(b, 65504.f), -65504.f);
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// same for values known to be >= 0 (only the overflow clamp is needed)
+__device__ __forceinline__ void split_pack_pos(float a, float b, uint32_t& hi, uint32_t& lo) {
+  a = fminf(a, 65504.f);
+  b = fminf(b, 65504.f);
   const __half2 h = __floats2half2_rn(a, b);
   const float2 hf = __half22float2(h);
   const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
@@ -249,18 +272,21 @@ __device__ __forceinline__ void epilogue_group(const GemmParams& p, const EpiCon
   }
 }
 
-template <int BK, int NPASS>
-__global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_constant__ GemmParams p) {
-  using Cfg = GemmCfg<BK, NPASS>;
+template <int BK, int NPASS, bool GEN>
+__global__ void __launch_bounds__(GEN ? kGenThreads : kGemmThreads, 1) gemm_kernel(const __grid_constant__ GemmParams p) {
+  using Cfg = GemmCfg<BK, NPASS, GEN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
+  const uint32_t gen_base = smem_base + Cfg::kStages * Cfg::kStageBytes;   // GEN: c staging ring (1024-aligned)
+  const uint32_t bar_base = gen_base + Cfg::kGenBytes;
   // barrier layout (8 B each): full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], then tmem ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::kStages + 4);
+  auto cfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + 5 + s); };
+  auto cempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + 5 + kGenStages + s); };
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
   uint8_t* epi_smem = smem_raw + (bar_base + 256u - smem_u32(smem_raw));   // EpiConsts, then 8 warp staging blocks
@@ -272,17 +298,24 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
   const int num_chunks = (p.num_kblocks + p.chunk_kblocks - 1) / p.chunk_kblocks;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&p.tm_a_hi);
+    if (!GEN) tma_prefetch_desc(&p.tm_a_hi);
     tma_prefetch_desc(&p.tm_b_hi);
+    if (GEN) tma_prefetch_desc(&p.tm_gen_c);
     if (NPASS == 3) {
-      tma_prefetch_desc(&p.tm_a_lo);
+      if (!GEN) tma_prefetch_desc(&p.tm_a_lo);
       tma_prefetch_desc(&p.tm_b_lo);
     }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) {
-      mbar_init(full_bar(s), 1);
+      mbar_init(full_bar(s), GEN ? 3 : 1);   // TMA producer (+ one arrive per warp of the generator team)
       mbar_init(empty_bar(s), 1);
+    }
+    if (GEN) {
+      for (int s = 0; s < kGenStages; ++s) {
+        mbar_init(cfull_bar(s), 1);
+        mbar_init(cempty_bar(s), 2);   // one arrive per warp of the generator team
+      }
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
@@ -314,7 +347,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
       // ---------------------------------------------------------------- TMA producer
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t tx_bytes = Cfg::kPlanes * (Cfg::kATile + (uint32_t)p.bn * BK * 2);
+      int cs = 0;
+      uint32_t cphase = 0;
+      long long c_seq = 0, main_seq = 0;   // GEN: k-blocks whose label tile / operand stage has been issued
+      int c_tile = blockIdx.x, c_kb = 0;
+      const uint32_t tx_bytes = Cfg::kPlanes * ((GEN ? 0u : (uint32_t)Cfg::kATile) + (uint32_t)p.bn * BK * 2);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int m_tile = tile / p.tiles_n, n_tile = tile % p.tiles_n;
         if (tile_is_padding(m_tile)) continue;
@@ -336,12 +373,32 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
             kcol = tap * p.conv_cpad + kc;
             tma_load_3d(sa, &p.tm_a_hi, full_bar(stage), kc, t, seq);
             if (NPASS == 3) tma_load_3d(sa + Cfg::kATile, &p.tm_a_lo, full_bar(stage), kc, t, seq);
-          } else {
+          } else if (!GEN) {
             tma_load_2d(sa, &p.tm_a_hi, full_bar(stage), kcol, m_tile * kBM);
             if (NPASS == 3) tma_load_2d(sa + Cfg::kATile, &p.tm_a_lo, full_bar(stage), kcol, m_tile * kBM);
           }
           tma_load_2d(sb, &p.tm_b_hi, full_bar(stage), kcol, n_tile * p.bn);
           if (NPASS == 3) tma_load_2d(sb + Cfg::kBTile, &p.tm_b_lo, full_bar(stage), kcol, n_tile * p.bn);
+          if (GEN) {
+            // Label-half tiles run AHEAD of the operand stages (up to the depth of their own ring), so that the
+            // generator can start on a k-block the moment its operand stage is released.
+            while (c_seq < main_seq + kGenStages && c_tile < total_tiles) {
+              mbar_wait(cempty_bar(cs), cphase ^ 1);
+              mbar_arrive_expect_tx(cfull_bar(cs), kGenTileBytes);
+              tma_load_2d(gen_base + cs * kGenTileBytes, &p.tm_gen_c, cfull_bar(cs), c_kb * BK,
+                          (int)(((long long)(c_tile / p.tiles_n) * kBM) % p.pair_nl));
+              if (++cs == kGenStages) {
+                cs = 0;
+                cphase ^= 1;
+              }
+              ++c_seq;
+              if (++c_kb == p.num_kblocks) {
+                c_kb = 0;
+                c_tile += gridDim.x;
+              }
+            }
+            ++main_seq;
+          }
           if (++stage == Cfg::kStages) {
             stage = 0;
             phase ^= 1;
@@ -405,9 +462,81 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
         }
       }
     }
+  } else if (GEN && warp >= 12) {
+    // ------------------------------------------------------------------ A-operand generator (4 warps, GEN only)
+    // A[r][k] = relu(a[b][k] + c[l0 + r][k]) for the tile's protein b and its 128 consecutive label rows
+    // (layer 1 of the pair scorer after the exact split of Linear(2d -> H), ProtNote.py:112-126,293).
+    // The fp32 c tile arrives by TMA (SWIZZLE_128B) in a 3-deep staging ring; thread g owns tile row g: it reads its
+    // 128-byte row (conflict-free: chunk ^= row & 7), adds the protein half, applies ReLU, splits into fp16 planes
+    // and stores them in the SWIZZLE_64B layout the UMMA descriptors expect (chunk ^= (row >> 1) & 3).
+    static_assert(!GEN || BK == 32, "the generator writes the 64-byte-swizzle layout");
+    // Two teams of two warps take alternate k-blocks, so the load -> convert -> store -> publish latency of one
+    // k-block overlaps the other team's; within a team thread t owns tile rows t and t + 64.
+    reg_dealloc<kGenWarpRegs>();
+    const int team = (warp - 12) >> 1;
+    const int t = (threadIdx.x - 384) & 63;
+    long long gk = 0;   // k-blocks this CTA has been through (both teams count all of them)
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m_tile = tile / p.tiles_n;
+      const long long row0 = (long long)m_tile * kBM;
+      const bool ok0 = row0 + t < p.M, ok1 = row0 + t + 64 < p.M;
+      const float* arow = p.gen_a + (row0 / p.pair_nl) * p.ld_gen_a;   // one protein per tile (pair_nl % 128 == 0)
+      for (int kb = 0; kb < p.num_kblocks; ++kb, ++gk) {
+        if ((int)(gk & 1) != team) continue;
+        const int stage = (int)(gk % Cfg::kStages);
+        const uint32_t phase = (uint32_t)((gk / Cfg::kStages) & 1);
+        const int cs = (int)(gk % kGenStages);
+        const uint32_t cphase = (uint32_t)((gk / kGenStages) & 1);
+        mbar_wait(cfull_bar(cs), cphase);
+        mbar_wait(empty_bar(stage), phase ^ 1);
+        const uint32_t sc = gen_base + cs * kGenTileBytes;
+        const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+        const float* ak = arow + kb * BK;
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {      // 8 k-values = one 16-byte chunk of each fp16 plane
+          const float4 a0 = __ldg(reinterpret_cast<const float4*>(ak + 8 * q4));
+          const float4 a1 = __ldg(reinterpret_cast<const float4*>(ak + 8 * q4 + 4));
+#pragma unroll
+          for (int rr = 0; rr < 2; ++rr) {
+            const int r = t + 64 * rr;
+            float cv[8];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const uint32_t chunk = (uint32_t)((2 * q4 + h) ^ (r & 7));
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                           : "=f"(cv[4 * h]), "=f"(cv[4 * h + 1]), "=f"(cv[4 * h + 2]), "=f"(cv[4 * h + 3])
+                           : "r"(sc + r * 128 + (chunk << 4)));
+            }
+            uint32_t hi[4], lo[4];
+            split_pack_pos(fmaxf(a0.x + cv[0], 0.f), fmaxf(a0.y + cv[1], 0.f), hi[0], lo[0]);
+            split_pack_pos(fmaxf(a0.z + cv[2], 0.f), fmaxf(a0.w + cv[3], 0.f), hi[1], lo[1]);
+            split_pack_pos(fmaxf(a1.x + cv[4], 0.f), fmaxf(a1.y + cv[5], 0.f), hi[2], lo[2]);
+            split_pack_pos(fmaxf(a1.z + cv[6], 0.f), fmaxf(a1.w + cv[7], 0.f), hi[3], lo[3]);
+            if (!(rr == 0 ? ok0 : ok1)) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) hi[e] = lo[e] = 0u;
+            }
+            const uint32_t dst = sa + (uint32_t)(r * 64 + ((q4 ^ ((r >> 1) & 3)) << 4));
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]),
+                         "r"(hi[3])
+                         : "memory");
+            if (NPASS == 3)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + Cfg::kATile), "r"(lo[0]), "r"(lo[1]),
+                           "r"(lo[2]), "r"(lo[3])
+                           : "memory");
+          }
+        }
+        fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(full_bar(stage));
+          mbar_arrive(cempty_bar(cs));
+        }
+      }
+    }
   } else {
     // ------------------------------------------------------------------ epilogue (8 warps)
-    reg_alloc<kEpiRegs>();
+    reg_alloc<GEN ? kGenEpiRegs : kEpiRegs>();
     const int q = warp & 3;                   // TMEM lane quarter this warp may read
     const int half = (warp - 4) >> 2;         // which half of the tile's column groups
     const int ngroups = p.bn >> 5;            // 32-column groups in a tile (<= 8)

@@ -167,3 +167,21 @@ def test_save_embeddings_contract():
     assert (emb["joint_embeddings"] - joint).abs().max().item() <= 2e-5
     assert emb["output_layer_embeddings"].shape == hidden.shape
     assert (emb["output_layer_embeddings"] - hidden).abs().max().item() <= 1e-4
+
+
+def test_fused_feature_generator_matches_separate_kernel():
+    """Option fuse_features=1 builds relu(a[b] + c[l]) inside the first scorer GEMM's operand producer (TMA-staged label
+    tiles, generator warps writing the swizzled fp16 planes); it must give bit-identical logits to the default path."""
+    from protnote_b200 import native
+    ecfg, scfg = EncoderCfg(), ScorerCfg()
+    sd = synth_state_dict(ecfg, scfg, seed=46, calib_T=128)
+    onehots, lengths, labels = synth_inputs(3, 200, 640, ecfg, scfg, ragged=True, seed=5)
+    model = build_b200_model(ecfg, scfg, sd)
+    base = run(model, onehots, lengths, labels)
+    native.set_option("fuse_features", 1)
+    try:
+        model._label_cache = None
+        fused = run(model, onehots, lengths, labels)
+    finally:
+        native.set_option("fuse_features", 0)
+    assert torch.equal(fused, base)

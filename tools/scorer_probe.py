@@ -19,11 +19,10 @@ L_f = torch.randn(L, 1024, device="cuda")
 FLOP_PAIR = 37_754_880
 for mode_name in modes:
     mode = native.MODES[mode_name]
-    for bk, pk in ((32, 256), (64, 256), (32, 128), (64, 64)):
-        if mode_name == "fast" and pk != 256:
-            continue
+    for bk, pk, fuse in ((32, 256, 1), (32, 256, 0), (64, 256, 0)):
         native.set_option("bk", bk)
-        native.set_option("promote_k", pk)
+        native.set_option("promote_k_scorer", pk)
+        native.set_option("fuse_features", fuse)
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         for it in range(2):
             ev[0].record()
@@ -36,8 +35,9 @@ for mode_name in modes:
             torch.cuda.synchronize()
         t_p, t_l, t_s = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3])
         pairs = B * L
-        print(f"{mode_name} bk={bk} promote_k={pk}: W_p {t_p:.2f} ms, W_l {t_l:.2f} ms ({L*50.33e6/t_l/1e9:.0f} TFLOP/s), "
+        print(f"{mode_name} bk={bk} promote_k={pk} fuse={fuse}: W_p {t_p:.2f} ms, W_l {t_l:.2f} ms ({L*50.33e6/t_l/1e9:.0f} TFLOP/s), "
               f"score {t_s:.2f} ms -> {pairs/t_s/1e3:.2f} M pairs/s, {pairs*FLOP_PAIR/t_s/1e9:.0f} TFLOP/s algorithmic "
               f"({(3 if mode_name=='strict' else 1)*pairs*FLOP_PAIR/t_s/1e9:.0f} executed), logits finite={torch.isfinite(logits).all().item()}")
 native.set_option("bk", 0)
-native.set_option("promote_k", 256)
+native.set_option("promote_k_scorer", 256)
+native.set_option("fuse_features", 0)
