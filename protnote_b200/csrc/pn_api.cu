@@ -11,6 +11,7 @@
 
 #include "../../include/protnote_b200.h"
 #include "pn_kernels.cuh"
+#include "pn_gemm2.cuh"
 
 namespace {
 
@@ -25,6 +26,8 @@ long long g_chunk_rows = 0;      // 0 = auto
 // the generator's extra shared-memory traffic (+32 KB per k-block on top of ~120 KB) competes with the tensor core's
 // operand reads; it needs the 2-CTA operand sharing planned for the next round to pay off.  Off by default.
 int g_fuse_features = 0;
+// 1: run the engine as CTA pairs (tcgen05 cta_group::2, 256-row tiles, each CTA loads half of the weight tile)
+int g_cta2 = 0;
 // strict mode: K elements accumulated in TMEM between fp32 promotions, per stage of the path
 enum { kStageEncoder = 0, kStageHeads = 1, kStageScorer = 2, kStageOther = 3 };
 int g_promote_k[4] = {32, 32, 256, 64};
@@ -193,11 +196,42 @@ int launch_gemm_t(const GemmParams& p, cudaStream_t stream) {
   return 0;
 }
 
+template <int BK, int NPASS>
+int launch_gemm2_t(const GemmParams& p, cudaStream_t stream) {
+  using Cfg = Gemm2Cfg<BK, NPASS>;
+  static bool configured = false;
+  if (!configured) {
+    PN_CUDA(cudaFuncSetAttribute(gemm2_kernel<BK, NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured = true;
+  }
+  const int total = p.tiles_m * p.tiles_n;
+  int clusters = num_sms() / 2;
+  if (total < clusters) clusters = total;
+  TimedLaunch tl;
+  const bool timed = g_timing && p.timed_flops > 0;
+  if (timed) {
+    PN_CUDA(cudaEventCreate(&tl.start));
+    PN_CUDA(cudaEventCreate(&tl.stop));
+    tl.flops = p.timed_flops;
+    PN_CUDA(cudaEventRecord(tl.start, stream));
+  }
+  gemm2_kernel<BK, NPASS><<<2 * clusters, kGemmThreads, Cfg::kSmemBytes, stream>>>(p);
+  PN_CUDA(cudaGetLastError());
+  if (timed) {
+    PN_CUDA(cudaEventRecord(tl.stop, stream));
+    g_timed.push_back(tl);
+  }
+  g_launches++;
+  return 0;
+}
+
 // D = A * B^T with the fused epilogue.  A: plain [M][K] or conv view; B: packed weights [N][K_total].
 int launch_gemm(const Planes& A, const ConvView& cv, const Planes& B, long long N, const Epilogue& e, int mode,
                 cudaStream_t stream, int stage_kind = kStageOther) {
   if (mode != PN_STRICT && mode != PN_FAST) return fail("mode must be PN_STRICT or PN_FAST");
   const bool gen = e.gen_a != nullptr;
+  const bool cta2 = g_cta2 && !gen;
+  const int tile_rows = cta2 ? 2 * kBM : kBM;
   const int bk = gen ? 32 : pick_bk(mode);
   GemmParams p;
   memset(&p, 0, sizeof(p));
@@ -213,7 +247,7 @@ int launch_gemm(const Planes& A, const ConvView& cv, const Planes& B, long long 
     p.conv_cpad = cv.cpad;
     p.conv_dil = cv.dil;
     p.conv_T = cv.T;
-    p.conv_tiles_per_seq = (cv.T + kBM - 1) / kBM;
+    p.conv_tiles_per_seq = (cv.T + tile_rows - 1) / tile_rows;
     p.lengths = cv.lengths;
     p.M = cv.batch * cv.T;
     p.tiles_m = cv.batch * p.conv_tiles_per_seq;
@@ -225,7 +259,7 @@ int launch_gemm(const Planes& A, const ConvView& cv, const Planes& B, long long 
     if (need_lo) PN_TRY(make_map(&p.tm_a_lo, A.lo, 3, dims, strides, box, bk * 2));
   } else {
     p.M = (int)A.rows;
-    p.tiles_m = (int)((A.rows + kBM - 1) / kBM);
+    p.tiles_m = (int)((A.rows + tile_rows - 1) / tile_rows);
     p.num_kblocks = (int)((A.cols + bk - 1) / bk);
     if (!gen) {
       const cuuint64_t dims[2] = {(cuuint64_t)A.cols, (cuuint64_t)A.rows};
@@ -247,7 +281,7 @@ int launch_gemm(const Planes& A, const ConvView& cv, const Planes& B, long long 
   {
     const cuuint64_t dims[2] = {(cuuint64_t)B.cols, (cuuint64_t)B.rows};
     const cuuint64_t strides[1] = {(cuuint64_t)B.ld * 2};
-    const cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)p.bn};
+    const cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)(cta2 ? p.bn / 2 : p.bn)};
     PN_TRY(make_map(&p.tm_b_hi, B.hi, 2, dims, strides, box, bk * 2));
     if (need_lo) PN_TRY(make_map(&p.tm_b_lo, B.lo, 2, dims, strides, box, bk * 2));
   }
@@ -278,6 +312,10 @@ int launch_gemm(const Planes& A, const ConvView& cv, const Planes& B, long long 
   if (gen) {
     if (cv.taps > 0 || e.pair_nl <= 0) return fail("generated A operand needs plain addressing and pair_nl");
     return mode == PN_STRICT ? launch_gemm_t<32, 3, true>(p, stream) : launch_gemm_t<32, 1, true>(p, stream);
+  }
+  if (cta2) {
+    if (bk == 32) return mode == PN_STRICT ? launch_gemm2_t<32, 3>(p, stream) : launch_gemm2_t<32, 1>(p, stream);
+    return mode == PN_STRICT ? launch_gemm2_t<64, 3>(p, stream) : launch_gemm2_t<64, 1>(p, stream);
   }
   if (bk == 32) return mode == PN_STRICT ? launch_gemm_t<32, 3>(p, stream) : launch_gemm_t<32, 1>(p, stream);
   return mode == PN_STRICT ? launch_gemm_t<64, 3>(p, stream) : launch_gemm_t<64, 1>(p, stream);
@@ -623,6 +661,10 @@ int pn_set_option(const char* name, long long value) {
     } else {
       return fail("unknown option '%s'", name);
     }
+    return 0;
+  }
+  if (strcmp(name, "cta2") == 0) {
+    g_cta2 = value != 0;
     return 0;
   }
   if (strcmp(name, "fuse_features") == 0) {

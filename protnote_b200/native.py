@@ -51,6 +51,15 @@ def set_option(name: str, value: int):
     check(_lib.load().pn_set_option(name.encode(), int(value)))
 
 
+def _apply_env_options():
+    """Experiment switches: PN_OPTIONS="cta2=1,bk=64" sets engine options when the package is imported."""
+    import os
+    spec = os.environ.get("PN_OPTIONS", "")
+    for item in filter(None, (x.strip() for x in spec.split(","))):
+        name, _, value = item.partition("=")
+        set_option(name, int(value))
+
+
 def launch_count() -> int:
     return int(_lib.load().pn_launch_count())
 
@@ -64,6 +73,9 @@ def gemm_timing_read():
     ms, n, fl = C.c_double(), C.c_longlong(), C.c_double()
     check(_lib.load().pn_gemm_timing_read(C.byref(ms), C.byref(n), C.byref(fl)))
     return ms.value, n.value, fl.value
+
+
+_apply_env_options()
 
 
 class PackedEncoder:

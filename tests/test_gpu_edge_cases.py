@@ -185,3 +185,21 @@ def test_fused_feature_generator_matches_separate_kernel():
     finally:
         native.set_option("fuse_features", 0)
     assert torch.equal(fused, base)
+
+
+def test_cta_pair_kernels_match_single_cta_kernels():
+    """Option cta2=1 runs every contraction as CTA pairs (tcgen05 cta_group::2, 256-row tiles, each CTA loading half of
+    the weight tile, cross-CTA mbarrier protocol).  Same arithmetic per output element -> bit-identical logits."""
+    from protnote_b200 import native
+    for case in ("tiny_long", "base_small"):
+        ecfg, scfg, sd, onehots, lengths, labels, g = load_case(case)
+        model = build_b200_model(ecfg, scfg, sd)
+        base = run(model, onehots, lengths, labels)
+        native.set_option("cta2", 1)
+        try:
+            model._label_cache = None
+            pair = run(model, onehots, lengths, labels)
+        finally:
+            native.set_option("cta2", 0)
+        assert torch.equal(pair, base)
+        assert (pair - g["logits"]).abs().max().item() <= TOL
