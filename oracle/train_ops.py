@@ -1,0 +1,205 @@
+"""TEST INFRASTRUCTURE ONLY - a torch (CPU) stand-in for the `pn_t_*` training primitives.
+
+`protnote_b200/train.py` sequences a small set of primitives (GEMMs on fp16 planes, column statistics, BatchNorm
+normalise / backward kernels).  On the product path those primitives are the sm_100a kernels bound in
+`protnote_b200/train_native.py`.  This class implements the SAME primitive contracts with plain torch tensor
+arithmetic so that
+  * the sequencing logic (analytic layer-1 statistics, BatchNorm backward through shared sums, label sharding) can be
+    checked on the CPU against the reference's autograd (tests/test_train_cpu.py, tests/test_train_gloo.py), and
+  * every CUDA primitive has an independent statement of what it must compute (tests/test_gpu_train.py).
+The product package never imports this file.
+
+BatchNorm1d training semantics follow torch.nn.BatchNorm1d as used by the reference (ProtNote.py:63-81 via
+torchvision.ops.MLP, ProtNote.py:364-365): biased batch variance for normalisation, unbiased for running_var,
+running = (1 - momentum) * running + momentum * batch.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+
+@dataclass
+class TAct:
+    val: torch.Tensor            # [rows, cols] = true value * sc
+    sc: float = 1.0
+    has_T: bool = False
+
+
+@dataclass
+class TPacked:
+    w: torch.Tensor              # [N, K] (already transposed when packed with transposed=True)
+
+
+@dataclass
+class TBN:
+    scale: torch.Tensor
+    shift: torch.Tensor
+    mean: torch.Tensor
+    invstd: torch.Tensor
+
+
+@dataclass
+class TOuter:
+    g_logit: torch.Tensor        # [rows]
+    w: torch.Tensor              # [cols]
+
+
+@dataclass
+class TPair:
+    a: torch.Tensor              # [B, H]
+    c: torch.Tensor              # [L, H]
+
+
+@dataclass
+class TBwdStats:
+    sums: torch.Tensor           # float64 [2, cols]: sum g_y, sum g_y * xhat   (true scale)
+    maxes: torch.Tensor          # [2]: max |g_y|, max |xhat|
+    local: Optional[torch.Tensor] = None
+    dw: Optional[torch.Tensor] = None
+    db: Optional[torch.Tensor] = None
+
+
+def pow2_scale(absmax: float) -> float:
+    """power of two that puts `absmax` into [2^5, 2^6) - the rule of pn_t_autoscale / pn_t_bwd_scale."""
+    if not (absmax > 0) or not math.isfinite(absmax):
+        return 1.0
+    _, e = math.frexp(absmax)    # absmax = f * 2^e, f in [0.5, 1)
+    return math.ldexp(1.0, 6 - e)
+
+
+class TorchOps:
+    def __init__(self, dtype=torch.float64):
+        self.dtype = dtype
+
+    # ------------------------------------------------------------------ operands
+    def split(self, x, want_T=False, autoscale=False):
+        x = x.detach().to(self.dtype)
+        sc = pow2_scale(float(x.abs().max())) if autoscale and x.numel() else 1.0
+        return TAct(x * sc, sc, want_T)
+
+    def pack(self, W, transposed=False):
+        W = W.detach().to(self.dtype)
+        return TPacked(W.t().contiguous() if transposed else W.contiguous())
+
+    # ------------------------------------------------------------------ GEMMs
+    def linear(self, x: TAct, W: TPacked, out_f32=False):
+        y = (x.val / x.sc) @ W.w.t()
+        return y if out_f32 else TAct(y, 1.0, False)
+
+    def dgrad(self, g: TAct, WT: TPacked, out_f32=False):
+        y = (g.val / g.sc) @ WT.w.t()
+        return y if out_f32 else TAct(y * g.sc, g.sc, False)
+
+    def wgrad(self, g: TAct, x: TAct, out=None):
+        assert g.has_T and x.has_T, "wgrad contracts over rows: both operands need their transposed planes"
+        dW = (g.val / g.sc).t() @ (x.val / x.sc)
+        if out is not None:
+            out.copy_(dW.to(out.dtype))
+            return out
+        return dW
+
+    # ------------------------------------------------------------------ statistics / BatchNorm forward
+    def col_stats(self, z: TAct):
+        v = (z.val / z.sc).double()
+        return torch.stack([v.sum(0), (v * v).sum(0)])
+
+    def col_stats_f32(self, x):
+        v = x.double()
+        return torch.stack([v.sum(0), (v * v).sum(0)])
+
+    def _finalize(self, mean, var, count, bn, update_running):
+        eps = bn.eps
+        invstd = 1.0 / torch.sqrt(var + eps)
+        scale = bn.weight.detach().double() * invstd
+        shift = bn.bias.detach().double() - mean * scale
+        if update_running and bn.track_running_stats:
+            m = bn.momentum
+            with torch.no_grad():
+                bn.running_mean.mul_(1 - m).add_((m * mean).to(bn.running_mean.dtype))
+                unbiased = var * (count / max(count - 1.0, 1.0))
+                bn.running_var.mul_(1 - m).add_((m * unbiased).to(bn.running_var.dtype))
+        t = self.dtype
+        return TBN(scale.to(t), shift.to(t), mean.to(t), invstd.to(t))
+
+    def bn_finalize(self, stats, count, bn, update_running=True):
+        mean = stats[0] / count
+        var = (stats[1] / count - mean * mean).clamp_min(0)
+        return self._finalize(mean, var, float(count), bn, update_running)
+
+    def bn_finalize_pair(self, sa, B, sc, L, bn, update_running=True):
+        ma, mc = sa[0] / B, sc[0] / L
+        va = (sa[1] / B - ma * ma).clamp_min(0)
+        vc = (sc[1] / L - mc * mc).clamp_min(0)
+        return self._finalize(ma + mc, va + vc, float(B) * float(L), bn, update_running)
+
+    def bn_relu(self, z: TAct, st: TBN, want_T=False):
+        return TAct(torch.relu(z.val * st.scale + st.shift), 1.0, want_T)
+
+    def bn_relu_dot(self, z: TAct, st: TBN, w, b):
+        h = torch.relu(z.val * st.scale + st.shift)
+        return h @ w.detach().to(self.dtype).reshape(-1) + b.detach().to(self.dtype).reshape(())
+
+    def pair_hidden(self, a, c, st: TBN, want_T=False):
+        z = (a[:, None, :] + c[None, :, :]).reshape(-1, a.shape[1])
+        return TAct(torch.relu(z * st.scale + st.shift), 1.0, want_T)
+
+    # ------------------------------------------------------------------ BatchNorm + ReLU backward
+    def outer(self, g_logit, w):
+        return TOuter(g_logit.detach().to(self.dtype).reshape(-1), w.detach().to(self.dtype).reshape(-1))
+
+    def pair_source(self, a, c):
+        return TPair(a, c)
+
+    def _g(self, g):
+        if isinstance(g, TOuter):
+            return g.g_logit[:, None] * g.w[None, :]
+        return g.val / g.sc
+
+    def _z(self, z):
+        if isinstance(z, TPair):
+            return (z.a[:, None, :] + z.c[None, :, :]).reshape(-1, z.a.shape[1])
+        return z.val / z.sc
+
+    def bwd_stats(self, g, z, st: TBN):
+        G, Z = self._g(g), self._z(z)
+        pre = Z * st.scale + st.shift
+        gy = G * (pre > 0)
+        xh = (Z - st.mean) * st.invstd
+        s = TBwdStats(torch.stack([gy.double().sum(0), (gy * xh).double().sum(0)]),
+                      torch.stack([gy.abs().max(), xh.abs().max()]))
+        s.local = s.sums.clone()
+        if isinstance(g, TOuter):
+            s.dw = (g.g_logit[:, None] * torch.relu(pre)).double().sum(0)
+            s.db = g.g_logit.double().sum().reshape(1)
+        return s
+
+    def bn_param_grads(self, s: TBwdStats):
+        return s.local[1].clone(), s.local[0].clone()       # d gamma = sum g_y xhat, d beta = sum g_y
+
+    def final_param_grads(self, s: TBwdStats):
+        return s.dw.reshape(1, -1).clone(), s.db.clone()
+
+    def _gz(self, g, z, st, s, count):
+        G, Z = self._g(g), self._z(z)
+        gy = G * ((Z * st.scale + st.shift) > 0)
+        xh = (Z - st.mean) * st.invstd
+        s1 = (s.sums[0] / count).to(self.dtype)
+        s2 = (s.sums[1] / count).to(self.dtype)
+        return st.scale * (gy - s1 - xh * s2)
+
+    def bwd_apply(self, g, z, st: TBN, s: TBwdStats, count, want_T=False):
+        gz = self._gz(g, z, st, s, float(count))
+        bound = float(st.scale.abs().max()) * (float(s.maxes[0]) + float(s.sums[0].abs().max()) / count
+                                               + float(s.maxes[1]) * float(s.sums[1].abs().max()) / count)
+        sc = pow2_scale(bound)
+        return TAct(gz * sc, sc, want_T)
+
+    def bwd_apply_pair(self, g, zp: TPair, st: TBN, s: TBwdStats, count):
+        gz = self._gz(g, zp, st, s, float(count))
+        B, L, H = zp.a.shape[0], zp.c.shape[0], zp.a.shape[1]
+        gz = gz.reshape(B, L, H)
+        return gz.sum(1), gz.sum(0)

@@ -1,0 +1,74 @@
+"""TEST INFRASTRUCTURE ONLY - CPU oracle of the TRAINING-mode scoring step (travels to the GPU box).
+
+Restates, with plain torch autograd, what the reference computes for one training step of the trainable part of
+ProtNote when the sequence embeddings are given (frozen encoder, TRAIN_SEQUENCE_ENCODER False):
+
+    P_f, L_f -> W_p / W_l (torchvision MLP, BatchNorm1d in training mode, ProtNote.py:63-81,270-271)
+             -> joint [B*L, 2d] (ProtNote.py:112-126) -> output MLP (get_mlp, ProtNote.py:337-378, BN training mode)
+             -> logits [B, L] (ProtNote.py:308-309) -> BCE-with-logits (utils/losses.py:270-294 'BCE') -> backward
+
+Parity status: pinned against the reference's own `ProtNote` class in train mode (imported unmodified in the build
+container) by tests/test_train_cpu.py::test_train_oracle_matches_reference, and through tests/golden/train_*.pt
+(generated from the reference class by oracle/make_golden_train.py).
+"""
+from __future__ import annotations
+
+from typing import Dict
+
+import torch
+import torch.nn.functional as F
+
+from .protnote_oracle import ScorerCfg, joint_features, output_mlp_layout
+
+
+def _bn_train(x, sd, prefix, eps, new_stats, momentum=0.1):
+    """BatchNorm1d training forward; records the updated running statistics (momentum 0.1: torch default,
+    which torchvision MLP / get_mlp do not override)."""
+    rm = sd[prefix + ".running_mean"].detach().clone().to(x.dtype)
+    rv = sd[prefix + ".running_var"].detach().clone().to(x.dtype)
+    y = F.batch_norm(x, rm, rv, sd[prefix + ".weight"], sd[prefix + ".bias"], True, momentum, eps)
+    new_stats[prefix + ".running_mean"] = rm
+    new_stats[prefix + ".running_var"] = rv
+    return y
+
+
+def train_step_oracle(sd: Dict[str, torch.Tensor], P_f, L_f, targets, cfg: ScorerCfg, dtype=torch.float64):
+    """Returns (logits [B, L], loss, {state_dict key: gradient}, {running-stat key: updated value})."""
+    if cfg.feature_fusion != "concatenation":
+        raise NotImplementedError(cfg.feature_fusion)
+    p = {k: v.detach().clone().to(dtype).requires_grad_(True) for k, v in sd.items()
+         if v.is_floating_point() and not k.startswith("sequence_encoder.") and "running_" not in k}
+    full = dict(sd)
+    full.update(p)
+    new_stats: Dict[str, torch.Tensor] = {}
+
+    def head(prefix, x):
+        n = cfg.projection_head_num_layers
+        for i in range(n):
+            x = x @ full[f"{prefix}.{4 * i}.weight"].T
+            if i < n - 1:
+                x = torch.relu(_bn_train(x, full, f"{prefix}.{4 * i + 1}", cfg.bn_eps, new_stats))
+        return x
+
+    P_e = head("W_p", P_f.to(dtype))
+    L_e = head("W_l", L_f.to(dtype))
+    x = joint_features(P_e, L_e, cfg.feature_fusion)
+    hidden, last = output_mlp_layout(cfg)
+    for lin, bn in hidden:
+        x = x @ full[f"output_layer.{lin}.weight"].T
+        if f"output_layer.{lin}.bias" in full:
+            x = x + full[f"output_layer.{lin}.bias"]
+        if bn is not None:
+            x = _bn_train(x, full, f"output_layer.{bn}", cfg.bn_eps, new_stats)
+        x = torch.relu(x)
+    logits = (x @ full[f"output_layer.{last}.weight"].T + full[f"output_layer.{last}.bias"]).reshape(
+        P_e.shape[0], L_e.shape[0])
+    loss = F.binary_cross_entropy_with_logits(logits, targets.to(dtype))
+    loss.backward()
+    grads = {k: v.grad.detach() for k, v in p.items() if v.grad is not None}
+    return logits.detach(), loss.detach(), grads, new_stats
+
+
+def synth_targets(B: int, L: int, seed: int = 99, density: float = 0.05):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.rand(B, L, generator=g) < density).float()

@@ -1,0 +1,281 @@
+"""Training-mode forward + backward of the ProtNote scoring path (reference: `ProtNote.forward` with
+`self.training == True`, protnote/models/ProtNote.py:168-334, driven by `ProtNoteTrainer.train_one_epoch`,
+protnote/models/ProtNoteTrainer.py:675-825).
+
+What training mode changes with respect to the eval path (csrc/pn_api.cu):
+  * every BatchNorm1d uses BATCH statistics - over the B proteins in W_p, over the L label rows in W_l and over all
+    B*L (protein, label) pairs in the output MLP (ProtNote.py:63-81,337-378) - and updates its running statistics;
+  * the result has to be differentiable with respect to W_p, W_l and output_layer (the sequence encoder is frozen:
+    TRAIN_SEQUENCE_ENCODER False, base_config.yaml:71; ProtNoteTrainer.py:211-214).
+
+The arithmetic runs on the sm_100a library through the `pn_t_*` primitives of include/protnote_b200.h (tensor-core GEMMs
+on fp16 hi/lo planes + HBM-streaming reduction / normalisation kernels).  This file is launch logic only: it sequences
+those primitives, and - when the label axis is sharded over ranks - all-reduces the few per-column statistics that couple
+the shards (BatchNorm sums in forward, the two BatchNorm-backward sums in backward).  The same sequencing is exercised on
+the CPU by the tests with a torch stand-in for the primitives (oracle/train_ops.py, test infrastructure only).
+
+Exact identities used (so that the [B*L, 2d] joint tensor never exists in training either):
+  layer 1 of the output MLP is linear in [p; t]:  z1[b,l] = a[b] + c[l],  a = P_e W1p^T, c = L_e W1l^T
+  its batch statistics over the full B x L grid follow from the factors:
+      mean(z1) = mean_b(a) + mean_l(c),     var(z1) = var_b(a) + var_l(c)      (the cross term sums to zero)
+  and its backward reduces to  da[b] = sum_l g_z1[b,l],  dc[l] = sum_b g_z1[b,l].
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+
+class Comm:
+    """The collectives the label-sharded training step needs.  `None` group / world 1 -> no-ops."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+
+    def sum_(self, t: torch.Tensor):
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def max_(self, t: torch.Tensor):
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
+        return t
+
+
+class _NoComm:
+    world = 1
+
+    def sum_(self, t):
+        return t
+
+    def max_(self, t):
+        return t
+
+
+def _split_sequential(seq: nn.Module) -> List[Tuple[nn.Linear, Optional[nn.BatchNorm1d]]]:
+    """[(Linear, BatchNorm1d or None)] of a torchvision-MLP-shaped Sequential (ProtNote.py:63-81,337-378).
+    Dropout layers must be inactive (p == 0): the reference's defaults (base_config.yaml:39-41)."""
+    mods = list(seq)
+    if len(mods) == 2 and isinstance(mods[0], nn.Dropout) and isinstance(mods[1], nn.Sequential):
+        if mods[0].p > 0:
+            raise NotImplementedError("dropout > 0 is not implemented on the sm_100a training path")
+        mods = list(mods[1])
+    out = []
+    for i, m in enumerate(mods):
+        if isinstance(m, nn.Dropout) and m.p > 0:
+            raise NotImplementedError("dropout > 0 is not implemented on the sm_100a training path")
+        if isinstance(m, nn.Linear):
+            bn = mods[i + 1] if i + 1 < len(mods) and isinstance(mods[i + 1], nn.BatchNorm1d) else None
+            out.append((m, bn))
+    return out
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# projection heads W_p / W_l  (ProtNote.py:63-81):  [Linear(no bias), BN, ReLU] x (n-1), Linear(no bias)
+# --------------------------------------------------------------------------------------------------------------------
+def head_forward(ops, comm, x_f32, layers, rows_total: int, sharded: bool, update_running: bool):
+    x = ops.split(x_f32, want_T=True)
+    saved, out = [], None
+    for lin, bn in layers:
+        if lin.bias is not None:
+            raise NotImplementedError("projection heads are bias-free in the reference (ProtNote.py:67,77)")
+        W = ops.pack(lin.weight)
+        if bn is None:
+            out = ops.linear(x, W, out_f32=True)
+            saved.append((x, None, None, lin, None))
+        else:
+            z = ops.linear(x, W, out_f32=False)
+            stats = ops.col_stats(z)
+            if sharded:
+                comm.sum_(stats)
+            st = ops.bn_finalize(stats, rows_total, bn, update_running)
+            saved.append((x, z, st, lin, bn))
+            x = ops.bn_relu(z, st, want_T=True)
+    return out, saved
+
+
+def head_backward(ops, comm, g_f32, saved, rows_total: int, sharded: bool, grads: Dict):
+    g = ops.split(g_f32, want_T=True, autoscale=True)
+    for idx in range(len(saved) - 1, -1, -1):
+        x, z, st, lin, bn = saved[idx]
+        if st is not None:                       # g is the gradient w.r.t. the ReLU output of this layer
+            s = ops.bwd_stats(g, z, st)
+            grads[bn.weight], grads[bn.bias] = ops.bn_param_grads(s)        # this rank's rows only (before the sum)
+            if sharded:
+                comm.sum_(s.sums)
+            g = ops.bwd_apply(g, z, st, s, rows_total, want_T=True)         # gradient w.r.t. the Linear output
+        grads[lin.weight] = ops.wgrad(g, x)
+        if idx > 0:
+            g = ops.dgrad(g, ops.pack(lin.weight, transposed=True))
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# pair scorer (ProtNote.py:112-126,293,337-378)
+# --------------------------------------------------------------------------------------------------------------------
+def pairs_forward(ops, comm, P_e, L_e, hidden, final: nn.Linear, L_total: int, sharded: bool, update_running: bool):
+    B, d = P_e.shape
+    lin1, bn1 = hidden[0]
+    if bn1 is None or any(bn is None for _, bn in hidden):
+        raise NotImplementedError("the training path implements OUTPUT_MLP_BATCHNORM True (base_config.yaml:36)")
+    if lin1.weight.shape[1] != 2 * d:
+        raise NotImplementedError("the training path implements FEATURE_FUSION 'concatenation' (base_config.yaml:44)")
+    pe = ops.split(P_e, want_T=True)
+    le = ops.split(L_e, want_T=True)
+    a = ops.linear(pe, ops.pack(lin1.weight[:, :d]), out_f32=True)          # [B, H] raw protein half
+    c = ops.linear(le, ops.pack(lin1.weight[:, d:]), out_f32=True)          # [L_local, H] raw label half
+    sa = ops.col_stats_f32(a)
+    sc = ops.col_stats_f32(c)
+    if sharded:
+        comm.sum_(sc)
+    st1 = ops.bn_finalize_pair(sa, B, sc, L_total, bn1, update_running)
+    h = ops.pair_hidden(a, c, st1, want_T=True)                             # [B * L_local, H]
+    ctx = {"pe": pe, "le": le, "a": a, "c": c, "st1": st1, "layers": [], "B": B, "d": d, "hidden": hidden,
+           "final": final, "count": B * L_total}
+    logits = None
+    for j in range(1, len(hidden)):
+        lin, bn = hidden[j]
+        z = ops.linear(h, ops.pack(lin.weight), out_f32=False)
+        stats = ops.col_stats(z)
+        if sharded:
+            comm.sum_(stats)
+        st = ops.bn_finalize(stats, B * L_total, bn, update_running)
+        ctx["layers"].append((h, z, st, lin, bn))
+        if j + 1 < len(hidden):
+            h = ops.bn_relu(z, st, want_T=True)
+        else:                                                               # the last hidden layer is never stored:
+            logits = ops.bn_relu_dot(z, st, final.weight, final.bias)       # relu(BN(z)) . w_out + b_out per pair
+    return logits, ctx
+
+
+def pairs_backward(ops, comm, ctx, g_logit, sharded: bool, grads: Dict):
+    hidden, final, count = ctx["hidden"], ctx["final"], ctx["count"]
+    layers = ctx["layers"]
+    # ---- last hidden layer: the incoming gradient is the outer product g_logit (x) w_out, generated on the fly
+    h_prev, z, st, lin, bn = layers[-1]
+    go = ops.outer(g_logit, final.weight)
+    s = ops.bwd_stats(go, z, st)
+    grads[bn.weight], grads[bn.bias] = ops.bn_param_grads(s)
+    grads[final.weight], grads[final.bias] = ops.final_param_grads(s)
+    if sharded:
+        comm.sum_(s.sums)
+    g = ops.bwd_apply(go, z, st, s, count, want_T=True)
+    grads[lin.weight] = ops.wgrad(g, h_prev)
+    g = ops.dgrad(g, ops.pack(lin.weight, transposed=True))
+    # ---- middle layers
+    for j in range(len(layers) - 2, -1, -1):
+        h_prev, z, st, lin, bn = layers[j]
+        s = ops.bwd_stats(g, z, st)
+        grads[bn.weight], grads[bn.bias] = ops.bn_param_grads(s)
+        if sharded:
+            comm.sum_(s.sums)
+        g = ops.bwd_apply(g, z, st, s, count, want_T=True)
+        grads[lin.weight] = ops.wgrad(g, h_prev)
+        g = ops.dgrad(g, ops.pack(lin.weight, transposed=True))
+    # ---- layer 1: z1 = a[b] + c[l] is regenerated, its gradient is reduced to the two factors
+    lin1, bn1 = hidden[0]
+    d = ctx["d"]
+    zp = ops.pair_source(ctx["a"], ctx["c"])
+    s = ops.bwd_stats(g, zp, ctx["st1"])
+    grads[bn1.weight], grads[bn1.bias] = ops.bn_param_grads(s)
+    if sharded:
+        comm.sum_(s.sums)
+    da, dc = ops.bwd_apply_pair(g, zp, ctx["st1"], s, count)                # fp32 [B, H], [L_local, H]
+    dW1 = torch.empty_like(lin1.weight)
+    ga = ops.split(da, want_T=True, autoscale=True)
+    gc = ops.split(dc, want_T=True, autoscale=True)
+    ops.wgrad(ga, ctx["pe"], out=dW1[:, :d])
+    ops.wgrad(gc, ctx["le"], out=dW1[:, d:])
+    grads[lin1.weight] = dW1
+    dPe = ops.dgrad(ga, ops.pack(lin1.weight[:, :d], transposed=True), out_f32=True)
+    dLe = ops.dgrad(gc, ops.pack(lin1.weight[:, d:], transposed=True), out_f32=True)
+    return dPe, dLe
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# whole step
+# --------------------------------------------------------------------------------------------------------------------
+def trainable_parameters(model) -> List[nn.Parameter]:
+    ps = []
+    for part in (model.W_p, model.W_l, model.output_layer):
+        ps += [p for p in part.parameters()]
+    return ps
+
+
+def forward_train(ops, comm, model, P_f, L_f, L_total: Optional[int] = None, update_running: bool = True):
+    """P_f [B, protein_dim] (all proteins), L_f [L_local, label_dim] (this rank's label rows) -> logits [B, L_local]."""
+    comm = comm or _NoComm()
+    sharded = comm.world > 1
+    L_total = int(L_total if L_total is not None else L_f.shape[0])
+    B = P_f.shape[0]
+    wp, wl = _split_sequential(model.W_p), _split_sequential(model.W_l)
+    mods = _split_sequential(model.output_layer)
+    hidden, final = mods[:-1], mods[-1][0]
+    P_e, saved_p = head_forward(ops, comm, P_f, wp, B, False, update_running)
+    L_e, saved_l = head_forward(ops, comm, L_f, wl, L_total, sharded, update_running)
+    logits, pctx = pairs_forward(ops, comm, P_e, L_e, hidden, final, L_total, sharded, update_running)
+    ctx = {"saved_p": saved_p, "saved_l": saved_l, "pairs": pctx, "B": B, "L_total": L_total, "sharded": sharded}
+    if update_running:
+        for part in (model.W_p, model.W_l, model.output_layer):
+            for m in part.modules():
+                if isinstance(m, nn.BatchNorm1d) and m.num_batches_tracked is not None:
+                    m.num_batches_tracked += 1
+    return logits.reshape(B, L_f.shape[0]), ctx
+
+
+def backward_train(ops, comm, ctx, g_logits) -> Dict[nn.Parameter, torch.Tensor]:
+    """g_logits [B, L_local] -> {parameter: gradient} for this rank's label rows (sum over ranks = full gradient)."""
+    comm = comm or _NoComm()
+    grads: Dict = {}
+    sharded = ctx["sharded"]
+    dPe, dLe = pairs_backward(ops, comm, ctx["pairs"], g_logits.reshape(-1), sharded, grads)
+    head_backward(ops, comm, dPe, ctx["saved_p"], ctx["B"], False, grads)
+    head_backward(ops, comm, dLe, ctx["saved_l"], ctx["L_total"], sharded, grads)
+    return grads
+
+
+class _TrainFunction(torch.autograd.Function):
+    """Connects the primitives to autograd: the trainable parameters are inputs, so `loss.backward()` in the caller
+    (ProtNoteTrainer.py:738) delivers their gradients exactly as it does for the reference module."""
+
+    @staticmethod
+    def forward(fctx, ops, comm, model, P_f, L_f, L_total, *params):
+        logits, ctx = forward_train(ops, comm, model, P_f, L_f, L_total)
+        fctx.ops, fctx.comm, fctx.tctx, fctx.params = ops, comm, ctx, params
+        return logits
+
+    @staticmethod
+    def backward(fctx, g_logits):
+        grads = backward_train(fctx.ops, fctx.comm, fctx.tctx, g_logits.contiguous())
+        fctx.tctx = None
+        out = tuple(grads.get(p) if p.requires_grad else None for p in fctx.params)
+        return (None, None, None, None, None, None) + out
+
+
+def train_logits(model, P_f, L_f, ops=None, comm=None, L_total=None):
+    """Differentiable training-mode logits [B, L_local] of a protnote_b200.ProtNote module."""
+    if ops is None:
+        from .train_native import NativeOps
+        ops = NativeOps(model.precision)
+    params = trainable_parameters(model)
+    return _TrainFunction.apply(ops, comm, model, P_f.detach(), L_f.detach(), L_total, *params)
+
+
+def allreduce_gradients(model, comm: Comm):
+    """Label-sharded step: every rank holds the gradient of ITS label rows; the sum over ranks is the gradient of the
+    whole B x L batch (backward is linear in the incoming gradient once the BatchNorm sums have been shared)."""
+    ps = [p for p in trainable_parameters(model) if p.grad is not None]
+    if comm.world == 1 or not ps:
+        return
+    flat = torch.cat([p.grad.reshape(-1) for p in ps])
+    comm.sum_(flat)
+    off = 0
+    for p in ps:
+        n = p.grad.numel()
+        p.grad.copy_(flat[off:off + n].view_as(p.grad))
+        off += n

@@ -1,0 +1,100 @@
+"""CPU tests of the training step: (1) the travelling training oracle is pinned against the reference's own ProtNote class
+in train mode, (2) the primitive sequencing of protnote_b200/train.py - run here with the torch stand-in for the CUDA
+primitives - reproduces that oracle's logits, gradients and running statistics."""
+import copy
+
+import pytest
+import torch
+
+from oracle.cases import CASES
+from oracle.protnote_oracle import ScorerCfg, synth_state_dict
+from oracle.ref_import import import_reference, reference_available
+from oracle.train_ops import TorchOps
+from oracle.train_oracle import synth_targets, train_step_oracle
+from protnote_b200 import train as pn_train
+from tests.helpers import build_b200_model
+
+
+def _problem(name="tiny_concat", B=6, L=10, seed=5):
+    ecfg, scfg, *_ = CASES[name]
+    sd = synth_state_dict(ecfg, scfg, seed=CASES[name][6], calib_T=64)
+    g = torch.Generator().manual_seed(seed)
+    P_f = torch.randn(B, scfg.protein_embedding_dim, generator=g)
+    L_f = torch.randn(L, scfg.label_embedding_dim, generator=g)
+    return ecfg, scfg, sd, P_f, L_f, synth_targets(B, L, seed)
+
+
+@pytest.mark.skipif(not reference_available(), reason="needs /root/reference (build container only)")
+def test_train_oracle_matches_reference():
+    ecfg, scfg, sd, P_f, L_f, y = _problem()
+    from oracle.make_golden import build_reference_model
+    ref = build_reference_model(ecfg, scfg, sd).double().train()
+    logits, _ = ref(sequence_embeddings=P_f.double(), label_embeddings=L_f.double())
+    loss = torch.nn.functional.binary_cross_entropy_with_logits(logits, y.double())
+    loss.backward()
+    o_logits, o_loss, o_grads, o_stats = train_step_oracle(sd, P_f, L_f, y, scfg)
+    assert (logits.detach() - o_logits).abs().max() < 1e-10
+    assert abs(float(loss) - float(o_loss)) < 1e-12
+    named = dict(ref.named_parameters())
+    checked = 0
+    for k, g in o_grads.items():
+        assert (named[k].grad - g).abs().max() <= 1e-10 * max(1.0, float(g.abs().max())), k
+        checked += 1
+    assert checked >= 20
+    bufs = dict(ref.named_buffers())
+    for k, v in o_stats.items():
+        assert (bufs[k] - v).abs().max() < 1e-10, k
+
+
+def _ours_vs_oracle(scfg, ecfg, sd, P_f, L_f, y, tol):
+    model = build_b200_model(ecfg, scfg, sd, device="cpu").double().train()
+    ops = TorchOps(torch.float64)
+    logits, ctx = pn_train.forward_train(ops, None, model, P_f.double(), L_f.double())
+    o_logits, o_loss, o_grads, o_stats = train_step_oracle(sd, P_f, L_f, y, scfg)
+    assert (logits - o_logits).abs().max() < tol
+    # BCE-with-logits (mean reduction) gradient w.r.t. the logits
+    g_logits = (torch.sigmoid(logits) - y.double()) / logits.numel()
+    grads = pn_train.backward_train(ops, None, ctx, g_logits)
+    named = dict(model.named_parameters())
+    for k, g in o_grads.items():
+        got = grads[named[k]]
+        assert got.shape == g.shape, k
+        assert (got - g).abs().max() <= tol * max(1.0, float(g.abs().max())), k
+    bufs = dict(model.named_buffers())
+    for k, v in o_stats.items():
+        assert (bufs[k] - v).abs().max() < tol, k
+    for k, b in bufs.items():
+        if k.endswith("num_batches_tracked") and not k.startswith("sequence_encoder"):
+            assert int(b) == 1, k
+
+
+def test_sequencing_matches_oracle_tiny():
+    ecfg, scfg, sd, P_f, L_f, y = _problem()
+    _ours_vs_oracle(scfg, ecfg, sd, P_f, L_f, y, 1e-9)
+
+
+def test_sequencing_matches_oracle_two_layer_mlp():
+    ecfg, _, *_ = CASES["tiny_concat"]
+    scfg = ScorerCfg(protein_embedding_dim=72, label_embedding_dim=40, latent_dim=32,
+                     output_mlp_hidden_dim_scale_factor=2, output_mlp_num_layers=2,
+                     projection_head_num_layers=2, projection_head_hidden_dim_scale_factor=2)
+    sd = synth_state_dict(ecfg, scfg, seed=11, calib_T=64)
+    g = torch.Generator().manual_seed(3)
+    P_f, L_f = torch.randn(4, 72, generator=g), torch.randn(7, 40, generator=g)
+    _ours_vs_oracle(scfg, ecfg, sd, P_f, L_f, synth_targets(4, 7, 3), 1e-9)
+
+
+def test_autograd_function_delivers_parameter_gradients():
+    ecfg, scfg, sd, P_f, L_f, y = _problem(B=5, L=8, seed=8)
+    model = build_b200_model(ecfg, scfg, sd, device="cpu").double().train()
+    before = copy.deepcopy(model.state_dict())
+    logits = pn_train.train_logits(model, P_f.double(), L_f.double(), ops=TorchOps(torch.float64))
+    loss = torch.nn.functional.binary_cross_entropy_with_logits(logits, y.double())
+    loss.backward()
+    _, o_loss, o_grads, _ = train_step_oracle(before, P_f, L_f, y, scfg)
+    assert abs(float(loss) - float(o_loss)) < 1e-10
+    named = dict(model.named_parameters())
+    for k, g in o_grads.items():
+        assert named[k].grad is not None, k
+        assert (named[k].grad - g).abs().max() <= 1e-9 * max(1.0, float(g.abs().max())), k
+    assert all(p.grad is None for n, p in named.items() if n.startswith("sequence_encoder."))

@@ -1,0 +1,94 @@
+"""world_size-2 gloo test of the label-sharded TRAINING step: every rank owns a contiguous block of label rows, the
+BatchNorm sums (forward) and the two BatchNorm-backward sums are all-reduced, and the summed per-rank gradients must
+equal the single-process gradients of the whole B x L batch.  The per-rank compute step is the
+torch stand-in for the CUDA primitives (oracle/train_ops.py); the sequencing under test is protnote_b200/train.py."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle.cases import CASES
+from oracle.protnote_oracle import synth_state_dict
+from oracle.train_ops import TorchOps
+from oracle.train_oracle import synth_targets, train_step_oracle
+from protnote_b200 import train as pn_train
+from protnote_b200.sharded import label_row_bounds
+from tests.helpers import build_b200_model
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _problem():
+    ecfg, scfg, *_ = CASES["tiny_concat"]
+    sd = synth_state_dict(ecfg, scfg, seed=42, calib_T=64)
+    g = torch.Generator().manual_seed(21)
+    B, L = 5, 11     # 11 rows over 2 ranks: uneven shards
+    return ecfg, scfg, sd, torch.randn(B, 72, generator=g), torch.randn(L, 40, generator=g), synth_targets(B, L, 21)
+
+
+def _worker(rank, world, port, q):
+    try:
+        os.environ["MASTER_ADDR"] = "127.0.0.1"
+        os.environ["MASTER_PORT"] = str(port)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        torch.set_num_threads(2)
+        ecfg, scfg, sd, P_f, L_f, y = _problem()
+        model = build_b200_model(ecfg, scfg, sd, device="cpu").double().train()
+        comm = pn_train.Comm()
+        ls, le = label_row_bounds(L_f.shape[0], 1, rank, world)
+        logits = pn_train.train_logits(model, P_f.double(), L_f[ls:le].double(), ops=TorchOps(torch.float64), comm=comm,
+                                       L_total=L_f.shape[0])
+        # the loss of the whole batch is the mean over all B x L pairs: each rank contributes its slab's sum
+        loss = torch.nn.functional.binary_cross_entropy_with_logits(logits, y[:, ls:le].double(), reduction="sum") / y.numel()
+        loss.backward()
+        pn_train.allreduce_gradients(model, comm)
+        total = loss.detach().clone()
+        dist.all_reduce(total)
+        if rank == 0:
+            # numpy copies: pickled by value (torch tensors would travel as shared-memory handles that die with the rank)
+            out = {k: p.grad.numpy().copy() for k, p in model.named_parameters() if p.grad is not None}
+            bufs = {k: b.numpy().copy() for k, b in model.named_buffers()
+                    if "running_" in k and not k.startswith("sequence_encoder")}
+            q.put((0, None, float(total), out, bufs, logits.detach().numpy().copy()))
+        else:
+            q.put((rank, None))
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception as e:  # noqa: BLE001
+        q.put((rank, repr(e)))
+        raise
+
+
+def test_label_sharded_training_step_equals_single_process():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    for r in results:
+        assert r[1] is None, r
+    r0 = next(r for r in results if r[0] == 0)
+    _, _, loss, grads, bufs, logits0 = r0
+    grads = {k: torch.from_numpy(v) for k, v in grads.items()}
+    bufs = {k: torch.from_numpy(v) for k, v in bufs.items()}
+    logits0 = torch.from_numpy(logits0)
+    ecfg, scfg, sd, P_f, L_f, y = _problem()
+    o_logits, o_loss, o_grads, o_stats = train_step_oracle(sd, P_f, L_f, y, scfg)
+    ls, le = label_row_bounds(L_f.shape[0], 1, 0, world)
+    assert (logits0 - o_logits[:, ls:le]).abs().max() < 1e-9
+    assert abs(loss - float(o_loss)) < 1e-10
+    for k, g in o_grads.items():
+        assert (grads[k] - g).abs().max() <= 1e-9 * max(1.0, float(g.abs().max())), k
+    for k, v in o_stats.items():
+        assert (bufs[k] - v).abs().max() < 1e-9, k
