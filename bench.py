@@ -313,6 +313,125 @@ def run_ours(args, rank, world, local_rank):
     print(json.dumps(line), flush=True)
 
 
+TRAIN_B = 64
+# algorithmic FLOPs of one training step per (protein, label-row) pair: forward 2 GEMMs + dot, backward dgrad + wgrad of
+# the same two layers (layer 1 is factorised in both directions) -> 3 x the forward GEMM work
+TRAIN_FLOP_PER_PAIR = 3 * 2 * (2 * 3072 * 3072) + 2 * 3072
+TRAIN_FLOP_PER_LABEL_ROW = 3 * 50_331_648 + 3 * 2 * 1024 * 3072     # W_l forward + backward, label half of layer 1
+TRAIN_FLOP_PER_PROTEIN = 3 * 50_798_592 + 3 * 2 * 1024 * 3072 + 1024 * 60_896_000   # W_p, protein half, frozen encoder
+
+
+def run_train(args, rank, world, local_rank):
+    """BASELINE.json configs[2]: one training step = frozen encoder forward -> W_p / W_l / output MLP forward with BATCH
+    statistics -> BCE-with-logits -> backward -> gradient all-reduce (label-sharded ranks) -> Adam.  Label rows are
+    sharded over ranks; BatchNorm sums are all-reduced so the step equals the single-process step on the whole batch."""
+    import torch.distributed as dist
+    from protnote_b200 import native, train as pn_train
+    from protnote_b200.sharded import label_row_bounds
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    B = TRAIN_B if args.sequences == B_TOTAL else args.sequences
+    T, L = args.seq_len, args.labels
+    mode = args.mode if args.train_mode is None else args.train_mode
+    model = base_config_model(mode).to(dev).train()
+    model.sequence_encoder.eval()           # frozen encoder (TRAIN_SEQUENCE_ENCODER False), running statistics
+    params = pn_train.trainable_parameters(model)
+    for p in model.sequence_encoder.parameters():
+        p.requires_grad_(False)
+    opt = torch.optim.Adam(params, lr=3e-4, fused=True)
+    comm = pn_train.Comm() if world > 1 else None
+    onehots_h, lengths_h, labels_h = synthetic_inputs(B, T, L, pinned=False)
+    ls, le = label_row_bounds(L, 1, rank, world)
+    y_h = (torch.rand(B, L, generator=torch.Generator().manual_seed(5)) < 0.02).float()
+    x_h, len_h = onehots_h.pin_memory(), lengths_h.pin_memory()
+    lab_h, yl_h = labels_h[ls:le].contiguous().pin_memory(), y_h[:, ls:le].contiguous().pin_memory()
+    x_d, len_d, lab_d, y_d = x_h.to(dev), len_h.to(dev), lab_h.to(dev), yl_h.to(dev)
+    loss_host = torch.zeros(1).pin_memory()
+    last = {}
+
+    def step(x, lens, lab, y):
+        opt.zero_grad(set_to_none=True)
+        with torch.no_grad():
+            P_f = model.sequence_encoder.get_embeddings(x, lens)
+        logits = pn_train.train_logits(model, P_f, lab, comm=comm, L_total=L)
+        loss = torch.nn.functional.binary_cross_entropy_with_logits(logits, y, reduction="sum") / float(B * L)
+        loss.backward()
+        if comm is not None:
+            pn_train.allreduce_gradients(model, comm)
+        opt.step()
+        last["loss"] = loss.detach()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()) / steps
+
+    def step_device():
+        step(x_d, len_d, lab_d, y_d)
+
+    def step_e2e():
+        step(x_h.to(dev, non_blocking=True), len_h.to(dev, non_blocking=True), lab_h.to(dev, non_blocking=True),
+             yl_h.to(dev, non_blocking=True))
+        loss_host.copy_(last["loss"].reshape(1), non_blocking=True)
+
+    losses = []
+    for _ in range(args.warmup):
+        step_device()
+        losses.append(float(last["loss"]))
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = native.launch_count()
+    ms_step = timed(step_device, args.steps)
+    launches = native.launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    losses.append(float(last["loss"]))
+    step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    peak_mem = torch.cuda.max_memory_allocated(dev) / 2 ** 30
+    if rank != 0:
+        return
+    pairs = B * L
+    flops = pairs * TRAIN_FLOP_PER_PAIR + L * TRAIN_FLOP_PER_LABEL_ROW + B * TRAIN_FLOP_PER_PROTEIN
+    peak, peak_src = measured_peaks()
+    achieved = flops / (ms_step * 1e-3) / 1e12 / world
+    passes = 3 if mode == "strict" else 1
+    line = {
+        "metric": "(protein,label) pairs/sec through one TRAINING step (forward + backward + Adam), batch 64 x 32K label rows",
+        "value": pairs / (ms_step * 1e-3), "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32-grade (fp16 hi/lo planes, 3 tcgen05 passes)" if passes == 3 else "f16 operands, fp32 accumulate",
+        "data": "synthetic",
+        "config": {"workload": f"training step, batch {B} x {T} aa x {L} label rows, BCE + Adam (BASELINE.json configs[2])",
+                   "mode": mode, "sequences": B, "seq_len": T, "label_rows": L,
+                   "parallelism": "1 GPU" if world == 1 else f"label-sharded x{world}: BatchNorm sums and parameter "
+                                                              "gradients all-reduced over NCCL",
+                   "encoder": "frozen, eval-mode BatchNorm", "l2": "activations (GBs per layer) are far larger than the L2"},
+        "e2e": {"value": pairs / (ms_e2e * 1e-3), "unit": "pairs/s", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": int(onehots_h.numel() * 4 + lengths_h.numel() * 8 + labels_h.numel() * 4 + y_h.numel() * 4),
+                "d2h_bytes_per_step": 4 * world},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": {"kernel": "whole step (tensor-core GEMMs: forward, dgrad, wgrad)", "bound": "tensor",
+                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s per GPU", "frac": achieved / peak, "traffic": None,
+                     "peak_source": peak_src, "tensor_passes": passes, "executed_frac": achieved * passes / peak,
+                     "algorithmic_flops_per_step": flops},
+        "loss_trajectory": losses, "peak_memory_gib_rank0": peak_mem,
+    }
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -320,10 +439,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="strict", choices=["strict", "fast"])
+    ap.add_argument("--train-mode", default=None, choices=["strict", "fast"], help="precision of --workload train")
     ap.add_argument("--sequences", type=int, default=B_TOTAL)
     ap.add_argument("--seq-len", type=int, default=T_LEN)
     ap.add_argument("--labels", type=int, default=L_ROWS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="inference", choices=["inference", "train"],
+                    help="inference = BASELINE.json configs[1] (the metric's configuration, default); "
+                         "train = configs[2]: one training step, batch 64 x 32K label rows, BCE + Adam, label-sharded")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -338,7 +461,10 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
-        run_ours(args, rank, world, local_rank)
+        if args.workload == "train":
+            run_train(args, rank, world, local_rank)
+        else:
+            run_ours(args, rank, world, local_rank)
     finally:
         if world > 1:
             import torch.distributed as dist

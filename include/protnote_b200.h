@@ -167,6 +167,93 @@ int pn_conv1d(const float* x, const int64_t* lengths, int batch, int cin, int T,
               int cout, int taps, int dilation, float* y, void* workspace, size_t workspace_bytes, int mode,
               void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Training step primitives (`pn_t_*`).  Replace, for the trainable part of ProtNote.forward in TRAINING mode
+ * (protnote/models/ProtNote.py:168-334 with self.training; called from ProtNoteTrainer.train_one_epoch,
+ * protnote/models/ProtNoteTrainer.py:721-738), the autograd graph of
+ *   W_p / W_l  = torchvision MLP: [Linear(no bias), BatchNorm1d(batch statistics), ReLU] x (n-1), Linear   (ProtNote.py:63-81)
+ *   output MLP = get_mlp: [Linear, BatchNorm1d(batch statistics over all B*L pairs), ReLU] x n, Linear(H -> 1) (:337-378)
+ * protnote_b200/train.py sequences them (and all-reduces the per-column sums when the label axis is sharded).
+ *
+ * Activations travel as fp16 planes `hi`, `lo` ([rows][ld], ld a multiple of 64; lo NULL in PN_FAST) and, where a wgrad
+ * will contract over rows, also as transposed planes `hiT`, `loT` in the K-blocked layout [blocksT][cols][64],
+ * blocksT >= ceil(rows / 64): block i holds rows 64 i .. 64 i + 63 of every column (zero beyond `rows`).
+ * A tensor may carry a power-of-two scale `sc` (device scalar; stored = true * sc; NULL = 1): gradients are tiny and
+ * fp16 has 5 exponent bits.  All per-column sums are fp64.
+ * ---------------------------------------------------------------------------------------------------------- */
+/* sc[0] = power of two that puts max|x| into [2^5, 2^6); sc[1] is scratch (sc points to 2 floats). */
+int pn_t_autoscale(const float* x, long long rows, long long cols, long long ldx, float* sc, void* stream);
+/* planes (and transposed planes, nullable) of x * sc */
+int pn_t_split(const float* x, long long rows, long long cols, long long ldx, const float* sc, void* hi, void* lo,
+               long long ld, void* hiT, void* loT, long long blocksT, void* stream);
+/* planes [N][ld] of w * ws, element (n, k) = w[n * stride_n + k * stride_k] (so a column block of a Linear weight, or
+ * its transpose for dgrad, needs no copy); ws[0] = the power-of-two scale chosen, ws[1] scratch. */
+int pn_t_pack_weight(const float* w, long long N, long long K, long long stride_n, long long stride_k, void* hi, void* lo,
+                     long long ld, float* ws, void* stream);
+/* D[M][N] = (A[M][K] * B[N][K]^T) / (s0 * s1 * s2) on the tensor-core engine (s* device scalars, nullable).
+ *   forward Linear: A = activations, B = packed weight, s0 = ws
+ *   dgrad:          A = g_z planes,  B = packed weight^T (output keeps g_z's scale: pass s0 = ws only)
+ *   wgrad:          A = g_z^T, B = x^T (transposed planes, K-blocked: k_blocked = 1; lda / ldb unused), K = rows,
+ *                   s0 = g scale, s1 = x scale
+ * Output: fp32 `out_f32` (ld_out; accumulate != 0 adds to what is there) and/or planes out_hi/out_lo (ld_split).
+ * scale_scratch: N floats.  promote_k: K elements summed in TMEM between fp32 promotions (0 = engine default).
+ * split_k > 0 (multiple of 64, fp32 output only): K is cut into slices of split_k, one launch each, accumulated in
+ * out_f32 - for wgrad, whose K (the rows of the batch) is so long that the CTAs of one launch drift out of L2 reach. */
+int pn_t_gemm(const void* a_hi, const void* a_lo, long long M, long long K, long long lda, const void* b_hi,
+              const void* b_lo, long long N, long long ldb, const float* s0, const float* s1, const float* s2,
+              float* scale_scratch, float* out_f32, long long ld_out, int accumulate, void* out_hi, void* out_lo,
+              long long ld_split, int mode, int promote_k, long long split_k, int k_blocked, void* stream);
+/* out[0][c] = sum_r v[r][c], out[1][c] = sum_r v[r][c]^2 (fp64 [2][cols], overwritten) of planes (hi, lo) or, when x is
+ * not NULL, of the fp32 matrix x; ld = row pitch of whichever is given. */
+int pn_t_col_stats(const void* hi, const void* lo, const float* x, long long rows, int cols, long long ld, double* out,
+                   void* stream);
+/* BatchNorm1d training statistics -> state[4][cols] = scale (gamma*invstd), shift (beta - mean*scale), mean, invstd;
+ * running_mean / running_var (nullable) are updated with `momentum` (unbiased variance), as torch.nn.BatchNorm1d does.
+ * stats2 != NULL: the batch is the grid z[b][l] = a[b] + c[l] (layer 1 of the pair scorer): stats = sums of a over
+ * `count` proteins, stats2 = sums of c over `count2` label rows; mean = mean_a + mean_c, var = var_a + var_c. */
+int pn_t_bn_finalize(const double* stats, double count, const double* stats2, double count2, const float* gamma,
+                     const float* beta, float eps, float momentum, float* running_mean, float* running_var, int cols,
+                     float* state, void* stream);
+/* h = relu(z * scale + shift) as planes (+ transposed planes, nullable) */
+int pn_t_bn_relu(const void* z_hi, const void* z_lo, long long rows, int cols, long long ld_z, const float* state,
+                 void* h_hi, void* h_lo, long long ld_h, void* hT_hi, void* hT_lo, long long blocksT, void* stream);
+/* out[r] = relu(z[r] * scale + shift) . w + b  - the last hidden layer and Linear(H -> 1) (ProtNote.py:373-377) */
+int pn_t_bn_relu_dot(const void* z_hi, const void* z_lo, long long rows, int cols, long long ld_z, const float* state,
+                     const float* w, const float* b, float* out, void* stream);
+/* layer 1 of the pair scorer: h[(b, l)] = relu((a[b] + c[l]) * scale + shift), rows b * L + l; a [B][H], c [L][H] dense */
+int pn_t_pair_hidden(const float* a, long long B, const float* c, long long L, int H, const float* state, void* hi,
+                     void* lo, long long ld, void* hiT, void* loT, long long blocksT, void* stream);
+
+/* Source of a BatchNorm+ReLU backward.  kind 0: g planes, z planes.  kind 1: g = g_logit[r] * w[n] (gradient of the final
+ * Linear(H -> 1), generated on the fly), z planes.  kind 2: g planes, z[r] = a[r / L] + c[r % L] (layer 1). */
+typedef struct pn_bwd_src {
+  int kind;
+  long long rows;
+  int cols;
+  const void* g_hi; const void* g_lo; long long ld_g; const float* g_sc;
+  const float* g_logit; const float* w;
+  const void* z_hi; const void* z_lo; long long ld_z;
+  const float* a; const float* c; long long L;
+  const float* state;
+} pn_bwd_src;
+/* sums[0][c] = sum_r g_y, sums[1][c] = sum_r g_y * xhat  with g_y = g * [z*scale+shift > 0], xhat = (z - mean) * invstd
+ * (true scale, fp64 [2][cols], overwritten) = the gradients of BatchNorm's beta and gamma over these rows;
+ * maxes[2] = max|g_y|, max|xhat|; kind 1 only: dw[c] = sum_r g_logit[r] * relu(z*scale+shift)[r][c], db = sum_r g_logit[r]
+ * (gradients of the final Linear). */
+int pn_t_bwd_stats(const pn_bwd_src* src, double* sums, float* maxes, double* dw, double* db, void* stream);
+/* means[2][cols] (fp32) = sums / count, the two per-column means pass 2 subtracts; sc_out (nullable) = power-of-two scale
+ * for the g_z tensor pn_t_bwd_apply will write (from an upper bound of |g_z|).  `sums` are the totals over ALL rows of
+ * the batch (all-reduced over ranks when the rows are sharded), count = that number of rows. */
+int pn_t_bwd_scale(const double* sums, const float* maxes, const float* state, double count, int cols, float* sc_out,
+                   float* means, void* stream);
+/* g_z = scale * (g_y - means[0] - xhat * means[1]) * sc_out as planes (+ transposed planes) */
+int pn_t_bwd_apply(const pn_bwd_src* src, const float* means, const float* sc_out, void* hi, void* lo, long long ld,
+                   void* hiT, void* loT, long long blocksT, void* stream);
+/* kind 2 only: the same g_z reduced on the fly to da[b] = sum_l g_z[b, l] (fp64 scratch da64 [B][H] -> fp32 da) and
+ * dc[l] = sum_b g_z[b, l] (fp32 [L][H]), true scale. */
+int pn_t_bwd_apply_pair(const pn_bwd_src* src, const float* means, long long B, double* da64, float* da, float* dc,
+                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

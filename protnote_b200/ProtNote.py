@@ -185,12 +185,50 @@ class ProtNote(nn.Module):
         self._label_cache = (key, out, L_f)
         return out
 
+    # ------------------------------------------------------------------ training mode
+    def _forward_train(self, sequence_onehots, sequence_embeddings, sequence_lengths, label_embeddings,
+                       label_token_counts, save_embeddings):
+        """ProtNote.forward with self.training (ProtNote.py:168-334): BatchNorm batch statistics in W_p / W_l / output MLP,
+        label-embedding noise, logits [B, L] differentiable w.r.t. W_p, W_l and output_layer.  The arithmetic is the
+        `pn_t_*` primitives sequenced by protnote_b200/train.py (custom autograd.Function)."""
+        from . import train as pn_train
+        if save_embeddings:
+            raise ProtnoteB200Error("save_embeddings=True is an evaluation diagnostic; it is not available in training mode")
+        if self.train_sequence_encoder or self.label_encoder_num_trainable_layers:
+            raise ProtnoteB200Error("the sm_100a training path trains W_p, W_l and output_layer; the sequence encoder and the "
+                                    "label text encoder are frozen (TRAIN_SEQUENCE_ENCODER False, "
+                                    "LABEL_ENCODER_NUM_TRAINABLE_LAYERS 0: base_config.yaml:71-72)")
+        if label_embeddings is None:
+            raise ValueError("Incompatible label parameters passed to forward method.")
+        if self.label_embedding_pooling_method == "all":
+            raise ProtnoteB200Error("LABEL_EMBEDDING_POOLING_METHOD 'all' is not on the cached-embedding path")
+        if self.feature_fusion != "concatenation":
+            raise ProtnoteB200Error("the training path implements FEATURE_FUSION 'concatenation' (base_config.yaml:44)")
+        dev = next(self.W_p.parameters()).device
+        L_f = label_embeddings.to(dev, non_blocking=True)
+        # label-embedding noise (ProtNote.py:219-240): RNG-stream dependent, kept as the reference's own torch ops
+        if label_token_counts is not None and self.label_embedding_noising_alpha > 0:
+            scalars = self.label_embedding_noising_alpha / math.sqrt(L_f.shape[1])
+            L_f = L_f + (2 * torch.rand_like(L_f) - 1) * scalars
+        if sequence_embeddings is not None:
+            P_f = sequence_embeddings.to(dev, non_blocking=True)
+        elif sequence_onehots is not None and sequence_lengths is not None:
+            if self.sequence_encoder is None:
+                raise ValueError("Incompatible sequence parameters passed to forward method.")
+            with torch.no_grad():
+                P_f = self.sequence_encoder.get_embeddings(sequence_onehots.to(dev, non_blocking=True),
+                                                           sequence_lengths.to(dev, non_blocking=True))
+        else:
+            raise ValueError("Incompatible sequence parameters passed to forward method.")
+        logits = pn_train.train_logits(self, P_f, L_f)
+        return logits, {"output_layer_embeddings": [], "joint_embeddings": []}
+
     # ------------------------------------------------------------------ reference interface
     def forward(self, sequence_onehots=None, sequence_embeddings=None, sequence_lengths=None, tokenized_labels=None,
                 label_embeddings=None, label_token_counts=None, save_embeddings=False):
         if self.training:
-            raise ProtnoteB200Error("protnote_b200.ProtNote implements the eval-mode scoring path (BatchNorm running "
-                                    "statistics, no dropout/noise); call .eval().  Training is out of scope this round.")
+            return self._forward_train(sequence_onehots, sequence_embeddings, sequence_lengths, label_embeddings,
+                                       label_token_counts, save_embeddings)
         # ---- label embeddings (ProtNote.py:192-217): cached embeddings only
         if label_embeddings is not None:
             L_f = label_embeddings

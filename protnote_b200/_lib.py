@@ -26,6 +26,16 @@ class ScorerCfg(C.Structure):
                 ("descriptions_per_label", C.c_int), ("bn_eps", C.c_float)]
 
 
+class BwdSrc(C.Structure):
+    """pn_bwd_src of include/protnote_b200.h"""
+    _fields_ = [("kind", C.c_int), ("rows", C.c_longlong), ("cols", C.c_int),
+                ("g_hi", C.c_void_p), ("g_lo", C.c_void_p), ("ld_g", C.c_longlong), ("g_sc", C.c_void_p),
+                ("g_logit", C.c_void_p), ("w", C.c_void_p),
+                ("z_hi", C.c_void_p), ("z_lo", C.c_void_p), ("ld_z", C.c_longlong),
+                ("a", C.c_void_p), ("c", C.c_void_p), ("L", C.c_longlong),
+                ("state", C.c_void_p)]
+
+
 _P = C.c_void_p
 _LL = C.c_longlong
 _SZ = C.c_size_t
@@ -60,6 +70,20 @@ SIGNATURES = {
     "pn_linear": (_I, [_P, _LL, _LL, _LL, _P, _LL, _P, _P, _LL, _P, _SZ, _I, _P]),
     "pn_conv1d_workspace_bytes": (_SZ, [_I, _I, _I, _I, _I]),
     "pn_conv1d": (_I, [_P, _P, _I, _I, _I, _P, _P, _I, _I, _I, _P, _P, _SZ, _I, _P]),
+    # training primitives
+    "pn_t_autoscale": (_I, [_P, _LL, _LL, _LL, _P, _P]),
+    "pn_t_split": (_I, [_P, _LL, _LL, _LL, _P, _P, _P, _LL, _P, _P, _LL, _P]),
+    "pn_t_pack_weight": (_I, [_P, _LL, _LL, _LL, _LL, _P, _P, _LL, _P, _P]),
+    "pn_t_gemm": (_I, [_P, _P, _LL, _LL, _LL, _P, _P, _LL, _LL, _P, _P, _P, _P, _P, _LL, _I, _P, _P, _LL, _I, _I, _LL, _I, _P]),
+    "pn_t_col_stats": (_I, [_P, _P, _P, _LL, _I, _LL, _P, _P]),
+    "pn_t_bn_finalize": (_I, [_P, C.c_double, _P, C.c_double, _P, _P, C.c_float, C.c_float, _P, _P, _I, _P, _P]),
+    "pn_t_bn_relu": (_I, [_P, _P, _LL, _I, _LL, _P, _P, _P, _LL, _P, _P, _LL, _P]),
+    "pn_t_bn_relu_dot": (_I, [_P, _P, _LL, _I, _LL, _P, _P, _P, _P, _P]),
+    "pn_t_pair_hidden": (_I, [_P, _LL, _P, _LL, _I, _P, _P, _P, _LL, _P, _P, _LL, _P]),
+    "pn_t_bwd_stats": (_I, [C.POINTER(BwdSrc), _P, _P, _P, _P, _P]),
+    "pn_t_bwd_scale": (_I, [_P, _P, _P, C.c_double, _I, _P, _P, _P]),
+    "pn_t_bwd_apply": (_I, [C.POINTER(BwdSrc), _P, _P, _P, _P, _LL, _P, _P, _LL, _P]),
+    "pn_t_bwd_apply_pair": (_I, [C.POINTER(BwdSrc), _P, _LL, _P, _P, _P, _P]),
 }
 
 _lib = None

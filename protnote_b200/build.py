@@ -14,7 +14,7 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_DIR = os.path.join(PKG_DIR, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libprotnote_b200.so")
 SOURCES = ["pn_api.cu"]
-HEADERS = ["pn_ptx.cuh", "pn_gemm.cuh", "pn_kernels.cuh", os.path.join("..", "..", "include", "protnote_b200.h")]
+HEADERS = ["pn_ptx.cuh", "pn_gemm.cuh", "pn_gemm2.cuh", "pn_kernels.cuh", "pn_train.cuh", os.path.join("..", "..", "include", "protnote_b200.h")]
 
 
 def _nvcc() -> str:

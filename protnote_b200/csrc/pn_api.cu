@@ -12,6 +12,7 @@
 #include "../../include/protnote_b200.h"
 #include "pn_kernels.cuh"
 #include "pn_gemm2.cuh"
+#include "pn_train.cuh"
 
 namespace {
 
@@ -110,6 +111,7 @@ struct Planes {             // an fp32 tensor carried as fp16 planes, row-major,
   long long rows = 0;       // plain: M or N.  conv: batch * T
   long long cols = 0;       // logical K extent (channels for conv)
   long long ld = 0;         // row pitch in elements (multiple of 8)
+  bool kblocked = false;    // stored as [cols/64][rows][64] (K-blocked, see GemmParams::a_kblk); ld is unused
 };
 
 struct ConvView {           // A operand as [batch][T][C] with taps (taps == 0 -> plain matrix)
@@ -227,10 +229,10 @@ int launch_gemm2_t(const GemmParams& p, cudaStream_t stream) {
 
 // D = A * B^T with the fused epilogue.  A: plain [M][K] or conv view; B: packed weights [N][K_total].
 int launch_gemm(const Planes& A, const ConvView& cv, const Planes& B, long long N, const Epilogue& e, int mode,
-                cudaStream_t stream, int stage_kind = kStageOther) {
+                cudaStream_t stream, int stage_kind = kStageOther, int promote_override = -1) {
   if (mode != PN_STRICT && mode != PN_FAST) return fail("mode must be PN_STRICT or PN_FAST");
   const bool gen = e.gen_a != nullptr;
-  const bool cta2 = g_cta2 && !gen;
+  const bool cta2 = g_cta2 && !gen && !A.kblocked && !B.kblocked;
   const int tile_rows = cta2 ? 2 * kBM : kBM;
   const int bk = gen ? 32 : pick_bk(mode);
   GemmParams p;
@@ -261,7 +263,14 @@ int launch_gemm(const Planes& A, const ConvView& cv, const Planes& B, long long 
     p.M = (int)A.rows;
     p.tiles_m = (int)((A.rows + tile_rows - 1) / tile_rows);
     p.num_kblocks = (int)((A.cols + bk - 1) / bk);
-    if (!gen) {
+    if (!gen && A.kblocked) {
+      const cuuint64_t dims[3] = {64, (cuuint64_t)A.rows, (cuuint64_t)((A.cols + 63) / 64)};
+      const cuuint64_t strides[2] = {128, (cuuint64_t)A.rows * 128};
+      const cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)kBM, 1};
+      PN_TRY(make_map(&p.tm_a_hi, A.hi, 3, dims, strides, box, bk * 2));
+      if (need_lo) PN_TRY(make_map(&p.tm_a_lo, A.lo, 3, dims, strides, box, bk * 2));
+      p.a_kblk = 1;
+    } else if (!gen) {
       const cuuint64_t dims[2] = {(cuuint64_t)A.cols, (cuuint64_t)A.rows};
       const cuuint64_t strides[1] = {(cuuint64_t)A.ld * 2};
       const cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)kBM};
@@ -273,12 +282,21 @@ int launch_gemm(const Planes& A, const ConvView& cv, const Planes& B, long long 
   p.chunk_kblocks = p.num_kblocks;
   // algorithmic FLOPs of this launch (2*M*N*K), recorded only for the pair scorer's GEMMs
   p.timed_flops = stage_kind == kStageScorer ? 2.0 * (double)A.rows * (double)N * (double)A.cols : 0.0;
-  const int promote_k = g_promote_k[stage_kind];
-  if (mode == PN_STRICT && promote_k > 0) {
+  // promote_override > 0 forces a promotion period in either mode (wgrad: K = rows of the batch, far too long a chain
+  // for the truncating tensor-core accumulator even at fp16 operand precision)
+  const int promote_k = promote_override >= 0 ? promote_override : g_promote_k[stage_kind];
+  if ((mode == PN_STRICT || promote_override > 0) && promote_k > 0) {
     p.chunk_kblocks = promote_k / bk > 0 ? promote_k / bk : 1;
     if (p.chunk_kblocks > p.num_kblocks) p.chunk_kblocks = p.num_kblocks;
   }
-  {
+  if (B.kblocked) {
+    const cuuint64_t dims[3] = {64, (cuuint64_t)B.rows, (cuuint64_t)((B.cols + 63) / 64)};
+    const cuuint64_t strides[2] = {128, (cuuint64_t)B.rows * 128};
+    const cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)p.bn, 1};
+    PN_TRY(make_map(&p.tm_b_hi, B.hi, 3, dims, strides, box, bk * 2));
+    if (need_lo) PN_TRY(make_map(&p.tm_b_lo, B.lo, 3, dims, strides, box, bk * 2));
+    p.b_kblk = 1;
+  } else {
     const cuuint64_t dims[2] = {(cuuint64_t)B.cols, (cuuint64_t)B.rows};
     const cuuint64_t strides[1] = {(cuuint64_t)B.ld * 2};
     const cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)(cta2 ? p.bn / 2 : p.bn)};
@@ -595,6 +613,56 @@ size_t scorer_row_bytes(const pn_scorer_cfg& c) {
   return ld_h * 2 /*bytes*/ * 2 /*planes*/ * 2 /*ping-pong*/ + (size_t)tiles_n_for(c.out_hidden) * 2 * 4;
 }
 
+}  // namespace
+
+// helpers of the training primitives
+namespace {
+template <class P>
+int launch_emit(const P& prod, long long rows, int cols, void* hi, void* lo, long long ld, void* hiT, void* loT,
+                long long blocksT, cudaStream_t stream) {
+  if (rows <= 0 || cols <= 0) return fail("empty tensor");
+  if (hi == nullptr) return fail("hi plane is required");
+  if (ld % 8 != 0 || ld < cols) return fail("plane pitch %lld must be a multiple of 8 and >= cols %d", ld, cols);
+  if (hiT && blocksT * kTileDim < rows) return fail("transposed planes hold %lld blocks of 64 rows, %lld rows need more", blocksT, rows);
+  const long long row_tiles = (rows + kTileDim - 1) / kTileDim;
+  const long long col_tiles = (ld + kTileDim - 1) / kTileDim;
+  if (col_tiles > 65535) return fail("too many columns");
+  emit_tile_kernel<P><<<dim3((unsigned)row_tiles, (unsigned)col_tiles), 256, 0, stream>>>(
+      prod, rows, cols, static_cast<__half*>(hi), static_cast<__half*>(lo), ld, static_cast<__half*>(hiT),
+      static_cast<__half*>(loT));
+  g_launches++;
+  PN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+long long slab_rows(long long rows, int col_blocks) {
+  long long slabs = ((long long)num_sms() * 8 + col_blocks - 1) / col_blocks;
+  if (slabs < 1) slabs = 1;
+  long long per = (rows + slabs - 1) / slabs;
+  per = (per + 7) / 8 * 8;
+  return per < 8 ? 8 : per;
+}
+
+BwdSrc to_src(const pn_bwd_src& s) {
+  BwdSrc d;
+  d.kind = s.kind; d.rows = s.rows; d.cols = s.cols;
+  d.g_hi = static_cast<const __half*>(s.g_hi); d.g_lo = static_cast<const __half*>(s.g_lo); d.ld_g = s.ld_g; d.g_sc = s.g_sc;
+  d.g_logit = s.g_logit; d.w = s.w;
+  d.z_hi = static_cast<const __half*>(s.z_hi); d.z_lo = static_cast<const __half*>(s.z_lo); d.ld_z = s.ld_z;
+  d.a = s.a; d.c = s.c; d.L = s.L;
+  d.state = s.state;
+  return d;
+}
+
+int check_src(const pn_bwd_src* s) {
+  if (!s) return fail("null backward source");
+  if (s->kind < 0 || s->kind > 2) return fail("unknown backward source kind %d", s->kind);
+  if (s->rows <= 0 || s->cols <= 0 || !s->state) return fail("empty backward source");
+  if (s->kind == 1 ? (!s->g_logit || !s->w) : (!s->g_hi || s->ld_g % 8 != 0)) return fail("backward source: gradient operand missing");
+  if (s->kind == 2 ? (!s->a || !s->c || s->L <= 0 || s->rows % s->L != 0) : (!s->z_hi || s->ld_z % 8 != 0))
+    return fail("backward source: pre-activation operand missing");
+  return 0;
+}
 }  // namespace
 
 // ================================================================================================
@@ -1177,6 +1245,225 @@ int pn_conv1d(const float* x, const int64_t* lengths, int batch, int cin, int T,
   e.scale = ws.at<float>(pl.scale); e.shift = ws.at<float>(pl.shift);
   e.out_f32 = y; e.ld_out = cout;
   return launch_gemm(A, cv, weight_planes(ws, pl), cout, e, mode, stream);
+}
+
+// ---------------------------------------------------------------------------------------- training primitives
+int pn_t_autoscale(const float* x, long long rows, long long cols, long long ldx, float* sc, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (rows <= 0 || cols <= 0) return fail("empty tensor");
+  unsigned* am = reinterpret_cast<unsigned*>(sc) + 1;
+  PN_CUDA(cudaMemsetAsync(am, 0, 4, stream));
+  absmax_kernel<<<ew_grid(rows * cols), 256, 0, stream>>>(x, rows, cols, ldx, am);
+  autoscale_finish_kernel<<<1, 1, 0, stream>>>(sc);
+  g_launches += 2;
+  PN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+
+int pn_t_split(const float* x, long long rows, long long cols, long long ldx, const float* sc, void* hi, void* lo,
+               long long ld, void* hiT, void* loT, long long blocksT, void* stream) {
+  SplitProducer p{x, rows, (int)cols, ldx, sc};
+  return launch_emit(p, rows, (int)cols, hi, lo, ld, hiT, loT, blocksT, static_cast<cudaStream_t>(stream));
+}
+
+int pn_t_pack_weight(const float* w, long long N, long long K, long long stride_n, long long stride_k, void* hi, void* lo,
+                     long long ld, float* ws, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (N <= 0 || K <= 0 || ld < K || ld % 64 != 0) return fail("bad weight shape (N %lld, K %lld, ld %lld)", N, K, ld);
+  unsigned* am = reinterpret_cast<unsigned*>(ws) + 1;
+  PN_CUDA(cudaMemsetAsync(am, 0, 4, stream));
+  // max |w| over the N x K view: walk it as N*K single-element "rows" when it is not row-contiguous
+  if (stride_k == 1) {
+    absmax_kernel<<<ew_grid(N * K), 256, 0, stream>>>(w, N, K, stride_n, am);
+  } else if (stride_n == 1) {
+    absmax_kernel<<<ew_grid(N * K), 256, 0, stream>>>(w, K, N, stride_k, am);
+  } else {
+    return fail("weight view must be contiguous along one axis");
+  }
+  g_launches++;
+  PN_CUDA(cudaGetLastError());
+  pack_weight_kernel<<<ew_grid(N * ld), 256, 0, stream>>>(w, (int)N, (int)K, 1, stride_n, stride_k, 0, (int)ld, (int)ld, am,
+                                                          ws, static_cast<__half*>(hi), static_cast<__half*>(lo));
+  g_launches++;
+  PN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int pn_t_gemm(const void* a_hi, const void* a_lo, long long M, long long K, long long lda, const void* b_hi,
+              const void* b_lo, long long N, long long ldb, const float* s0, const float* s1, const float* s2,
+              float* scale_scratch, float* out_f32, long long ld_out, int accumulate, void* out_hi, void* out_lo,
+              long long ld_split, int mode, int promote_k, long long split_k, int k_blocked, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (M <= 0 || N <= 0 || K <= 0) return fail("empty GEMM");
+  if (split_k < 0 || split_k % 64 != 0) return fail("split_k must be a non-negative multiple of 64");
+  if (split_k > 0 && (!out_f32 || out_hi)) return fail("split_k needs an fp32 output only");
+  if (!a_hi || !b_hi || !scale_scratch) return fail("GEMM operand missing");
+  if (!k_blocked && (lda % 8 != 0 || ldb % 8 != 0)) return fail("operand pitches must be multiples of 8 elements");
+  if (!out_f32 && !out_hi) return fail("GEMM has no output");
+  scale_vector_kernel<<<(int)((N + 255) / 256), 256, 0, stream>>>(scale_scratch, (int)N, s0, s1, s2);
+  g_launches++;
+  PN_CUDA(cudaGetLastError());
+  Planes A, B;
+  A.hi = static_cast<const __half*>(a_hi); A.lo = static_cast<const __half*>(a_lo); A.rows = M; A.cols = K; A.ld = lda;
+  B.hi = static_cast<const __half*>(b_hi); B.lo = static_cast<const __half*>(b_lo); B.rows = N; B.cols = K; B.ld = ldb;
+  A.kblocked = B.kblocked = k_blocked != 0;
+  Epilogue e;
+  e.scale = scale_scratch;
+  if (out_f32) {
+    e.out_f32 = out_f32; e.ld_out = ld_out;
+    if (accumulate) { e.resid = out_f32; e.ld_resid = ld_out; }
+  }
+  if (out_hi) {
+    e.out_hi = static_cast<__half*>(out_hi); e.out_lo = static_cast<__half*>(out_lo); e.ld_split = ld_split;
+  }
+  if (split_k == 0 || K <= split_k)
+    return launch_gemm(A, ConvView(), B, N, e, mode, stream, kStageHeads, promote_k > 0 ? promote_k : -1);
+  // K in slices, one launch each, accumulating in the fp32 output: CTAs of one launch stay within `split_k` of each other
+  // along K, so the operand panels they share are still in L2 when the next CTA asks for them (a single launch over
+  // K = millions of rows lets the CTAs drift apart and re-reads the panels from HBM ~8x, measured).
+  for (long long k0 = 0; k0 < K; k0 += split_k) {
+    Planes As = A, Bs = B;
+    const long long kk = K - k0 < split_k ? K - k0 : split_k;
+    // K-blocked operands [K/64][rows][64]: slice k0 starts at block k0/64
+    const long long oa = k_blocked ? (k0 / 64) * M * 64 : k0, ob = k_blocked ? (k0 / 64) * N * 64 : k0;
+    As.hi += oa; Bs.hi += ob;
+    if (As.lo) As.lo += oa;
+    if (Bs.lo) Bs.lo += ob;
+    As.cols = kk; Bs.cols = kk;
+    if (k0 > 0) { e.resid = out_f32; e.ld_resid = ld_out; }
+    PN_TRY(launch_gemm(As, ConvView(), Bs, N, e, mode, stream, kStageHeads, promote_k > 0 ? promote_k : -1));
+  }
+  return 0;
+}
+
+int pn_t_col_stats(const void* hi, const void* lo, const float* x, long long rows, int cols, long long ld, double* out,
+                   void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (rows <= 0 || cols <= 0) return fail("empty tensor");
+  if (!x && (!hi || ld % 8 != 0)) return fail("column statistics: planes missing or pitch not a multiple of 8");
+  PN_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * 2 * cols, stream));
+  const int col_blocks = (cols + 255) / 256;
+  const long long per = slab_rows(rows, col_blocks);
+  const long long slabs = (rows + per - 1) / per;
+  col_stats_kernel<<<dim3(col_blocks, (unsigned)slabs), dim3(32, 8), 0, stream>>>(
+      static_cast<const __half*>(hi), static_cast<const __half*>(lo), x, rows, cols, ld, per, out);
+  g_launches++;
+  PN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int pn_t_bn_finalize(const double* stats, double count, const double* stats2, double count2, const float* gamma,
+                     const float* beta, float eps, float momentum, float* running_mean, float* running_var, int cols,
+                     float* state, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (cols <= 0 || !(count > 0) || (stats2 && !(count2 > 0))) return fail("bad BatchNorm statistics");
+  bn_finalize_kernel<<<(cols + 255) / 256, 256, 0, stream>>>(stats, count, stats2, count2, gamma, beta, eps, momentum,
+                                                             running_mean, running_var, cols, state);
+  g_launches++;
+  PN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int pn_t_bn_relu(const void* z_hi, const void* z_lo, long long rows, int cols, long long ld_z, const float* state,
+                 void* h_hi, void* h_lo, long long ld_h, void* hT_hi, void* hT_lo, long long blocksT, void* stream) {
+  if (!z_hi || ld_z % 8 != 0) return fail("pre-activation planes missing or pitch not a multiple of 8");
+  BnReluProducer p{static_cast<const __half*>(z_hi), static_cast<const __half*>(z_lo), rows, cols, ld_z, state};
+  return launch_emit(p, rows, cols, h_hi, h_lo, ld_h, hT_hi, hT_lo, blocksT, static_cast<cudaStream_t>(stream));
+}
+
+int pn_t_bn_relu_dot(const void* z_hi, const void* z_lo, long long rows, int cols, long long ld_z, const float* state,
+                     const float* w, const float* b, float* out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (rows <= 0 || cols <= 0 || !z_hi || ld_z % 8 != 0) return fail("bad input to bn_relu_dot");
+  bn_relu_dot_kernel<<<ew_grid(rows * 32), 256, 0, stream>>>(static_cast<const __half*>(z_hi),
+                                                             static_cast<const __half*>(z_lo), rows, cols, ld_z, state, w,
+                                                             b, out);
+  g_launches++;
+  PN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int pn_t_pair_hidden(const float* a, long long B, const float* c, long long L, int H, const float* state, void* hi,
+                     void* lo, long long ld, void* hiT, void* loT, long long blocksT, void* stream) {
+  if (B <= 0 || L <= 0) return fail("empty pair grid");
+  PairHiddenProducer p{a, c, L, B * L, H, state};
+  return launch_emit(p, B * L, H, hi, lo, ld, hiT, loT, blocksT, static_cast<cudaStream_t>(stream));
+}
+
+int pn_t_bwd_stats(const pn_bwd_src* src, double* sums, float* maxes, double* dw, double* db, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PN_TRY(check_src(src));
+  const BwdSrc s = to_src(*src);
+  PN_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * s.cols, stream));
+  PN_CUDA(cudaMemsetAsync(maxes, 0, 8, stream));
+  if (s.kind == 1) {
+    if (!dw || !db) return fail("kind 1 needs dw and db");
+    PN_CUDA(cudaMemsetAsync(dw, 0, sizeof(double) * s.cols, stream));
+    PN_CUDA(cudaMemsetAsync(db, 0, sizeof(double), stream));
+  }
+  const int col_blocks = (s.cols + 255) / 256;
+  // kind 2 walks a slab of LABELS for every protein (pn_train.cuh): 128 labels keep the slab's c rows cache-resident
+  const long long extent = s.kind == 2 ? s.L : s.rows;
+  long long per = s.kind == 2 ? 128 : slab_rows(s.rows, col_blocks);
+  long long slabs = (extent + per - 1) / per;
+  if (slabs > 65535) {
+    per = (extent + 65534) / 65535;
+    per = (per + 31) / 32 * 32;
+    slabs = (extent + per - 1) / per;
+  }
+  const dim3 grid(col_blocks, (unsigned)slabs), block(32, 8);
+  unsigned* mx = reinterpret_cast<unsigned*>(maxes);
+  if (s.kind == 0) bwd_stats_kernel<0><<<grid, block, 0, stream>>>(s, per, sums, mx, dw, db);
+  else if (s.kind == 1) bwd_stats_kernel<1><<<grid, block, 0, stream>>>(s, per, sums, mx, dw, db);
+  else bwd_stats_kernel<2><<<grid, block, 0, stream>>>(s, per, sums, mx, dw, db);
+  g_launches++;
+  PN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int pn_t_bwd_scale(const double* sums, const float* maxes, const float* state, double count, int cols, float* sc_out,
+                   float* means, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (cols <= 0 || !(count > 0) || !means) return fail("bad backward statistics");
+  bwd_scale_kernel<<<1, 256, 0, stream>>>(sums, reinterpret_cast<const unsigned*>(maxes), state, count, cols, sc_out, means);
+  g_launches++;
+  PN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int pn_t_bwd_apply(const pn_bwd_src* src, const float* means, const float* sc_out, void* hi, void* lo, long long ld,
+                   void* hiT, void* loT, long long blocksT, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PN_TRY(check_src(src));
+  if (!means) return fail("means missing");
+  const BwdSrc s = to_src(*src);
+  if (s.kind == 0) return launch_emit(BwdApplyProducer<0>{s, means, sc_out}, s.rows, s.cols, hi, lo, ld, hiT, loT, blocksT, stream);
+  if (s.kind == 1) return launch_emit(BwdApplyProducer<1>{s, means, sc_out}, s.rows, s.cols, hi, lo, ld, hiT, loT, blocksT, stream);
+  return launch_emit(BwdApplyProducer<2>{s, means, sc_out}, s.rows, s.cols, hi, lo, ld, hiT, loT, blocksT, stream);
+}
+
+int pn_t_bwd_apply_pair(const pn_bwd_src* src, const float* means, long long B, double* da64, float* da, float* dc,
+                        void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PN_TRY(check_src(src));
+  if (src->kind != 2 || B <= 0 || B * src->L != src->rows) return fail("pair backward needs a kind-2 source with rows == B * L");
+  if (!means) return fail("means missing");
+  if (B > 65535) return fail("too many proteins for one launch (%lld)", B);
+  const BwdSrc s = to_src(*src);
+  PN_CUDA(cudaMemsetAsync(da64, 0, sizeof(double) * B * s.cols, stream));
+  const int col_blocks = (s.cols + 255) / 256;
+  const long long l_blocks = (s.L + 7) / 8;
+  if (l_blocks > 65535) return fail("too many label rows for one launch (%lld)", s.L);
+  pair_dc_kernel<<<dim3(col_blocks, (unsigned)l_blocks), dim3(32, 8), 0, stream>>>(s, means, B, dc);
+  long long per = 128;
+  long long slabs = (s.L + per - 1) / per;
+  if (slabs > 65535) return fail("too many label rows for one launch (%lld)", s.L);
+  pair_da_kernel<<<dim3(col_blocks, (unsigned)slabs), dim3(32, 8), 0, stream>>>(s, means, B, per, da64);
+  f64_to_f32_kernel<<<ew_grid(B * s.cols), 256, 0, stream>>>(da64, da, B * s.cols);
+  g_launches += 3;
+  PN_CUDA(cudaGetLastError());
+  return 0;
 }
 
 }  // extern "C"

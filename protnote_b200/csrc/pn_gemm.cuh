@@ -60,6 +60,9 @@ struct alignas(64) GemmParams {
   int chunk_kblocks;     // k-blocks per accumulator chunk (promotion period), >= 1
   // conv addressing (conv_taps == 0 -> plain)
   int conv_taps, conv_cblocks, conv_cpad, conv_dil, conv_T, conv_tiles_per_seq;
+  // K-blocked operands (wgrad): the operand is stored as [K/64][rows][64] so that the 128-byte row pieces of one k-block
+  // are contiguous; its tensor map is 3-D (k within block, row, block) and the K coordinate is split accordingly
+  int a_kblk, b_kblk;
   const long long* lengths;      // [B] valid positions per sequence (conv) or nullptr
   // pair-row addressing for the additive row terms: row r -> (r / pair_nl, r % pair_nl)
   int pair_nl;
@@ -374,11 +377,21 @@ __global__ void __launch_bounds__(GEN ? kGenThreads : kGemmThreads, 1) gemm_kern
             tma_load_3d(sa, &p.tm_a_hi, full_bar(stage), kc, t, seq);
             if (NPASS == 3) tma_load_3d(sa + Cfg::kATile, &p.tm_a_lo, full_bar(stage), kc, t, seq);
           } else if (!GEN) {
-            tma_load_2d(sa, &p.tm_a_hi, full_bar(stage), kcol, m_tile * kBM);
-            if (NPASS == 3) tma_load_2d(sa + Cfg::kATile, &p.tm_a_lo, full_bar(stage), kcol, m_tile * kBM);
+            if (p.a_kblk) {
+              tma_load_3d(sa, &p.tm_a_hi, full_bar(stage), kcol & 63, m_tile * kBM, kcol >> 6);
+              if (NPASS == 3) tma_load_3d(sa + Cfg::kATile, &p.tm_a_lo, full_bar(stage), kcol & 63, m_tile * kBM, kcol >> 6);
+            } else {
+              tma_load_2d(sa, &p.tm_a_hi, full_bar(stage), kcol, m_tile * kBM);
+              if (NPASS == 3) tma_load_2d(sa + Cfg::kATile, &p.tm_a_lo, full_bar(stage), kcol, m_tile * kBM);
+            }
           }
-          tma_load_2d(sb, &p.tm_b_hi, full_bar(stage), kcol, n_tile * p.bn);
-          if (NPASS == 3) tma_load_2d(sb + Cfg::kBTile, &p.tm_b_lo, full_bar(stage), kcol, n_tile * p.bn);
+          if (p.b_kblk) {
+            tma_load_3d(sb, &p.tm_b_hi, full_bar(stage), kcol & 63, n_tile * p.bn, kcol >> 6);
+            if (NPASS == 3) tma_load_3d(sb + Cfg::kBTile, &p.tm_b_lo, full_bar(stage), kcol & 63, n_tile * p.bn, kcol >> 6);
+          } else {
+            tma_load_2d(sb, &p.tm_b_hi, full_bar(stage), kcol, n_tile * p.bn);
+            if (NPASS == 3) tma_load_2d(sb + Cfg::kBTile, &p.tm_b_lo, full_bar(stage), kcol, n_tile * p.bn);
+          }
           if (GEN) {
             // Label-half tiles run AHEAD of the operand stages (up to the depth of their own ring), so that the
             // generator can start on a k-block the moment its operand stage is released.

@@ -1,0 +1,670 @@
+// HBM-streaming kernels of the TRAINING step (reference: ProtNote.forward with self.training, protnote/models/
+// ProtNote.py:168-334; BatchNorm1d batch statistics of torchvision MLP / get_mlp, ProtNote.py:63-81,337-378).
+//
+// The contractions of the training step (forward Linear, dgrad, wgrad) run on the tensor-core engine of pn_gemm.cuh.
+// What is left is memory-bound work over [rows][cols] activation tensors stored as fp16 hi/lo planes:
+//   column statistics (sum, sum of squares)            -> BatchNorm batch mean / variance
+//   normalise + ReLU (+ transposed copy for wgrad)      -> next layer's operand
+//   BatchNorm+ReLU backward: two column sums, then the gradient w.r.t. the Linear output (+ transposed copy)
+//   layer 1 of the pair scorer, z1[b,l] = a[b] + c[l]: generated on the fly in forward, reduced to (da, dc) in backward
+// Every kernel moves 16 bytes per thread per plane, rows are 128-byte aligned, column sums accumulate in fp64.
+//
+// Transposed copies.  wgrad contracts over ROWS (dW = g^T x), and the engine wants both operands K-major, so every
+// tensor that feeds a wgrad is also written transposed, in the K-BLOCKED layout [ceil(rows/64)][cols][64]: the 64 rows
+// of a block are the contiguous 128 bytes the tensor core's k-block wants, and the pieces of consecutive columns are
+// adjacent, so an operand tile of a k-block is one contiguous 16-32 KB run (a plain [cols][rows] matrix would put
+// every 128-byte piece on a different page: measured 7x slower wgrad from TLB / DRAM-page misses).  A 64x64 tile goes
+// through shared memory as 32-bit words holding two vertically adjacent halves, so both the row-major and the
+// transposed stores are 16-byte vectors.
+#pragma once
+
+#include "pn_kernels.cuh"
+
+namespace pn {
+
+constexpr int kTileDim = 64;
+constexpr int kTilePitch = 33;
+// rows a reduction thread keeps in flight per iteration (2 measured faster than 4 on B200: registers -> occupancy)
+constexpr int kRif = 2;   // words per transposed tile row (odd pitch: conflict-free column reads)
+
+__device__ __forceinline__ void load8(const __half* __restrict__ hi, const __half* __restrict__ lo, float (&v)[8]) {
+  const uint4 h = *reinterpret_cast<const uint4*>(hi);
+  const __half2* h2 = reinterpret_cast<const __half2*>(&h);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = __half22float2(h2[j]);
+    v[2 * j] = f.x;
+    v[2 * j + 1] = f.y;
+  }
+  if (lo) {
+    const uint4 l = *reinterpret_cast<const uint4*>(lo);
+    const __half2* l2 = reinterpret_cast<const __half2*>(&l);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(l2[j]);
+      v[2 * j] += f.x;
+      v[2 * j + 1] += f.y;
+    }
+  }
+}
+
+__device__ __forceinline__ void load8_f32(const float* __restrict__ p, int n_valid, float (&v)[8]) {
+  if (n_valid >= 8 && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p + 4));
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = j < n_valid ? __ldg(p + j) : 0.f;
+  }
+}
+
+// BatchNorm state of one layer: float state[4][cols] = scale (gamma * invstd), shift (beta - mean * scale), mean, invstd
+struct BnVec {
+  float scale[8], shift[8], mean[8], invstd[8];
+};
+__device__ __forceinline__ void load_bn(const float* __restrict__ state, int cols, int c0, BnVec& b) {
+  const int n = cols - c0;
+  load8_f32(state + c0, n, b.scale);
+  load8_f32(state + cols + c0, n, b.shift);
+  load8_f32(state + 2 * (long long)cols + c0, n, b.mean);
+  load8_f32(state + 3 * (long long)cols + c0, n, b.invstd);
+}
+
+// ------------------------------------------------------------------------------------------------
+// producers: 8 consecutive columns of one row of the tensor a kernel emits
+// ------------------------------------------------------------------------------------------------
+// raw 16-byte plane loads first, conversion later: the two rows a thread produces have their loads in flight together
+struct Raw8 {
+  uint4 h, l;
+};
+__device__ __forceinline__ void raw_load(const __half* __restrict__ hi, const __half* __restrict__ lo, long long off,
+                                         Raw8& r) {
+  r.h = *reinterpret_cast<const uint4*>(hi + off);
+  r.l = lo ? *reinterpret_cast<const uint4*>(lo + off) : make_uint4(0u, 0u, 0u, 0u);
+}
+__device__ __forceinline__ void raw_to_f32(const Raw8& r, float (&v)[8]) {
+  const __half2* h2 = reinterpret_cast<const __half2*>(&r.h);
+  const __half2* l2 = reinterpret_cast<const __half2*>(&r.l);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = __half22float2(h2[j]), g = __half22float2(l2[j]);
+    v[2 * j] = f.x + g.x;
+    v[2 * j + 1] = f.y + g.y;
+  }
+}
+__device__ __forceinline__ void zero8(float (&v)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = 0.f;
+}
+
+struct SplitProducer {          // x * sc
+  const float* x; long long rows; int cols; long long ldx; const float* sc;
+  __device__ __forceinline__ void operator()(long long r, int c0, float (&va)[8], float (&vb)[8]) const {
+    const float s = sc ? __ldg(sc) : 1.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      va[j] = (r < rows && c0 + j < cols) ? x[r * ldx + c0 + j] * s : 0.f;
+      vb[j] = (r + 1 < rows && c0 + j < cols) ? x[(r + 1) * ldx + c0 + j] * s : 0.f;
+    }
+  }
+};
+
+struct BnReluProducer {         // relu(z * scale + shift)
+  const __half* zh; const __half* zl; long long rows; int cols; long long ld; const float* state;
+  __device__ __forceinline__ void operator()(long long r, int c0, float (&va)[8], float (&vb)[8]) const {
+    zero8(va);
+    zero8(vb);
+    if (r >= rows || c0 >= cols) return;
+    const bool two = r + 1 < rows;
+    Raw8 ra, rb;
+    raw_load(zh, zl, r * ld + c0, ra);
+    if (two) raw_load(zh, zl, (r + 1) * ld + c0, rb);
+    float sc[8], sf[8];
+    load8_f32(state + c0, cols - c0, sc);
+    load8_f32(state + cols + c0, cols - c0, sf);
+    raw_to_f32(ra, va);
+    if (two) raw_to_f32(rb, vb);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const bool ok = c0 + j < cols;
+      va[j] = ok ? fmaxf(fmaf(va[j], sc[j], sf[j]), 0.f) : 0.f;
+      vb[j] = (ok && two) ? fmaxf(fmaf(vb[j], sc[j], sf[j]), 0.f) : 0.f;
+    }
+  }
+};
+
+struct PairHiddenProducer {     // relu((a[b] + c[l]) * scale + shift), row r = b * L + l   (ProtNote.py:112-126 + layer 1)
+  const float* a; const float* c; long long L; long long rows; int cols; const float* state;
+  __device__ __forceinline__ void one(long long r, int c0, const float (&sc)[8], const float (&sf)[8], float (&v)[8]) const {
+    float av[8], cv[8];
+    load8_f32(a + (r / L) * cols + c0, cols - c0, av);
+    load8_f32(c + (r % L) * cols + c0, cols - c0, cv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = c0 + j < cols ? fmaxf(fmaf(av[j] + cv[j], sc[j], sf[j]), 0.f) : 0.f;
+  }
+  __device__ __forceinline__ void operator()(long long r, int c0, float (&va)[8], float (&vb)[8]) const {
+    zero8(va);
+    zero8(vb);
+    if (r >= rows || c0 >= cols) return;
+    float sc[8], sf[8];
+    load8_f32(state + c0, cols - c0, sc);
+    load8_f32(state + cols + c0, cols - c0, sf);
+    one(r, c0, sc, sf, va);
+    if (r + 1 < rows) one(r + 1, c0, sc, sf, vb);
+  }
+};
+
+// Sources of the BatchNorm+ReLU backward.  kind 0: g planes, z planes.  kind 1: g = g_logit[r] * w[n] (the gradient of
+// the final Linear(H -> 1), never materialised), z planes.  kind 2: g planes, z = a[r / L] + c[r % L].
+struct BwdSrc {
+  int kind;
+  long long rows; int cols;
+  const __half* g_hi; const __half* g_lo; long long ld_g; const float* g_sc;
+  const float* g_logit; const float* w;
+  const __half* z_hi; const __half* z_lo; long long ld_z;
+  const float* a; const float* c; long long L;
+  const float* state;
+};
+
+// what one thread needs from memory for 8 columns of one row
+struct BwdRaw {
+  Raw8 g, z;
+  float gl;
+};
+template <int KIND>
+__device__ __forceinline__ void bwd_raw_load(const BwdSrc& s, long long r, int c0, BwdRaw& q) {
+  if (KIND == 1) q.gl = __ldg(s.g_logit + r);
+  else raw_load(s.g_hi, s.g_lo, r * s.ld_g + c0, q.g);
+  if (KIND != 2) raw_load(s.z_hi, s.z_lo, r * s.ld_z + c0, q.z);
+}
+// true-scale g_y = g * [relu active], xhat and the pre-activation for 8 columns of row r (columns >= cols give zeros)
+template <int KIND>
+__device__ __forceinline__ void bwd_eval(const BwdSrc& s, const BwdRaw& q, long long r, int c0, const BnVec& b,
+                                         const float (&wv)[8], float inv_gsc, float (&gy)[8], float (&xh)[8],
+                                         float (&pre)[8]) {
+  float g[8], z[8];
+  if (KIND == 1) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] = q.gl * wv[j];
+  } else {
+    raw_to_f32(q.g, g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] *= inv_gsc;
+  }
+  if (KIND == 2) {
+    float av[8], cv[8];
+    load8_f32(s.a + (r / s.L) * s.cols + c0, s.cols - c0, av);
+    load8_f32(s.c + (r % s.L) * s.cols + c0, s.cols - c0, cv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) z[j] = av[j] + cv[j];
+  } else {
+    raw_to_f32(q.z, z);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const bool ok = c0 + j < s.cols;
+    pre[j] = ok ? fmaf(z[j], b.scale[j], b.shift[j]) : 0.f;
+    gy[j] = (ok && pre[j] > 0.f) ? g[j] : 0.f;
+    xh[j] = ok ? (z[j] - b.mean[j]) * b.invstd[j] : 0.f;
+  }
+}
+
+template <int KIND>
+struct BwdApplyProducer {       // g_z = scale * (g_y - m1 - xhat * m2) * sc_out,  m = sums / count (fp32 [2][cols])
+  BwdSrc s; const float* means; const float* sc_out;
+  __device__ __forceinline__ void operator()(long long r, int c0, float (&va)[8], float (&vb)[8]) const {
+    zero8(va);
+    zero8(vb);
+    if (r >= s.rows || c0 >= s.cols) return;
+    const bool two = r + 1 < s.rows;
+    BwdRaw qa, qb;
+    bwd_raw_load<KIND>(s, r, c0, qa);
+    if (two) bwd_raw_load<KIND>(s, r + 1, c0, qb);
+    BnVec b;
+    load_bn(s.state, s.cols, c0, b);
+    float m1[8], m2[8], wv[8];
+    load8_f32(means + c0, s.cols - c0, m1);
+    load8_f32(means + s.cols + c0, s.cols - c0, m2);
+    if (KIND == 1) load8_f32(s.w + c0, s.cols - c0, wv);
+    else zero8(wv);
+    const float inv_gsc = s.g_sc ? 1.f / __ldg(s.g_sc) : 1.f;
+    const float so = sc_out ? __ldg(sc_out) : 1.f;
+    float gy[8], xh[8], pre[8];
+    bwd_eval<KIND>(s, qa, r, c0, b, wv, inv_gsc, gy, xh, pre);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) va[j] = c0 + j < s.cols ? b.scale[j] * (gy[j] - m1[j] - xh[j] * m2[j]) * so : 0.f;
+    if (two) {
+      bwd_eval<KIND>(s, qb, r + 1, c0, b, wv, inv_gsc, gy, xh, pre);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) vb[j] = c0 + j < s.cols ? b.scale[j] * (gy[j] - m1[j] - xh[j] * m2[j]) * so : 0.f;
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// tile emitter: planes [rows][ld] and (optionally) K-blocked transposed planes [ceil(rows/64)][cols][64]
+// grid (row tiles, col tiles), 256 threads.  Thread (warp w, lane l) produces rows 2*rp, 2*rp+1 (rp = 4w + l/8) x
+// 8 columns (l%8); phase 2 thread t stores 16 rows of column t/4.
+// ------------------------------------------------------------------------------------------------
+template <class P>
+__global__ void __launch_bounds__(256) emit_tile_kernel(const P prod, long long rows, int cols, __half* __restrict__ hi,
+                                                        __half* __restrict__ lo, long long ld, __half* __restrict__ hiT,
+                                                        __half* __restrict__ loT) {
+  __shared__ uint32_t sh[2][kTileDim * kTilePitch];
+  const long long r0 = (long long)blockIdx.x * kTileDim;
+  const int c0 = blockIdx.y * kTileDim;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int cc = lane & 7, rp = warp * 4 + (lane >> 3);
+  const long long ra = r0 + 2 * rp;
+  const int col = c0 + cc * 8;
+  float va[8], vb[8];
+  prod(ra, col, va, vb);
+  __align__(16) __half ha[8], la[8], hb[8], lb[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    split_f16(fmaxf(fminf(va[j], 65504.f), -65504.f), ha[j], la[j]);
+    split_f16(fmaxf(fminf(vb[j], 65504.f), -65504.f), hb[j], lb[j]);
+  }
+  if (col < ld) {
+    if (ra < rows) {
+      *reinterpret_cast<uint4*>(hi + ra * ld + col) = *reinterpret_cast<const uint4*>(ha);
+      if (lo) *reinterpret_cast<uint4*>(lo + ra * ld + col) = *reinterpret_cast<const uint4*>(la);
+    }
+    if (ra + 1 < rows) {
+      *reinterpret_cast<uint4*>(hi + (ra + 1) * ld + col) = *reinterpret_cast<const uint4*>(hb);
+      if (lo) *reinterpret_cast<uint4*>(lo + (ra + 1) * ld + col) = *reinterpret_cast<const uint4*>(lb);
+    }
+  }
+  if (hiT == nullptr) return;   // uniform
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int w = (cc * 8 + j) * kTilePitch + rp;
+    sh[0][w] = (uint32_t)__half_as_ushort(ha[j]) | ((uint32_t)__half_as_ushort(hb[j]) << 16);
+    sh[1][w] = (uint32_t)__half_as_ushort(la[j]) | ((uint32_t)__half_as_ushort(lb[j]) << 16);
+  }
+  __syncthreads();
+  const int ct = t >> 2, part = t & 3;
+  const int gc = c0 + ct;
+  if (gc >= cols) return;
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    __half* dstT = p == 0 ? hiT : loT;
+    if (dstT == nullptr) continue;
+    uint32_t w[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) w[k] = sh[p][ct * kTilePitch + part * 8 + k];
+    // block r0/64 of the K-blocked layout: [cols][64] halves, this thread owns rows part*16..+16 of column gc
+    uint4* dst = reinterpret_cast<uint4*>(dstT + ((long long)blockIdx.x * cols + gc) * kTileDim + part * 16);
+    dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// column statistics: out[0][c] += sum_r v, out[1][c] += sum_r v^2   (fp64; BatchNorm1d batch mean / biased variance)
+// grid (ceil(cols/256), row slabs), block (32, 8): x -> 8-column chunk, y -> row phase
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) col_stats_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo,
+                                                        const float* __restrict__ x, long long rows, int cols,
+                                                        long long ld, long long rows_per_slab, double* __restrict__ out) {
+  __shared__ double sh[2][256];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int c0 = blockIdx.x * 256 + tx * 8;
+  const long long r_begin = (long long)blockIdx.y * rows_per_slab;
+  const long long r_end = r_begin + rows_per_slab < rows ? r_begin + rows_per_slab : rows;
+  double s[8], ss[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.0;
+  if (c0 < cols) {
+    for (long long r = r_begin + ty; r < r_end; r += 8) {
+      float v[8];
+      if (x) load8_f32(x + r * ld + c0, cols - c0, v);
+      else load8(hi + r * ld + c0, lo ? lo + r * ld + c0 : nullptr, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const double d = (double)v[j];
+        s[j] += d;
+        ss[j] += d * d;
+      }
+    }
+  }
+  for (int i = ty * 32 + tx; i < 512; i += 256) (&sh[0][0])[i] = 0.0;
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    atomicAdd(&sh[0][tx * 8 + j], s[j]);
+    atomicAdd(&sh[1][tx * 8 + j], ss[j]);
+  }
+  __syncthreads();
+  const int i = ty * 32 + tx;
+  const int c = blockIdx.x * 256 + i;
+  if (c < cols) {
+    atomicAdd(out + c, sh[0][i]);
+    atomicAdd(out + cols + c, sh[1][i]);
+  }
+}
+
+// mean / biased variance -> BatchNorm state (+ running statistics update, momentum as torch.nn.BatchNorm1d).
+// stats2 != null: statistics of the pair grid z[b,l] = a[b] + c[l]:  mean = mean_a + mean_c, var = var_a + var_c.
+__global__ void bn_finalize_kernel(const double* __restrict__ stats, double count, const double* __restrict__ stats2,
+                                   double count2, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float eps, float momentum, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, int cols, float* __restrict__ state) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  double mean = stats[c] / count;
+  double var = stats[cols + c] / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  double n = count;
+  if (stats2) {
+    const double m2 = stats2[c] / count2;
+    double v2 = stats2[cols + c] / count2 - m2 * m2;
+    if (v2 < 0.0) v2 = 0.0;
+    mean += m2;
+    var += v2;
+    n = count * count2;
+  }
+  const double invstd = 1.0 / sqrt(var + (double)eps);
+  const double sc = (gamma ? (double)gamma[c] : 1.0) * invstd;
+  state[c] = (float)sc;
+  state[cols + c] = (float)((beta ? (double)beta[c] : 0.0) - mean * sc);
+  state[2 * (long long)cols + c] = (float)mean;
+  state[3 * (long long)cols + c] = (float)invstd;
+  if (running_mean) running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * mean);
+  if (running_var) {
+    const double unbiased = var * (n / (n > 1.0 ? n - 1.0 : 1.0));
+    running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unbiased);
+  }
+}
+
+// logits[r] = sum_n relu(z[r][n] * scale[n] + shift[n]) * w[n] + b     (last hidden layer + Linear(H -> 1), one warp per row)
+__global__ void __launch_bounds__(256) bn_relu_dot_kernel(const __half* __restrict__ zh, const __half* __restrict__ zl,
+                                                          long long rows, int cols, long long ld,
+                                                          const float* __restrict__ state, const float* __restrict__ w,
+                                                          const float* __restrict__ b, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int chunks = (cols + 7) / 8;
+  for (long long r = warp0; r < rows; r += nwarps) {
+    float acc = 0.f;
+    for (int ch = lane; ch < chunks; ch += 32) {
+      const int c0 = ch * 8;
+      float v[8], sc[8], sf[8], wv[8];
+      load8(zh + r * ld + c0, zl ? zl + r * ld + c0 : nullptr, v);
+      load8_f32(state + c0, cols - c0, sc);
+      load8_f32(state + cols + c0, cols - c0, sf);
+      load8_f32(w + c0, cols - c0, wv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (c0 + j < cols) acc = fmaf(fmaxf(fmaf(v[j], sc[j], sf[j]), 0.f), wv[j], acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) out[r] = acc + (b ? __ldg(b) : 0.f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BatchNorm + ReLU backward, pass 1: sums[0][c] = sum_r g_y, sums[1][c] = sum_r g_y * xhat (true scale, fp64),
+// maxes = (max |g_y|, max |xhat|); kind 1 also dw[c] = sum_r g_logit[r] * relu(pre)[r][c] and db = sum_r g_logit[r].
+// A thread walks its rows two at a time (both rows' loads in flight), keeps fp32 partial sums over 16 rows and flushes
+// them into fp64 accumulators in shared memory, so few registers are live and many blocks fit an SM.
+// ------------------------------------------------------------------------------------------------
+template <int KIND>
+__global__ void __launch_bounds__(256) bwd_stats_kernel(const BwdSrc s, long long per_slab, double* __restrict__ sums,
+                                                        unsigned* __restrict__ maxes, double* __restrict__ dw,
+                                                        double* __restrict__ db) {
+  __shared__ double sh[3][256];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int c0 = blockIdx.x * 256 + tx * 8;
+  // kind 0/1: a slab is a range of rows.  kind 2 (rows = b * L + l): a slab is a range of LABELS walked for every
+  // protein in turn, so the slab's rows of c (per_slab x 256 columns, fp32) are re-read from L1/L2, not from HBM.
+  const long long n_outer = KIND == 2 ? s.rows / s.L : 1;
+  const long long extent = KIND == 2 ? s.L : s.rows;
+  const long long i_begin = (long long)blockIdx.y * per_slab;
+  const long long i_end = i_begin + per_slab < extent ? i_begin + per_slab : extent;
+  for (int i = ty * 32 + tx; i < 768; i += 256) (&sh[0][0])[i] = 0.0;
+  __syncthreads();
+  float p1[8], p2[8], p3[8];
+  zero8(p1);
+  zero8(p2);
+  zero8(p3);
+  float gmax = 0.f, xmax = 0.f;
+  double dbs = 0.0;
+  const float inv_gsc = s.g_sc ? 1.f / __ldg(s.g_sc) : 1.f;
+  auto flush = [&]() {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&sh[0][tx * 8 + j], (double)p1[j]);
+      atomicAdd(&sh[1][tx * 8 + j], (double)p2[j]);
+      if (KIND == 1) atomicAdd(&sh[2][tx * 8 + j], (double)p3[j]);
+      p1[j] = p2[j] = p3[j] = 0.f;
+    }
+  };
+  if (c0 < s.cols) {
+    BnVec b;
+    load_bn(s.state, s.cols, c0, b);
+    float wv[8];
+    if (KIND == 1) load8_f32(s.w + c0, s.cols - c0, wv);
+    else zero8(wv);
+    int it = 0;
+    for (long long bb = 0; bb < n_outer; ++bb) {
+      const long long base = bb * extent;
+      for (long long i = i_begin + ty; i < i_end; i += 8 * kRif) {
+        BwdRaw q[kRif];
+#pragma unroll
+        for (int k = 0; k < kRif; ++k)
+          if (i + 8 * k < i_end) bwd_raw_load<KIND>(s, base + i + 8 * k, c0, q[k]);
+#pragma unroll
+        for (int k = 0; k < kRif; ++k) {
+          if (i + 8 * k >= i_end) continue;
+          float gy[8], xh[8], pre[8];
+          bwd_eval<KIND>(s, q[k], base + i + 8 * k, c0, b, wv, inv_gsc, gy, xh, pre);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            p1[j] += gy[j];
+            p2[j] = fmaf(gy[j], xh[j], p2[j]);
+            if (KIND == 1) p3[j] = fmaf(q[k].gl, fmaxf(pre[j], 0.f), p3[j]);
+            gmax = fmaxf(gmax, fabsf(gy[j]));
+            xmax = fmaxf(xmax, fabsf(xh[j]));
+          }
+          if (KIND == 1 && blockIdx.x == 0 && tx == 0) dbs += (double)q[k].gl;
+        }
+        if ((++it & 7) == 0) flush();   // fp32 partial sums cover at most 8 * kRif rows
+      }
+    }
+    flush();
+  }
+  __syncthreads();
+  const int i = ty * 32 + tx;
+  const int c = blockIdx.x * 256 + i;
+  if (c < s.cols) {
+    atomicAdd(sums + c, sh[0][i]);
+    atomicAdd(sums + s.cols + c, sh[1][i]);
+    if (KIND == 1 && dw) atomicAdd(dw + c, sh[2][i]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+    xmax = fmaxf(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+  }
+  if (tx == 0) {
+    atomicMax(maxes, __float_as_uint(gmax));
+    atomicMax(maxes + 1, __float_as_uint(xmax));
+    if (KIND == 1 && blockIdx.x == 0 && db) atomicAdd(db, dbs);
+  }
+}
+
+// power of two that puts `bound` into [2^5, 2^6): fp16 planes of a gradient tensor keep ~22 bits for every element
+// within 2^-9 of the largest one and cannot overflow through one more dgrad
+__device__ __forceinline__ float grad_scale_from_bound(float bound) {
+  if (!(bound > 0.f) || !(bound < 3.0e38f)) return 1.f;
+  int e;
+  frexpf(bound, &e);
+  return ldexpf(1.f, 6 - e);
+}
+
+// means[0][c] = sums[0][c] / n, means[1][c] = sums[1][c] / n (fp32, what pass 2 subtracts) and, when sc_out is given,
+// the scale for the g_z tensor pass 2 writes, from an upper bound of |g_z|:
+//   max|scale| * (max|g_y| + max|s1|/n + max|xhat| * max|s2|/n)
+__global__ void bwd_scale_kernel(const double* __restrict__ sums, const unsigned* __restrict__ maxes,
+                                 const float* __restrict__ state, double count, int cols, float* __restrict__ sc_out,
+                                 float* __restrict__ means) {
+  __shared__ float red[3][32];
+  float ms = 0.f, m1 = 0.f, m2 = 0.f;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+    const float a1 = (float)(sums[c] / count), a2 = (float)(sums[cols + c] / count);
+    means[c] = a1;
+    means[cols + c] = a2;
+    ms = fmaxf(ms, fabsf(state[c]));
+    m1 = fmaxf(m1, fabsf(a1));
+    m2 = fmaxf(m2, fabsf(a2));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ms = fmaxf(ms, __shfl_xor_sync(0xffffffffu, ms, o));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, o));
+    m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    red[0][threadIdx.x >> 5] = ms;
+    red[1][threadIdx.x >> 5] = m1;
+    red[2][threadIdx.x >> 5] = m2;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && sc_out) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+      ms = fmaxf(ms, red[0][w]);
+      m1 = fmaxf(m1, red[1][w]);
+      m2 = fmaxf(m2, red[2][w]);
+    }
+    const float gmax = __uint_as_float(maxes[0]), xmax = __uint_as_float(maxes[1]);
+    *sc_out = grad_scale_from_bound(ms * (gmax + m1 + xmax * m2));
+  }
+}
+
+// sc[0] = power-of-two scale from the absmax bits left in sc[1] by absmax_kernel
+__global__ void autoscale_finish_kernel(float* __restrict__ sc) {
+  sc[0] = grad_scale_from_bound(__uint_as_float(reinterpret_cast<const unsigned*>(sc)[1]));
+}
+
+// out[n] = 1 / (s0 * s1 * s2)   (null -> 1): the epilogue scale that undoes the power-of-two operand scales
+__global__ void scale_vector_kernel(float* __restrict__ out, int n, const float* __restrict__ s0,
+                                    const float* __restrict__ s1, const float* __restrict__ s2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float d = 1.f;
+  if (s0) d *= *s0;
+  if (s1) d *= *s1;
+  if (s2) d *= *s2;
+  out[i] = 1.f / d;
+}
+
+// ------------------------------------------------------------------------------------------------
+// layer 1 backward (kind 2): the gradient w.r.t. z1[b,l] = a[b] + c[l] is never stored, only its two marginals:
+//   dc[l][n] = sum_b g_z1[b,l,n]   one thread per (l, 8 columns) walks the B proteins (rows L apart), plain store
+//   da[b][n] = sum_l g_z1[b,l,n]   a column sum over the L rows of protein b (same structure as pass 1), fp64 atomics
+// Reading g_h1 twice at streaming speed is cheaper than synchronising a block once per protein.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pair_gz(const BwdSrc& s, const BwdRaw& q, long long r, int c0, const BnVec& b,
+                                        const float (&m1)[8], const float (&m2)[8], float inv_gsc, float (&gz)[8]) {
+  float gy[8], xh[8], pre[8], wv[8];
+  zero8(wv);
+  bwd_eval<2>(s, q, r, c0, b, wv, inv_gsc, gy, xh, pre);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) gz[j] = c0 + j < s.cols ? b.scale[j] * (gy[j] - m1[j] - xh[j] * m2[j]) : 0.f;
+}
+
+// grid (ceil(cols/256), ceil(L/8)), block (32, 8)
+__global__ void __launch_bounds__(256) pair_dc_kernel(const BwdSrc s, const float* __restrict__ means, long long B,
+                                                      float* __restrict__ dc) {
+  const int c0 = blockIdx.x * 256 + threadIdx.x * 8;
+  const long long l = (long long)blockIdx.y * 8 + threadIdx.y;
+  if (c0 >= s.cols || l >= s.L) return;
+  BnVec b;
+  load_bn(s.state, s.cols, c0, b);
+  float m1[8], m2[8], acc[8];
+  load8_f32(means + c0, s.cols - c0, m1);
+  load8_f32(means + s.cols + c0, s.cols - c0, m2);
+  zero8(acc);
+  const float inv_gsc = s.g_sc ? 1.f / __ldg(s.g_sc) : 1.f;
+  for (long long bb = 0; bb < B; bb += kRif) {
+    BwdRaw q[kRif];
+#pragma unroll
+    for (int k = 0; k < kRif; ++k)
+      if (bb + k < B) bwd_raw_load<2>(s, (bb + k) * s.L + l, c0, q[k]);
+#pragma unroll
+    for (int k = 0; k < kRif; ++k) {
+      if (bb + k >= B) continue;
+      float gz[8];
+      pair_gz(s, q[k], (bb + k) * s.L + l, c0, b, m1, m2, inv_gsc, gz);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += gz[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (c0 + j < s.cols) dc[l * s.cols + c0 + j] = acc[j];
+}
+
+// grid (ceil(cols/256), label slabs), block (32, 8): the slab's labels are walked once per protein (c stays in L1/L2);
+// after each protein the block's 8 row phases are reduced through shared memory and added to da[b] (fp64 atomics).
+__global__ void __launch_bounds__(256) pair_da_kernel(const BwdSrc s, const float* __restrict__ means, long long B,
+                                                      long long labels_per_slab, double* __restrict__ da) {
+  __shared__ float sh[8][256];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int c0 = blockIdx.x * 256 + tx * 8;
+  const long long l_begin = (long long)blockIdx.y * labels_per_slab;
+  const long long l_end = l_begin + labels_per_slab < s.L ? l_begin + labels_per_slab : s.L;
+  const bool col_ok = c0 < s.cols;
+  BnVec b;
+  float m1[8], m2[8];
+  zero8(m1);
+  zero8(m2);
+  if (col_ok) {
+    load_bn(s.state, s.cols, c0, b);
+    load8_f32(means + c0, s.cols - c0, m1);
+    load8_f32(means + s.cols + c0, s.cols - c0, m2);
+  }
+  const float inv_gsc = s.g_sc ? 1.f / __ldg(s.g_sc) : 1.f;
+  for (long long bb = 0; bb < B; ++bb) {
+    float acc[8];
+    zero8(acc);
+    if (col_ok) {
+      for (long long l = l_begin + ty; l < l_end; l += 8 * kRif) {
+        BwdRaw q[kRif];
+#pragma unroll
+        for (int k = 0; k < kRif; ++k)
+          if (l + 8 * k < l_end) bwd_raw_load<2>(s, bb * s.L + l + 8 * k, c0, q[k]);
+#pragma unroll
+        for (int k = 0; k < kRif; ++k) {
+          if (l + 8 * k >= l_end) continue;
+          float gz[8];
+          pair_gz(s, q[k], bb * s.L + l + 8 * k, c0, b, m1, m2, inv_gsc, gz);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] += gz[j];
+        }
+      }
+    }
+    __syncthreads();   // the previous protein's readers are done with sh
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sh[ty][tx * 8 + j] = acc[j];
+    __syncthreads();
+    const int i = ty * 32 + tx;
+    const int c = blockIdx.x * 256 + i;
+    if (c < s.cols) {
+      float tot = 0.f;
+#pragma unroll
+      for (int y = 0; y < 8; ++y) tot += sh[y][i];
+      atomicAdd(da + bb * s.cols + c, (double)tot);
+    }
+  }
+}
+
+__global__ void f64_to_f32_kernel(const double* __restrict__ src, float* __restrict__ dst, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = (float)src[i];
+}
+
+}  // namespace pn

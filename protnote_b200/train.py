@@ -103,7 +103,7 @@ def head_forward(ops, comm, x_f32, layers, rows_total: int, sharded: bool, updat
 def head_backward(ops, comm, g_f32, saved, rows_total: int, sharded: bool, grads: Dict):
     g = ops.split(g_f32, want_T=True, autoscale=True)
     for idx in range(len(saved) - 1, -1, -1):
-        x, z, st, lin, bn = saved[idx]
+        x, z, st, lin, bn = saved.pop()          # consumed: activations are released layer by layer
         if st is not None:                       # g is the gradient w.r.t. the ReLU output of this layer
             s = ops.bwd_stats(g, z, st)
             grads[bn.weight], grads[bn.bias] = ops.bn_param_grads(s)        # this rank's rows only (before the sum)
@@ -157,7 +157,7 @@ def pairs_backward(ops, comm, ctx, g_logit, sharded: bool, grads: Dict):
     hidden, final, count = ctx["hidden"], ctx["final"], ctx["count"]
     layers = ctx["layers"]
     # ---- last hidden layer: the incoming gradient is the outer product g_logit (x) w_out, generated on the fly
-    h_prev, z, st, lin, bn = layers[-1]
+    h_prev, z, st, lin, bn = layers.pop()        # consumed: activations are released layer by layer
     go = ops.outer(g_logit, final.weight)
     s = ops.bwd_stats(go, z, st)
     grads[bn.weight], grads[bn.bias] = ops.bn_param_grads(s)
@@ -166,16 +166,18 @@ def pairs_backward(ops, comm, ctx, g_logit, sharded: bool, grads: Dict):
         comm.sum_(s.sums)
     g = ops.bwd_apply(go, z, st, s, count, want_T=True)
     grads[lin.weight] = ops.wgrad(g, h_prev)
+    del h_prev, z
     g = ops.dgrad(g, ops.pack(lin.weight, transposed=True))
     # ---- middle layers
-    for j in range(len(layers) - 2, -1, -1):
-        h_prev, z, st, lin, bn = layers[j]
+    while layers:
+        h_prev, z, st, lin, bn = layers.pop()
         s = ops.bwd_stats(g, z, st)
         grads[bn.weight], grads[bn.bias] = ops.bn_param_grads(s)
         if sharded:
             comm.sum_(s.sums)
         g = ops.bwd_apply(g, z, st, s, count, want_T=True)
         grads[lin.weight] = ops.wgrad(g, h_prev)
+        del h_prev, z
         g = ops.dgrad(g, ops.pack(lin.weight, transposed=True))
     # ---- layer 1: z1 = a[b] + c[l] is regenerated, its gradient is reduced to the two factors
     lin1, bn1 = hidden[0]
