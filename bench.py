@@ -40,7 +40,7 @@ B_TOTAL, T_LEN, L_ROWS = 4096, 1024, 32768
 CPU_SAMPLE = (8, 1024, 4096)        # sequences, residues, label rows of the bounded CPU sample
 
 
-def base_config_model(precision: str):
+def base_config_model(precision: str, descriptions_per_label: int = 1):
     """Random-init ProtNote with the published architecture (configs/base_config.yaml)."""
     from protnote_b200.ProtNote import ProtNote
     from protnote_b200.protein_encoders import ProteInfer
@@ -48,7 +48,8 @@ def base_config_model(precision: str):
     enc = ProteInfer(num_labels=8, input_channels=20, output_channels=1100, kernel_size=9, activation=torch.nn.ReLU,
                      dilation_base=3, num_resnet_blocks=5, bottleneck_factor=0.5, precision=precision)
     model = ProtNote(protein_embedding_dim=1100, label_embedding_dim=1024, latent_dim=1024,
-                     label_embedding_pooling_method="mean", sequence_encoder=enc, inference_descriptions_per_label=1,
+                     label_embedding_pooling_method="mean", sequence_encoder=enc,
+                     inference_descriptions_per_label=descriptions_per_label,
                      output_mlp_hidden_dim_scale_factor=3, output_mlp_num_layers=3, outout_mlp_add_batchnorm=True,
                      projection_head_num_layers=4, projection_head_hidden_dim_scale_factor=3,
                      feature_fusion="concatenation", precision=precision)
@@ -171,16 +172,17 @@ def run_ours(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     B, T, L = args.sequences, args.seq_len, args.labels
-    model = base_config_model(args.mode).to(dev)
+    kdesc = args.descriptions_per_label
+    model = base_config_model(args.mode, kdesc).to(dev)
     onehots_h, lengths_h, labels_h = synthetic_inputs(B, T, L, pinned=True)
     ps, pe = shard_bounds(B, rank, world)
-    ls, le = label_row_bounds(L, 1, rank, world)
+    ls, le = label_row_bounds(L, kdesc, rank, world)
     # this rank's shard of the inputs (world == 1: everything)
     x_h, len_h, lab_h = onehots_h[ps:pe], lengths_h[ps:pe], labels_h[ls:le]
     if world > 1:
         x_h, len_h, lab_h = x_h.contiguous().pin_memory(), len_h.contiguous().pin_memory(), lab_h.contiguous().pin_memory()
     x_d, len_d, lab_d = x_h.to(dev), len_h.to(dev), lab_h.to(dev)
-    logits_host = torch.empty(B, le - ls, dtype=torch.float32).pin_memory()
+    logits_host = torch.empty(B, (le - ls) // kdesc, dtype=torch.float32).pin_memory()
 
     def forward(x, lens, lab):
         model._label_cache = None          # W_l(label_embeddings) is recomputed every step, like the reference does
@@ -220,7 +222,7 @@ def run_ours(args, rank, world, local_rank):
         lens = len_h.to(dev, non_blocking=True)
         lab = lab_h.to(dev, non_blocking=True)
         out = forward(x, lens, lab)
-        logits_host.copy_(out[:, ls:le] if world > 1 else out, non_blocking=True)
+        logits_host.copy_(out[:, ls // kdesc:le // kdesc] if world > 1 else out, non_blocking=True)
 
     for _ in range(args.warmup):
         step_device()
@@ -261,6 +263,31 @@ def run_ours(args, rank, world, local_rank):
         breakdown["encoder_algorithmic_tflops"] = x_d.shape[0] * T * 60_896_000 / (breakdown["encoder_ms"] * 1e-3) / 1e12
         breakdown["scorer_pairs_per_s"] = a.shape[0] * c.shape[0] / (breakdown["pair_scorer_ms"] * 1e-3)
 
+    # the same step with one tensor-core pass per product (fp16 operands, fp32 accumulate = the arithmetic the reference
+    # itself uses on a GPU under torch.autocast): how fast the kernels are when fp32-grade logits are not required, and
+    # how far those logits are from the strict ones
+    fast = None
+    if args.mode == "strict" and world == 1 and not args.no_fast:
+        strict_out = out
+        model.precision = model.sequence_encoder.precision = "fast"
+        step_device()
+        native.gemm_timing(True)
+        ms_fast = timed(step_device, 1)
+        f_ms, f_n, f_flops = native.gemm_timing_read()
+        native.gemm_timing(False)
+        model.precision = model.sequence_encoder.precision = "strict"
+        diff = (out - strict_out).abs()
+        k10 = min(10, out.shape[1])
+        same = (out.topk(k10, dim=1).indices == strict_out.topk(k10, dim=1).indices).all(dim=1).float().mean()
+        fast = {"value": B * L / (ms_fast * 1e-3), "unit": UNIT, "ms_per_step": ms_fast,
+                "scorer_gemm_tflops": f_flops / (f_ms * 1e-3) / 1e12 if f_ms > 0 else None,
+                "max_abs_logit_diff_vs_strict": float(diff.max()), "mean_abs_logit_diff_vs_strict": float(diff.mean()),
+                "logit_std": float(strict_out.std()), "top10_identical_fraction": float(same),
+                "max_abs_logit_diff_over_logit_std": float(diff.max() / strict_out.std().clamp_min(1e-30)),
+                "note": "NOT the headline: fp16-operand arithmetic is a few percent of the logit std away from the fp32 "
+                        "result (5e-2 at logit std 2 on the calibrated golden cases), far outside the 1e-4 bar; this random-init "
+                        "bench model has un-calibrated BatchNorm statistics, hence the small logit std"}
+        out = strict_out
     if rank != 0:
         return
     pairs = B * L
@@ -269,14 +296,14 @@ def run_ours(args, rank, world, local_rank):
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     # whole-job bytes per step: every rank copies its own protein / label shard in and its own logit slab out
     h2d = onehots_h.numel() * 4 + lengths_h.numel() * 8 + labels_h.numel() * 4
-    d2h = B * L * 4
+    d2h = B * (L // kdesc) * 4
     line = {
         "metric": METRIC, "value": pairs / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32 (fp16 hi/lo planes, 3 tcgen05 passes, fp32 accumulate)" if passes == 3
         else "f16 operands, fp32 accumulate", "data": "synthetic",
         "config": {"workload": f"inference {B} x {T} aa x {L} label rows, fp32 in/out (BASELINE.json configs[1])",
-                   "mode": args.mode, "sequences": B, "seq_len": T, "label_rows": L,
+                   "mode": args.mode, "sequences": B, "seq_len": T, "label_rows": L, "descriptions_per_label": kdesc,
                    "parallelism": "1 GPU" if world == 1 else f"label-sharded x{world} (proteins sharded for the encoder), "
                                                               "NCCL all-gather of P_f and of the logit slab",
                    "l2": "inputs (one-hots 335 MB + label embeddings 134 MB) are larger than the 126 MB L2",
@@ -303,9 +330,17 @@ def run_ours(args, rank, world, local_rank):
                      "executed_frac": achieved * passes / peak if peak else None,
                      "note": "achieved counts ALGORITHMIC flops (2*M*N*K); strict mode executes 3 fp16 passes per "
                              "algorithmic flop to reach fp32 accuracy, so its ceiling is peak/3"},
+        "roofline_encoder": {"kernel": "pn::gemm_kernel (11 convolutions of the ProteInfer encoder as implicit GEMMs)",
+                             "bound": "tensor", "achieved": breakdown["encoder_algorithmic_tflops"], "peak": peak,
+                             "unit": "TFLOP/s", "frac": breakdown["encoder_algorithmic_tflops"] / peak if peak else None,
+                             "executed_frac": breakdown["encoder_algorithmic_tflops"] * passes / peak if peak else None,
+                             "share_of_step": breakdown["encoder_ms"] / ms_step},
         "breakdown_rank0": breakdown,
         "outputs_finite": finite,
     }
+    if fast is not None:
+        fast["frac_of_peak_scorer_gemm"] = fast["scorer_gemm_tflops"] / peak if fast["scorer_gemm_tflops"] else None
+        line["fast_mode"] = fast
     if world == 1 and not args.no_cpu_baseline:
         rate, ms, cores, sample = cpu_oracle_rate(reps=2, warmup=1)
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
@@ -444,6 +479,9 @@ def main():
     ap.add_argument("--seq-len", type=int, default=T_LEN)
     ap.add_argument("--labels", type=int, default=L_ROWS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fast", action="store_true", help="skip the extra fast-mode (fp16 operand) measurement")
+    ap.add_argument("--descriptions-per-label", type=int, default=1,
+                    help="k consecutive label rows ensembled per label (INFERENCE_GO_DESCRIPTIONS name+label -> 2)")
     ap.add_argument("--workload", default="inference", choices=["inference", "train"],
                     help="inference = BASELINE.json configs[1] (the metric's configuration, default); "
                          "train = configs[2]: one training step, batch 64 x 32K label rows, BCE + Adam, label-sharded")

@@ -98,3 +98,22 @@ def test_autograd_function_delivers_parameter_gradients():
         assert named[k].grad is not None, k
         assert (named[k].grad - g).abs().max() <= 1e-9 * max(1.0, float(g.abs().max())), k
     assert all(p.grad is None for n, p in named.items() if n.startswith("sequence_encoder."))
+
+
+@pytest.mark.parametrize("name", ["train_tiny", "train_tiny_wide"])
+def test_train_oracle_matches_committed_golden(name):
+    """tests/golden/train_*.pt were produced by the reference's own ProtNote class in train mode (oracle/make_golden_train.py)."""
+    import os
+    from oracle.make_golden_train import train_inputs
+    from tests.helpers import GOLDEN_DIR, weight_checksum
+    g = torch.load(os.path.join(GOLDEN_DIR, name + ".pt"))
+    ecfg, scfg, sd, P_f, L_f, y = train_inputs(name)
+    assert abs(weight_checksum(sd) - g["weights_checksum"]) <= 1e-6 * max(1.0, abs(g["weights_checksum"]))
+    logits, loss, grads, stats = train_step_oracle(sd, P_f, L_f, y, scfg)
+    assert (logits - g["logits"]).abs().max() < 1e-9
+    assert abs(float(loss) - g["loss"]) < 1e-10
+    assert set(grads) == set(g["grads"])
+    for k, v in g["grads"].items():
+        assert (grads[k] - v).abs().max() <= 1e-9 * max(1.0, float(v.abs().max())), k
+    for k, v in g["running"].items():
+        assert (stats[k] - v).abs().max() < 1e-9, k
