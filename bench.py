@@ -423,16 +423,22 @@ def run_train(args, rank, world, local_rank):
              yl_h.to(dev, non_blocking=True))
         loss_host.copy_(last["loss"].reshape(1), non_blocking=True)
 
+    def whole_batch_loss():
+        t = last["loss"].detach().clone().reshape(1)     # this rank's slab; the batch loss is the sum over ranks
+        if world > 1:
+            dist.all_reduce(t)
+        return float(t)
+
     losses = []
     for _ in range(args.warmup):
         step_device()
-        losses.append(float(last["loss"]))
+        losses.append(whole_batch_loss())
     sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = native.launch_count()
     ms_step = timed(step_device, args.steps)
     launches = native.launch_count() - launches0
     clocks = sampler.stop() if sampler else None
-    losses.append(float(last["loss"]))
+    losses.append(whole_batch_loss())
     step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
     peak_mem = torch.cuda.max_memory_allocated(dev) / 2 ** 30
