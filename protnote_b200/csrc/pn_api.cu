@@ -624,12 +624,18 @@ int launch_emit(const P& prod, long long rows, int cols, void* hi, void* lo, lon
   if (hi == nullptr) return fail("hi plane is required");
   if (ld % 8 != 0 || ld < cols) return fail("plane pitch %lld must be a multiple of 8 and >= cols %d", ld, cols);
   if (hiT && blocksT * kTileDim < rows) return fail("transposed planes hold %lld blocks of 64 rows, %lld rows need more", blocksT, rows);
+  if (hiT && ((lo != nullptr) != (loT != nullptr))) return fail("transposed planes must carry the same planes as the row-major ones");
   const long long row_tiles = (rows + kTileDim - 1) / kTileDim;
+  const long long strips = (row_tiles + kStripTiles - 1) / kStripTiles;
   const long long col_tiles = (ld + kTileDim - 1) / kTileDim;
   if (col_tiles > 65535) return fail("too many columns");
-  emit_tile_kernel<P><<<dim3((unsigned)row_tiles, (unsigned)col_tiles), 256, 0, stream>>>(
-      prod, rows, cols, static_cast<__half*>(hi), static_cast<__half*>(lo), ld, static_cast<__half*>(hiT),
-      static_cast<__half*>(loT));
+  const dim3 grid((unsigned)strips, (unsigned)col_tiles);
+  if (lo)
+    emit_tile_kernel<P, true><<<grid, 256, 0, stream>>>(prod, rows, cols, static_cast<__half*>(hi), static_cast<__half*>(lo),
+                                                        ld, static_cast<__half*>(hiT), static_cast<__half*>(loT));
+  else
+    emit_tile_kernel<P, false><<<grid, 256, 0, stream>>>(prod, rows, cols, static_cast<__half*>(hi), nullptr, ld,
+                                                         static_cast<__half*>(hiT), nullptr);
   g_launches++;
   PN_CUDA(cudaGetLastError());
   return 0;
@@ -654,6 +660,9 @@ BwdSrc to_src(const pn_bwd_src& s) {
   return d;
 }
 
+// strict-mode sources carry lo planes on every plane operand they have
+bool src_has_lo(const BwdSrc& s) { return s.kind == 1 ? s.z_lo != nullptr : s.g_lo != nullptr; }
+
 int check_src(const pn_bwd_src* s) {
   if (!s) return fail("null backward source");
   if (s->kind < 0 || s->kind > 2) return fail("unknown backward source kind %d", s->kind);
@@ -661,6 +670,8 @@ int check_src(const pn_bwd_src* s) {
   if (s->kind == 1 ? (!s->g_logit || !s->w) : (!s->g_hi || s->ld_g % 8 != 0)) return fail("backward source: gradient operand missing");
   if (s->kind == 2 ? (!s->a || !s->c || s->L <= 0 || s->rows % s->L != 0) : (!s->z_hi || s->ld_z % 8 != 0))
     return fail("backward source: pre-activation operand missing");
+  if (s->kind == 0 && ((s->g_lo != nullptr) != (s->z_lo != nullptr)))
+    return fail("backward source: g and z must both carry lo planes or neither");
   return 0;
 }
 }  // namespace
@@ -1414,9 +1425,13 @@ int pn_t_bwd_stats(const pn_bwd_src* src, double* sums, float* maxes, double* dw
   }
   const dim3 grid(col_blocks, (unsigned)slabs), block(32, 8);
   unsigned* mx = reinterpret_cast<unsigned*>(maxes);
-  if (s.kind == 0) bwd_stats_kernel<0><<<grid, block, 0, stream>>>(s, per, sums, mx, dw, db);
-  else if (s.kind == 1) bwd_stats_kernel<1><<<grid, block, 0, stream>>>(s, per, sums, mx, dw, db);
-  else bwd_stats_kernel<2><<<grid, block, 0, stream>>>(s, per, sums, mx, dw, db);
+  const bool lo = src_has_lo(s);
+  if (s.kind == 0 && lo) bwd_stats_kernel<0, true><<<grid, block, 0, stream>>>(s, per, sums, mx, dw, db);
+  else if (s.kind == 0) bwd_stats_kernel<0, false><<<grid, block, 0, stream>>>(s, per, sums, mx, dw, db);
+  else if (s.kind == 1 && lo) bwd_stats_kernel<1, true><<<grid, block, 0, stream>>>(s, per, sums, mx, dw, db);
+  else if (s.kind == 1) bwd_stats_kernel<1, false><<<grid, block, 0, stream>>>(s, per, sums, mx, dw, db);
+  else if (lo) bwd_stats_kernel<2, true><<<grid, block, 0, stream>>>(s, per, sums, mx, dw, db);
+  else bwd_stats_kernel<2, false><<<grid, block, 0, stream>>>(s, per, sums, mx, dw, db);
   g_launches++;
   PN_CUDA(cudaGetLastError());
   return 0;
@@ -1455,11 +1470,14 @@ int pn_t_bwd_apply_pair(const pn_bwd_src* src, const float* means, long long B, 
   const int col_blocks = (s.cols + 255) / 256;
   const long long l_blocks = (s.L + 7) / 8;
   if (l_blocks > 65535) return fail("too many label rows for one launch (%lld)", s.L);
-  pair_dc_kernel<<<dim3(col_blocks, (unsigned)l_blocks), dim3(32, 8), 0, stream>>>(s, means, B, dc);
+  const bool lo = src_has_lo(s);
+  if (lo) pair_dc_kernel<true><<<dim3(col_blocks, (unsigned)l_blocks), dim3(32, 8), 0, stream>>>(s, means, B, dc);
+  else pair_dc_kernel<false><<<dim3(col_blocks, (unsigned)l_blocks), dim3(32, 8), 0, stream>>>(s, means, B, dc);
   long long per = 128;
   long long slabs = (s.L + per - 1) / per;
   if (slabs > 65535) return fail("too many label rows for one launch (%lld)", s.L);
-  pair_da_kernel<<<dim3(col_blocks, (unsigned)slabs), dim3(32, 8), 0, stream>>>(s, means, B, per, da64);
+  if (lo) pair_da_kernel<true><<<dim3(col_blocks, (unsigned)slabs), dim3(32, 8), 0, stream>>>(s, means, B, per, da64);
+  else pair_da_kernel<false><<<dim3(col_blocks, (unsigned)slabs), dim3(32, 8), 0, stream>>>(s, means, B, per, da64);
   f64_to_f32_kernel<<<ew_grid(B * s.cols), 256, 0, stream>>>(da64, da, B * s.cols);
   g_launches += 3;
   PN_CUDA(cudaGetLastError());

@@ -71,25 +71,37 @@ __device__ __forceinline__ void load_bn(const float* __restrict__ state, int col
 }
 
 // ------------------------------------------------------------------------------------------------
-// producers: 8 consecutive columns of one row of the tensor a kernel emits
+// producers of the tile emitter.  A thread owns 8 consecutive columns of two vertically adjacent rows.  The work is
+// split in three so the emitter can software-pipeline a strip of tiles: init() loads the per-column constants once
+// per strip, load() only issues the 16-byte plane loads of a tile (the NEXT tile's loads are in flight while the
+// current one is converted and stored), eval() does the arithmetic.  LO = the tensors carry lo planes (strict mode).
 // ------------------------------------------------------------------------------------------------
-// raw 16-byte plane loads first, conversion later: the two rows a thread produces have their loads in flight together
 struct Raw8 {
   uint4 h, l;
 };
+template <bool LO>
 __device__ __forceinline__ void raw_load(const __half* __restrict__ hi, const __half* __restrict__ lo, long long off,
                                          Raw8& r) {
   r.h = *reinterpret_cast<const uint4*>(hi + off);
-  r.l = lo ? *reinterpret_cast<const uint4*>(lo + off) : make_uint4(0u, 0u, 0u, 0u);
+  if (LO) r.l = *reinterpret_cast<const uint4*>(lo + off);
 }
+template <bool LO>
 __device__ __forceinline__ void raw_to_f32(const Raw8& r, float (&v)[8]) {
   const __half2* h2 = reinterpret_cast<const __half2*>(&r.h);
-  const __half2* l2 = reinterpret_cast<const __half2*>(&r.l);
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const float2 f = __half22float2(h2[j]), g = __half22float2(l2[j]);
-    v[2 * j] = f.x + g.x;
-    v[2 * j + 1] = f.y + g.y;
+    const float2 f = __half22float2(h2[j]);
+    v[2 * j] = f.x;
+    v[2 * j + 1] = f.y;
+  }
+  if (LO) {
+    const __half2* l2 = reinterpret_cast<const __half2*>(&r.l);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 g = __half22float2(l2[j]);
+      v[2 * j] += g.x;
+      v[2 * j + 1] += g.y;
+    }
   }
 }
 __device__ __forceinline__ void zero8(float (&v)[8]) {
@@ -99,58 +111,97 @@ __device__ __forceinline__ void zero8(float (&v)[8]) {
 
 struct SplitProducer {          // x * sc
   const float* x; long long rows; int cols; long long ldx; const float* sc;
-  __device__ __forceinline__ void operator()(long long r, int c0, float (&va)[8], float (&vb)[8]) const {
-    const float s = sc ? __ldg(sc) : 1.f;
+  struct Ctx { float s; };
+  struct Raw { float a[8], b[8]; };
+  __device__ __forceinline__ void init(int c0, Ctx& k) const { k.s = sc ? __ldg(sc) : 1.f; }
+  template <bool LO>
+  __device__ __forceinline__ void load(long long r, int c0, Raw& q) const {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      va[j] = (r < rows && c0 + j < cols) ? x[r * ldx + c0 + j] * s : 0.f;
-      vb[j] = (r + 1 < rows && c0 + j < cols) ? x[(r + 1) * ldx + c0 + j] * s : 0.f;
+      q.a[j] = (r < rows && c0 + j < cols) ? x[r * ldx + c0 + j] : 0.f;
+      q.b[j] = (r + 1 < rows && c0 + j < cols) ? x[(r + 1) * ldx + c0 + j] : 0.f;
+    }
+  }
+  template <bool LO>
+  __device__ __forceinline__ void eval(const Ctx& k, const Raw& q, long long r, int c0, float (&va)[8], float (&vb)[8]) const {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      va[j] = q.a[j] * k.s;
+      vb[j] = q.b[j] * k.s;
     }
   }
 };
 
 struct BnReluProducer {         // relu(z * scale + shift)
   const __half* zh; const __half* zl; long long rows; int cols; long long ld; const float* state;
-  __device__ __forceinline__ void operator()(long long r, int c0, float (&va)[8], float (&vb)[8]) const {
+  struct Ctx { float sc[8], sf[8]; };
+  struct Raw { Raw8 a, b; };
+  __device__ __forceinline__ void init(int c0, Ctx& k) const {
+    zero8(k.sc);
+    zero8(k.sf);
+    if (c0 < cols) {
+      load8_f32(state + c0, cols - c0, k.sc);
+      load8_f32(state + cols + c0, cols - c0, k.sf);
+    }
+  }
+  template <bool LO>
+  __device__ __forceinline__ void load(long long r, int c0, Raw& q) const {
+    if (c0 >= cols) return;
+    if (r < rows) raw_load<LO>(zh, zl, r * ld + c0, q.a);
+    if (r + 1 < rows) raw_load<LO>(zh, zl, (r + 1) * ld + c0, q.b);
+  }
+  template <bool LO>
+  __device__ __forceinline__ void eval(const Ctx& k, const Raw& q, long long r, int c0, float (&va)[8], float (&vb)[8]) const {
     zero8(va);
     zero8(vb);
-    if (r >= rows || c0 >= cols) return;
-    const bool two = r + 1 < rows;
-    Raw8 ra, rb;
-    raw_load(zh, zl, r * ld + c0, ra);
-    if (two) raw_load(zh, zl, (r + 1) * ld + c0, rb);
-    float sc[8], sf[8];
-    load8_f32(state + c0, cols - c0, sc);
-    load8_f32(state + cols + c0, cols - c0, sf);
-    raw_to_f32(ra, va);
-    if (two) raw_to_f32(rb, vb);
+    if (c0 >= cols) return;
+    if (r < rows) {
+      raw_to_f32<LO>(q.a, va);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const bool ok = c0 + j < cols;
-      va[j] = ok ? fmaxf(fmaf(va[j], sc[j], sf[j]), 0.f) : 0.f;
-      vb[j] = (ok && two) ? fmaxf(fmaf(vb[j], sc[j], sf[j]), 0.f) : 0.f;
+      for (int j = 0; j < 8; ++j) va[j] = c0 + j < cols ? fmaxf(fmaf(va[j], k.sc[j], k.sf[j]), 0.f) : 0.f;
+    }
+    if (r + 1 < rows) {
+      raw_to_f32<LO>(q.b, vb);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) vb[j] = c0 + j < cols ? fmaxf(fmaf(vb[j], k.sc[j], k.sf[j]), 0.f) : 0.f;
     }
   }
 };
 
 struct PairHiddenProducer {     // relu((a[b] + c[l]) * scale + shift), row r = b * L + l   (ProtNote.py:112-126 + layer 1)
   const float* a; const float* c; long long L; long long rows; int cols; const float* state;
-  __device__ __forceinline__ void one(long long r, int c0, const float (&sc)[8], const float (&sf)[8], float (&v)[8]) const {
-    float av[8], cv[8];
-    load8_f32(a + (r / L) * cols + c0, cols - c0, av);
-    load8_f32(c + (r % L) * cols + c0, cols - c0, cv);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = c0 + j < cols ? fmaxf(fmaf(av[j] + cv[j], sc[j], sf[j]), 0.f) : 0.f;
+  struct Ctx { float sc[8], sf[8]; };
+  struct Raw { float ca[8], cb[8]; };
+  __device__ __forceinline__ void init(int c0, Ctx& k) const {
+    zero8(k.sc);
+    zero8(k.sf);
+    if (c0 < cols) {
+      load8_f32(state + c0, cols - c0, k.sc);
+      load8_f32(state + cols + c0, cols - c0, k.sf);
+    }
   }
-  __device__ __forceinline__ void operator()(long long r, int c0, float (&va)[8], float (&vb)[8]) const {
+  template <bool LO>
+  __device__ __forceinline__ void load(long long r, int c0, Raw& q) const {
+    if (c0 >= cols) return;
+    if (r < rows) load8_f32(c + (r % L) * cols + c0, cols - c0, q.ca);
+    if (r + 1 < rows) load8_f32(c + ((r + 1) % L) * cols + c0, cols - c0, q.cb);
+  }
+  template <bool LO>
+  __device__ __forceinline__ void eval(const Ctx& k, const Raw& q, long long r, int c0, float (&va)[8], float (&vb)[8]) const {
     zero8(va);
     zero8(vb);
-    if (r >= rows || c0 >= cols) return;
-    float sc[8], sf[8];
-    load8_f32(state + c0, cols - c0, sc);
-    load8_f32(state + cols + c0, cols - c0, sf);
-    one(r, c0, sc, sf, va);
-    if (r + 1 < rows) one(r + 1, c0, sc, sf, vb);
+    if (c0 >= cols) return;
+    float av[8];
+    if (r < rows) {
+      load8_f32(a + (r / L) * cols + c0, cols - c0, av);     // 64 rows of a: L1 / L2 resident
+#pragma unroll
+      for (int j = 0; j < 8; ++j) va[j] = c0 + j < cols ? fmaxf(fmaf(av[j] + q.ca[j], k.sc[j], k.sf[j]), 0.f) : 0.f;
+    }
+    if (r + 1 < rows) {
+      load8_f32(a + ((r + 1) / L) * cols + c0, cols - c0, av);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) vb[j] = c0 + j < cols ? fmaxf(fmaf(av[j] + q.cb[j], k.sc[j], k.sf[j]), 0.f) : 0.f;
+    }
   }
 };
 
@@ -171,14 +222,14 @@ struct BwdRaw {
   Raw8 g, z;
   float gl;
 };
-template <int KIND>
+template <int KIND, bool LO>
 __device__ __forceinline__ void bwd_raw_load(const BwdSrc& s, long long r, int c0, BwdRaw& q) {
   if (KIND == 1) q.gl = __ldg(s.g_logit + r);
-  else raw_load(s.g_hi, s.g_lo, r * s.ld_g + c0, q.g);
-  if (KIND != 2) raw_load(s.z_hi, s.z_lo, r * s.ld_z + c0, q.z);
+  else raw_load<LO>(s.g_hi, s.g_lo, r * s.ld_g + c0, q.g);
+  if (KIND != 2) raw_load<LO>(s.z_hi, s.z_lo, r * s.ld_z + c0, q.z);
 }
 // true-scale g_y = g * [relu active], xhat and the pre-activation for 8 columns of row r (columns >= cols give zeros)
-template <int KIND>
+template <int KIND, bool LO>
 __device__ __forceinline__ void bwd_eval(const BwdSrc& s, const BwdRaw& q, long long r, int c0, const BnVec& b,
                                          const float (&wv)[8], float inv_gsc, float (&gy)[8], float (&xh)[8],
                                          float (&pre)[8]) {
@@ -187,7 +238,7 @@ __device__ __forceinline__ void bwd_eval(const BwdSrc& s, const BwdRaw& q, long 
 #pragma unroll
     for (int j = 0; j < 8; ++j) g[j] = q.gl * wv[j];
   } else {
-    raw_to_f32(q.g, g);
+    raw_to_f32<LO>(q.g, g);
 #pragma unroll
     for (int j = 0; j < 8; ++j) g[j] *= inv_gsc;
   }
@@ -198,7 +249,7 @@ __device__ __forceinline__ void bwd_eval(const BwdSrc& s, const BwdRaw& q, long 
 #pragma unroll
     for (int j = 0; j < 8; ++j) z[j] = av[j] + cv[j];
   } else {
-    raw_to_f32(q.z, z);
+    raw_to_f32<LO>(q.z, z);
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -209,94 +260,145 @@ __device__ __forceinline__ void bwd_eval(const BwdSrc& s, const BwdRaw& q, long 
   }
 }
 
+// g_z = scale * (g_y - m1 - xhat * m2) * sc_out,  m = sums / count (fp32 [2][cols]).  Per column the thread keeps
+//   A = scale * sc_out (* 1/g_sc, * w for kind 1),  D = scale * sc_out * invstd * m2,  E = scale * sc_out * m1,
+// so g_z = A * g[masked] - E - D * (z - mean); the mask is (z * scale + shift > 0).
 template <int KIND>
-struct BwdApplyProducer {       // g_z = scale * (g_y - m1 - xhat * m2) * sc_out,  m = sums / count (fp32 [2][cols])
+struct BwdApplyProducer {
   BwdSrc s; const float* means; const float* sc_out;
-  __device__ __forceinline__ void operator()(long long r, int c0, float (&va)[8], float (&vb)[8]) const {
-    zero8(va);
-    zero8(vb);
-    if (r >= s.rows || c0 >= s.cols) return;
-    const bool two = r + 1 < s.rows;
-    BwdRaw qa, qb;
-    bwd_raw_load<KIND>(s, r, c0, qa);
-    if (two) bwd_raw_load<KIND>(s, r + 1, c0, qb);
-    BnVec b;
-    load_bn(s.state, s.cols, c0, b);
-    float m1[8], m2[8], wv[8];
+  struct Ctx { float sc[8], sf[8], mean[8], A[8], D[8], E[8]; };
+  struct Raw { BwdRaw a, b; };
+  __device__ __forceinline__ void init(int c0, Ctx& k) const {
+    zero8(k.sc); zero8(k.sf); zero8(k.mean); zero8(k.A); zero8(k.D); zero8(k.E);
+    if (c0 >= s.cols) return;
+    float invstd[8], m1[8], m2[8], wv[8];
+    load8_f32(s.state + c0, s.cols - c0, k.sc);
+    load8_f32(s.state + s.cols + c0, s.cols - c0, k.sf);
+    load8_f32(s.state + 2 * (long long)s.cols + c0, s.cols - c0, k.mean);
+    load8_f32(s.state + 3 * (long long)s.cols + c0, s.cols - c0, invstd);
     load8_f32(means + c0, s.cols - c0, m1);
     load8_f32(means + s.cols + c0, s.cols - c0, m2);
     if (KIND == 1) load8_f32(s.w + c0, s.cols - c0, wv);
-    else zero8(wv);
-    const float inv_gsc = s.g_sc ? 1.f / __ldg(s.g_sc) : 1.f;
+    const float inv_gsc = (KIND != 1 && s.g_sc) ? 1.f / __ldg(s.g_sc) : 1.f;
     const float so = sc_out ? __ldg(sc_out) : 1.f;
-    float gy[8], xh[8], pre[8];
-    bwd_eval<KIND>(s, qa, r, c0, b, wv, inv_gsc, gy, xh, pre);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) va[j] = c0 + j < s.cols ? b.scale[j] * (gy[j] - m1[j] - xh[j] * m2[j]) * so : 0.f;
-    if (two) {
-      bwd_eval<KIND>(s, qb, r + 1, c0, b, wv, inv_gsc, gy, xh, pre);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) vb[j] = c0 + j < s.cols ? b.scale[j] * (gy[j] - m1[j] - xh[j] * m2[j]) * so : 0.f;
+    for (int j = 0; j < 8; ++j) {
+      const float t = k.sc[j] * so;
+      k.A[j] = t * (KIND == 1 ? wv[j] : inv_gsc);
+      k.D[j] = t * invstd[j] * m2[j];
+      k.E[j] = t * m1[j];
     }
+  }
+  template <bool LO>
+  __device__ __forceinline__ void load(long long r, int c0, Raw& q) const {
+    if (c0 >= s.cols) return;
+    if (r < s.rows) bwd_raw_load<KIND, LO>(s, r, c0, q.a);
+    if (r + 1 < s.rows) bwd_raw_load<KIND, LO>(s, r + 1, c0, q.b);
+  }
+  template <bool LO>
+  __device__ __forceinline__ void one(const Ctx& k, const BwdRaw& q, long long r, int c0, float (&v)[8]) const {
+    float g[8], z[8];
+    if (KIND == 1) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] = q.gl;
+    } else {
+      raw_to_f32<LO>(q.g, g);
+    }
+    if (KIND == 2) {
+      float av[8], cv[8];
+      load8_f32(s.a + (r / s.L) * s.cols + c0, s.cols - c0, av);
+      load8_f32(s.c + (r % s.L) * s.cols + c0, s.cols - c0, cv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) z[j] = av[j] + cv[j];
+    } else {
+      raw_to_f32<LO>(q.z, z);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float gm = fmaf(z[j], k.sc[j], k.sf[j]) > 0.f ? g[j] : 0.f;
+      v[j] = c0 + j < s.cols ? fmaf(k.A[j], gm, -k.E[j]) - k.D[j] * (z[j] - k.mean[j]) : 0.f;
+    }
+  }
+  template <bool LO>
+  __device__ __forceinline__ void eval(const Ctx& k, const Raw& q, long long r, int c0, float (&va)[8], float (&vb)[8]) const {
+    zero8(va);
+    zero8(vb);
+    if (c0 >= s.cols) return;
+    if (r < s.rows) one<LO>(k, q.a, r, c0, va);
+    if (r + 1 < s.rows) one<LO>(k, q.b, r + 1, c0, vb);
   }
 };
 
 // ------------------------------------------------------------------------------------------------
-// tile emitter: planes [rows][ld] and (optionally) K-blocked transposed planes [ceil(rows/64)][cols][64]
-// grid (row tiles, col tiles), 256 threads.  Thread (warp w, lane l) produces rows 2*rp, 2*rp+1 (rp = 4w + l/8) x
-// 8 columns (l%8); phase 2 thread t stores 16 rows of column t/4.
+// tile emitter: planes [rows][ld] and (optionally) K-blocked transposed planes [ceil(rows/64)][cols][64].
+// grid (strips of kStripTiles row tiles, col tiles), 256 threads.  Thread (warp w, lane l) produces rows 2*rp, 2*rp+1
+// (rp = 4w + l/8) x 8 columns (l%8) of every 64x64 tile of its strip; phase 2 thread t stores 16 rows of column t/4.
 // ------------------------------------------------------------------------------------------------
-template <class P>
+constexpr int kStripTiles = 8;
+
+template <class P, bool LO>
 __global__ void __launch_bounds__(256) emit_tile_kernel(const P prod, long long rows, int cols, __half* __restrict__ hi,
                                                         __half* __restrict__ lo, long long ld, __half* __restrict__ hiT,
                                                         __half* __restrict__ loT) {
   __shared__ uint32_t sh[2][kTileDim * kTilePitch];
-  const long long r0 = (long long)blockIdx.x * kTileDim;
+  const long long row_tiles = (rows + kTileDim - 1) / kTileDim;
+  const long long tile0 = (long long)blockIdx.x * kStripTiles;
+  const long long tile_end = tile0 + kStripTiles < row_tiles ? tile0 + kStripTiles : row_tiles;
   const int c0 = blockIdx.y * kTileDim;
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const int cc = lane & 7, rp = warp * 4 + (lane >> 3);
-  const long long ra = r0 + 2 * rp;
   const int col = c0 + cc * 8;
-  float va[8], vb[8];
-  prod(ra, col, va, vb);
-  __align__(16) __half ha[8], la[8], hb[8], lb[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    split_f16(fmaxf(fminf(va[j], 65504.f), -65504.f), ha[j], la[j]);
-    split_f16(fmaxf(fminf(vb[j], 65504.f), -65504.f), hb[j], lb[j]);
-  }
-  if (col < ld) {
-    if (ra < rows) {
-      *reinterpret_cast<uint4*>(hi + ra * ld + col) = *reinterpret_cast<const uint4*>(ha);
-      if (lo) *reinterpret_cast<uint4*>(lo + ra * ld + col) = *reinterpret_cast<const uint4*>(la);
-    }
-    if (ra + 1 < rows) {
-      *reinterpret_cast<uint4*>(hi + (ra + 1) * ld + col) = *reinterpret_cast<const uint4*>(hb);
-      if (lo) *reinterpret_cast<uint4*>(lo + (ra + 1) * ld + col) = *reinterpret_cast<const uint4*>(lb);
-    }
-  }
-  if (hiT == nullptr) return;   // uniform
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int w = (cc * 8 + j) * kTilePitch + rp;
-    sh[0][w] = (uint32_t)__half_as_ushort(ha[j]) | ((uint32_t)__half_as_ushort(hb[j]) << 16);
-    sh[1][w] = (uint32_t)__half_as_ushort(la[j]) | ((uint32_t)__half_as_ushort(lb[j]) << 16);
-  }
-  __syncthreads();
   const int ct = t >> 2, part = t & 3;
   const int gc = c0 + ct;
-  if (gc >= cols) return;
+  typename P::Ctx ctx;
+  prod.init(col, ctx);
+  typename P::Raw cur, nxt;
+  prod.template load<LO>(tile0 * kTileDim + 2 * rp, col, cur);
+  for (long long tile = tile0; tile < tile_end; ++tile) {
+    const long long ra = tile * kTileDim + 2 * rp;
+    if (tile + 1 < tile_end) prod.template load<LO>(ra + kTileDim, col, nxt);
+    float va[8], vb[8];
+    prod.template eval<LO>(ctx, cur, ra, col, va, vb);
+    __align__(16) __half ha[8], la[8], hb[8], lb[8];
 #pragma unroll
-  for (int p = 0; p < 2; ++p) {
-    __half* dstT = p == 0 ? hiT : loT;
-    if (dstT == nullptr) continue;
-    uint32_t w[8];
+    for (int j = 0; j < 8; ++j) {
+      split_f16(fmaxf(fminf(va[j], 65504.f), -65504.f), ha[j], la[j]);
+      split_f16(fmaxf(fminf(vb[j], 65504.f), -65504.f), hb[j], lb[j]);
+    }
+    if (col < ld) {
+      if (ra < rows) {
+        *reinterpret_cast<uint4*>(hi + ra * ld + col) = *reinterpret_cast<const uint4*>(ha);
+        if (LO) *reinterpret_cast<uint4*>(lo + ra * ld + col) = *reinterpret_cast<const uint4*>(la);
+      }
+      if (ra + 1 < rows) {
+        *reinterpret_cast<uint4*>(hi + (ra + 1) * ld + col) = *reinterpret_cast<const uint4*>(hb);
+        if (LO) *reinterpret_cast<uint4*>(lo + (ra + 1) * ld + col) = *reinterpret_cast<const uint4*>(lb);
+      }
+    }
+    if (hiT != nullptr) {   // uniform
+      __syncthreads();      // the previous tile's column reads are done
 #pragma unroll
-    for (int k = 0; k < 8; ++k) w[k] = sh[p][ct * kTilePitch + part * 8 + k];
-    // block r0/64 of the K-blocked layout: [cols][64] halves, this thread owns rows part*16..+16 of column gc
-    uint4* dst = reinterpret_cast<uint4*>(dstT + ((long long)blockIdx.x * cols + gc) * kTileDim + part * 16);
-    dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
-    dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+      for (int j = 0; j < 8; ++j) {
+        const int w = (cc * 8 + j) * kTilePitch + rp;
+        sh[0][w] = (uint32_t)__half_as_ushort(ha[j]) | ((uint32_t)__half_as_ushort(hb[j]) << 16);
+        if (LO) sh[1][w] = (uint32_t)__half_as_ushort(la[j]) | ((uint32_t)__half_as_ushort(lb[j]) << 16);
+      }
+      __syncthreads();
+      if (gc < cols) {
+#pragma unroll
+        for (int p = 0; p < (LO ? 2 : 1); ++p) {
+          __half* dstT = p == 0 ? hiT : loT;
+          uint32_t w[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) w[k] = sh[p][ct * kTilePitch + part * 8 + k];
+          // block `tile` of the K-blocked layout: [cols][64] halves, this thread owns rows part*16..+16 of column gc
+          uint4* dst = reinterpret_cast<uint4*>(dstT + (tile * cols + gc) * kTileDim + part * 16);
+          dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+          dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+        }
+      }
+    }
+    cur = nxt;
   }
 }
 
@@ -411,11 +513,13 @@ __global__ void __launch_bounds__(256) bn_relu_dot_kernel(const __half* __restri
 // A thread walks its rows two at a time (both rows' loads in flight), keeps fp32 partial sums over 16 rows and flushes
 // them into fp64 accumulators in shared memory, so few registers are live and many blocks fit an SM.
 // ------------------------------------------------------------------------------------------------
-template <int KIND>
+template <int KIND, bool LO>
 __global__ void __launch_bounds__(256) bwd_stats_kernel(const BwdSrc s, long long per_slab, double* __restrict__ sums,
                                                         unsigned* __restrict__ maxes, double* __restrict__ dw,
                                                         double* __restrict__ db) {
-  __shared__ double sh[3][256];
+  // fp64 accumulators: one private slot per thread and column (no atomics while streaming), reduced over the 8 row
+  // phases at the end.  [sum][ty][256 columns] doubles = 32 KB (48 KB for kind 1).
+  __shared__ double sh[KIND == 1 ? 3 : 2][8][256];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int c0 = blockIdx.x * 256 + tx * 8;
   // kind 0/1: a slab is a range of rows.  kind 2 (rows = b * L + l): a slab is a range of LABELS walked for every
@@ -424,8 +528,12 @@ __global__ void __launch_bounds__(256) bwd_stats_kernel(const BwdSrc s, long lon
   const long long extent = KIND == 2 ? s.L : s.rows;
   const long long i_begin = (long long)blockIdx.y * per_slab;
   const long long i_end = i_begin + per_slab < extent ? i_begin + per_slab : extent;
-  for (int i = ty * 32 + tx; i < 768; i += 256) (&sh[0][0])[i] = 0.0;
-  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sh[0][ty][tx * 8 + j] = 0.0;
+    sh[1][ty][tx * 8 + j] = 0.0;
+    if (KIND == 1) sh[KIND == 1 ? 2 : 0][ty][tx * 8 + j] = 0.0;
+  }
   float p1[8], p2[8], p3[8];
   zero8(p1);
   zero8(p2);
@@ -436,43 +544,59 @@ __global__ void __launch_bounds__(256) bwd_stats_kernel(const BwdSrc s, long lon
   auto flush = [&]() {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      atomicAdd(&sh[0][tx * 8 + j], (double)p1[j]);
-      atomicAdd(&sh[1][tx * 8 + j], (double)p2[j]);
-      if (KIND == 1) atomicAdd(&sh[2][tx * 8 + j], (double)p3[j]);
+      sh[0][ty][tx * 8 + j] += (double)p1[j];
+      sh[1][ty][tx * 8 + j] += (double)p2[j];
+      if (KIND == 1) sh[KIND == 1 ? 2 : 0][ty][tx * 8 + j] += (double)p3[j];
       p1[j] = p2[j] = p3[j] = 0.f;
     }
   };
-  if (c0 < s.cols) {
+  if (c0 < s.cols && i_begin + ty < i_end) {
     BnVec b;
     load_bn(s.state, s.cols, c0, b);
     float wv[8];
     if (KIND == 1) load8_f32(s.w + c0, s.cols - c0, wv);
     else zero8(wv);
+    // software pipeline over (protein, row) steps of kRif rows: the next step's loads are issued before this step's math
+    long long bb = 0, i = i_begin + ty;
+    BwdRaw cur[kRif], nxt[kRif];
+#pragma unroll
+    for (int k = 0; k < kRif; ++k)
+      if (i + 8 * k < i_end) bwd_raw_load<KIND, LO>(s, i + 8 * k, c0, cur[k]);
     int it = 0;
-    for (long long bb = 0; bb < n_outer; ++bb) {
-      const long long base = bb * extent;
-      for (long long i = i_begin + ty; i < i_end; i += 8 * kRif) {
-        BwdRaw q[kRif];
+    bool have = true;
+    while (have) {
+      long long nbb = bb, ni = i + 8 * kRif;
+      if (ni >= i_end) {
+        ni = i_begin + ty;
+        ++nbb;
+      }
+      const bool have_next = nbb < n_outer;
+      if (have_next) {
 #pragma unroll
         for (int k = 0; k < kRif; ++k)
-          if (i + 8 * k < i_end) bwd_raw_load<KIND>(s, base + i + 8 * k, c0, q[k]);
-#pragma unroll
-        for (int k = 0; k < kRif; ++k) {
-          if (i + 8 * k >= i_end) continue;
-          float gy[8], xh[8], pre[8];
-          bwd_eval<KIND>(s, q[k], base + i + 8 * k, c0, b, wv, inv_gsc, gy, xh, pre);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            p1[j] += gy[j];
-            p2[j] = fmaf(gy[j], xh[j], p2[j]);
-            if (KIND == 1) p3[j] = fmaf(q[k].gl, fmaxf(pre[j], 0.f), p3[j]);
-            gmax = fmaxf(gmax, fabsf(gy[j]));
-            xmax = fmaxf(xmax, fabsf(xh[j]));
-          }
-          if (KIND == 1 && blockIdx.x == 0 && tx == 0) dbs += (double)q[k].gl;
-        }
-        if ((++it & 7) == 0) flush();   // fp32 partial sums cover at most 8 * kRif rows
+          if (ni + 8 * k < i_end) bwd_raw_load<KIND, LO>(s, nbb * extent + ni + 8 * k, c0, nxt[k]);
       }
+#pragma unroll
+      for (int k = 0; k < kRif; ++k) {
+        if (i + 8 * k >= i_end) continue;
+        float gy[8], xh[8], pre[8];
+        bwd_eval<KIND, LO>(s, cur[k], bb * extent + i + 8 * k, c0, b, wv, inv_gsc, gy, xh, pre);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          p1[j] += gy[j];
+          p2[j] = fmaf(gy[j], xh[j], p2[j]);
+          if (KIND == 1) p3[j] = fmaf(cur[k].gl, fmaxf(pre[j], 0.f), p3[j]);
+          gmax = fmaxf(gmax, fabsf(gy[j]));
+          xmax = fmaxf(xmax, fabsf(xh[j]));
+        }
+        if (KIND == 1 && blockIdx.x == 0 && tx == 0) dbs += (double)cur[k].gl;
+      }
+      if ((++it & 7) == 0) flush();   // fp32 partial sums cover at most 8 * kRif rows
+#pragma unroll
+      for (int k = 0; k < kRif; ++k) cur[k] = nxt[k];
+      bb = nbb;
+      i = ni;
+      have = have_next;
     }
     flush();
   }
@@ -480,9 +604,16 @@ __global__ void __launch_bounds__(256) bwd_stats_kernel(const BwdSrc s, long lon
   const int i = ty * 32 + tx;
   const int c = blockIdx.x * 256 + i;
   if (c < s.cols) {
-    atomicAdd(sums + c, sh[0][i]);
-    atomicAdd(sums + s.cols + c, sh[1][i]);
-    if (KIND == 1 && dw) atomicAdd(dw + c, sh[2][i]);
+    double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) {
+      t0 += sh[0][y][i];
+      t1 += sh[1][y][i];
+      if (KIND == 1) t2 += sh[KIND == 1 ? 2 : 0][y][i];
+    }
+    atomicAdd(sums + c, t0);
+    atomicAdd(sums + s.cols + c, t1);
+    if (KIND == 1 && dw) atomicAdd(dw + c, t2);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -567,16 +698,18 @@ __global__ void scale_vector_kernel(float* __restrict__ out, int n, const float*
 //   da[b][n] = sum_l g_z1[b,l,n]   a column sum over the L rows of protein b (same structure as pass 1), fp64 atomics
 // Reading g_h1 twice at streaming speed is cheaper than synchronising a block once per protein.
 // ------------------------------------------------------------------------------------------------
+template <bool LO>
 __device__ __forceinline__ void pair_gz(const BwdSrc& s, const BwdRaw& q, long long r, int c0, const BnVec& b,
                                         const float (&m1)[8], const float (&m2)[8], float inv_gsc, float (&gz)[8]) {
   float gy[8], xh[8], pre[8], wv[8];
   zero8(wv);
-  bwd_eval<2>(s, q, r, c0, b, wv, inv_gsc, gy, xh, pre);
+  bwd_eval<2, LO>(s, q, r, c0, b, wv, inv_gsc, gy, xh, pre);
 #pragma unroll
   for (int j = 0; j < 8; ++j) gz[j] = c0 + j < s.cols ? b.scale[j] * (gy[j] - m1[j] - xh[j] * m2[j]) : 0.f;
 }
 
 // grid (ceil(cols/256), ceil(L/8)), block (32, 8)
+template <bool LO>
 __global__ void __launch_bounds__(256) pair_dc_kernel(const BwdSrc s, const float* __restrict__ means, long long B,
                                                       float* __restrict__ dc) {
   const int c0 = blockIdx.x * 256 + threadIdx.x * 8;
@@ -589,19 +722,24 @@ __global__ void __launch_bounds__(256) pair_dc_kernel(const BwdSrc s, const floa
   load8_f32(means + s.cols + c0, s.cols - c0, m2);
   zero8(acc);
   const float inv_gsc = s.g_sc ? 1.f / __ldg(s.g_sc) : 1.f;
+  BwdRaw cur[kRif], nxt[kRif];
+#pragma unroll
+  for (int k = 0; k < kRif; ++k)
+    if (k < B) bwd_raw_load<2, LO>(s, k * s.L + l, c0, cur[k]);
   for (long long bb = 0; bb < B; bb += kRif) {
-    BwdRaw q[kRif];
 #pragma unroll
     for (int k = 0; k < kRif; ++k)
-      if (bb + k < B) bwd_raw_load<2>(s, (bb + k) * s.L + l, c0, q[k]);
+      if (bb + kRif + k < B) bwd_raw_load<2, LO>(s, (bb + kRif + k) * s.L + l, c0, nxt[k]);
 #pragma unroll
     for (int k = 0; k < kRif; ++k) {
       if (bb + k >= B) continue;
       float gz[8];
-      pair_gz(s, q[k], (bb + k) * s.L + l, c0, b, m1, m2, inv_gsc, gz);
+      pair_gz<LO>(s, cur[k], (bb + k) * s.L + l, c0, b, m1, m2, inv_gsc, gz);
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] += gz[j];
     }
+#pragma unroll
+    for (int k = 0; k < kRif; ++k) cur[k] = nxt[k];
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j)
@@ -610,6 +748,7 @@ __global__ void __launch_bounds__(256) pair_dc_kernel(const BwdSrc s, const floa
 
 // grid (ceil(cols/256), label slabs), block (32, 8): the slab's labels are walked once per protein (c stays in L1/L2);
 // after each protein the block's 8 row phases are reduced through shared memory and added to da[b] (fp64 atomics).
+template <bool LO>
 __global__ void __launch_bounds__(256) pair_da_kernel(const BwdSrc s, const float* __restrict__ means, long long B,
                                                       long long labels_per_slab, double* __restrict__ da) {
   __shared__ float sh[8][256];
@@ -617,34 +756,50 @@ __global__ void __launch_bounds__(256) pair_da_kernel(const BwdSrc s, const floa
   const int c0 = blockIdx.x * 256 + tx * 8;
   const long long l_begin = (long long)blockIdx.y * labels_per_slab;
   const long long l_end = l_begin + labels_per_slab < s.L ? l_begin + labels_per_slab : s.L;
-  const bool col_ok = c0 < s.cols;
+  const bool active = c0 < s.cols && l_begin + ty < l_end;
   BnVec b;
   float m1[8], m2[8];
   zero8(m1);
   zero8(m2);
-  if (col_ok) {
+  if (active) {
     load_bn(s.state, s.cols, c0, b);
     load8_f32(means + c0, s.cols - c0, m1);
     load8_f32(means + s.cols + c0, s.cols - c0, m2);
   }
   const float inv_gsc = s.g_sc ? 1.f / __ldg(s.g_sc) : 1.f;
-  for (long long bb = 0; bb < B; ++bb) {
+  // pipeline over (protein, label) steps; `acc` is handed to the block reduction whenever the protein changes
+  long long bb = 0, l = l_begin + ty;
+  BwdRaw cur[kRif], nxt[kRif];
+  if (active) {
+#pragma unroll
+    for (int k = 0; k < kRif; ++k)
+      if (l + 8 * k < l_end) bwd_raw_load<2, LO>(s, l + 8 * k, c0, cur[k]);
+  }
+  for (bb = 0; bb < B; ++bb) {
     float acc[8];
     zero8(acc);
-    if (col_ok) {
-      for (long long l = l_begin + ty; l < l_end; l += 8 * kRif) {
-        BwdRaw q[kRif];
+    if (active) {
+      for (l = l_begin + ty; l < l_end; l += 8 * kRif) {
+        long long nbb = bb, nl = l + 8 * kRif;
+        if (nl >= l_end) {
+          nl = l_begin + ty;
+          ++nbb;
+        }
+        if (nbb < B) {
 #pragma unroll
-        for (int k = 0; k < kRif; ++k)
-          if (l + 8 * k < l_end) bwd_raw_load<2>(s, bb * s.L + l + 8 * k, c0, q[k]);
+          for (int k = 0; k < kRif; ++k)
+            if (nl + 8 * k < l_end) bwd_raw_load<2, LO>(s, nbb * s.L + nl + 8 * k, c0, nxt[k]);
+        }
 #pragma unroll
         for (int k = 0; k < kRif; ++k) {
           if (l + 8 * k >= l_end) continue;
           float gz[8];
-          pair_gz(s, q[k], bb * s.L + l + 8 * k, c0, b, m1, m2, inv_gsc, gz);
+          pair_gz<LO>(s, cur[k], bb * s.L + l + 8 * k, c0, b, m1, m2, inv_gsc, gz);
 #pragma unroll
           for (int j = 0; j < 8; ++j) acc[j] += gz[j];
         }
+#pragma unroll
+        for (int k = 0; k < kRif; ++k) cur[k] = nxt[k];
       }
     }
     __syncthreads();   // the previous protein's readers are done with sh

@@ -69,8 +69,8 @@ class NativeOps:
         self.promote_fwd = 256 if self.strict else 0
         self.promote_small = 32 if self.strict else 0
         self.promote_wgrad = 256 if self.strict else 2048
-        # wgrad: rows per launch (measured on B200, fast mode, K = 2M rows: 4096 -> 42 ms, 8192 -> 35 ms, 16384 -> 31 ms per wgrad)
-        self.split_wgrad = 8192 if self.strict else 16384
+        # wgrad: rows per launch (measured on B200, fast mode, K = 2M rows: 4096 -> 42 ms, 8192 -> 35 ms, 16384 -> 31.5 ms, 32768 -> 30.4 ms per wgrad)
+        self.split_wgrad = 16384 if self.strict else 32768
         import os
         if os.environ.get("PN_SPLIT_WGRAD"):          # experiment switch
             self.split_wgrad = int(os.environ["PN_SPLIT_WGRAD"])
