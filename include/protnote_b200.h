@@ -84,6 +84,13 @@ int pn_encoder_forward(const pn_encoder_cfg* cfg, const void* packed, const floa
                        int batch, int T, float* out, void* workspace, size_t workspace_bytes, int mode,
                        void* stream);
 
+/* Same from token ids: tokens [batch][T] uint8 (index into the sorted amino-acid vocabulary, i.e. the argmax of the one-hot
+ * the reference's collator builds, protnote/data/collators.py:123-133; ids >= input_channels give an all-zero column).
+ * 1 byte per residue crosses PCIe instead of 80; the result is bit-identical to pn_encoder_forward on the one-hot. */
+int pn_encoder_forward_tokens(const pn_encoder_cfg* cfg, const void* packed, const uint8_t* tokens,
+                              const int64_t* lengths, int batch, int T, float* out, void* workspace,
+                              size_t workspace_bytes, int mode, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Projection heads + pair scorer: ProtNote.forward from the projections on, eval mode
  * (protnote/models/ProtNote.py:270-322): W_p / W_l (torchvision MLP, :63-81), _get_joint_embeddings (:112-152),
@@ -150,6 +157,18 @@ size_t pn_similarity_workspace_bytes(const pn_scorer_cfg* cfg, long long B, long
 int pn_score_similarity(const pn_scorer_cfg* cfg, const float* P_e, const float* L_e, long long B, long long L,
                         float temperature, float* logits, long long ld_logits, void* workspace, size_t workspace_bytes,
                         int mode, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Evaluation post-processing on the device - what ProtNoteTrainer.evaluate does with every batch of logits before its
+ * metrics (protnote/models/ProtNoteTrainer.py:522-537, calculate_tp_fn_fp :61-83): probs = sigmoid(logits) (nullable
+ * output), predictions = probs >= threshold, per-label true positives / false negatives / false positives ADDED to
+ * tp / fn / fp [L] (fp32, integer-valued).  labels: label_kind 0 none, 1 int64 multihots (collators.py), 2 float32;
+ * row strides in elements.  topk > 0 (<= 64) also writes the k largest logits of every row (descending, ties by lower
+ * index) and their label indices: topk_values [B][topk], topk_indices [B][topk].
+ * ---------------------------------------------------------------------------------------------------------- */
+int pn_postprocess(const float* logits, long long B, long long L, long long ld_logits, const void* labels, int label_kind,
+                   long long ld_labels, float threshold, float* probs, long long ld_probs, float* tp, float* fn, float* fp,
+                   int topk, float* topk_values, int* topk_indices, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Plain dense layer on the same engine: y[M][N] = x[M][K] * w[N][K]^T + bias   (ProteInfer.output_layer,

@@ -801,9 +801,27 @@ size_t pn_encoder_workspace_bytes(const pn_encoder_cfg* cfg, int batch, int T) {
   return encoder_ws(*cfg, batch, T).bytes;
 }
 
+static int encoder_forward_impl(const pn_encoder_cfg* cfg, const void* packed, const float* x, const uint8_t* tokens,
+                                const int64_t* lengths, int batch, int T, float* out, void* workspace,
+                                size_t workspace_bytes, int mode, void* stream_);
+
 int pn_encoder_forward(const pn_encoder_cfg* cfg, const void* packed, const float* x, const int64_t* lengths,
                        int batch, int T, float* out, void* workspace, size_t workspace_bytes, int mode,
                        void* stream_) {
+  if (!x) return fail("null encoder input");
+  return encoder_forward_impl(cfg, packed, x, nullptr, lengths, batch, T, out, workspace, workspace_bytes, mode, stream_);
+}
+
+int pn_encoder_forward_tokens(const pn_encoder_cfg* cfg, const void* packed, const uint8_t* tokens,
+                              const int64_t* lengths, int batch, int T, float* out, void* workspace,
+                              size_t workspace_bytes, int mode, void* stream_) {
+  if (!tokens) return fail("null token input");
+  return encoder_forward_impl(cfg, packed, nullptr, tokens, lengths, batch, T, out, workspace, workspace_bytes, mode, stream_);
+}
+
+static int encoder_forward_impl(const pn_encoder_cfg* cfg, const void* packed, const float* x, const uint8_t* tokens,
+                                const int64_t* lengths, int batch, int T, float* out, void* workspace,
+                                size_t workspace_bytes, int mode, void* stream_) {
   PN_TRY(check_encoder_cfg(cfg));
   const pn_encoder_cfg& c = *cfg;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -822,9 +840,13 @@ int pn_encoder_forward(const pn_encoder_cfg* cfg, const void* packed, const floa
     Arena ws(workspace, workspace_bytes);
     const long long* len = len64 + b0;
     const long long pos = (long long)nb * T;
-    conv_input_kernel<<<ew_grid(pos), 256, 0, stream>>>(x + (long long)b0 * c.input_channels * T, len, nb,
-                                                        c.input_channels, T, W.cin_pad, ws.at<__half>(W.in_hi),
-                                                        ws.at<__half>(W.in_lo));
+    if (tokens)
+      conv_input_tokens_kernel<<<ew_grid(pos * (W.cin_pad / 8)), 256, 0, stream>>>(
+          tokens + (long long)b0 * T, len, nb, c.input_channels, T, W.cin_pad, ws.at<__half>(W.in_hi), ws.at<__half>(W.in_lo));
+    else
+      conv_input_kernel<<<ew_grid(pos), 256, 0, stream>>>(x + (long long)b0 * c.input_channels * T, len, nb,
+                                                          c.input_channels, T, W.cin_pad, ws.at<__half>(W.in_hi),
+                                                          ws.at<__half>(W.in_lo));
     g_launches++;
     PN_CUDA(cudaGetLastError());
     float* X = ws.at<float>(W.x);
@@ -1256,6 +1278,36 @@ int pn_conv1d(const float* x, const int64_t* lengths, int batch, int cin, int T,
   e.scale = ws.at<float>(pl.scale); e.shift = ws.at<float>(pl.shift);
   e.out_f32 = y; e.ld_out = cout;
   return launch_gemm(A, cv, weight_planes(ws, pl), cout, e, mode, stream);
+}
+
+// ---------------------------------------------------------------------------------------- evaluation post-processing
+int pn_postprocess(const float* logits, long long B, long long L, long long ld_logits, const void* labels, int label_kind,
+                   long long ld_labels, float threshold, float* probs, long long ld_probs, float* tp, float* fn, float* fp,
+                   int topk, float* topk_values, int* topk_indices, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (B <= 0 || L <= 0 || !logits) return fail("empty logits");
+  if (label_kind < 0 || label_kind > 2) return fail("label_kind must be 0 (none), 1 (int64) or 2 (float32)");
+  if (label_kind != 0 && (!labels || !tp || !fn || !fp)) return fail("label counts need labels, tp, fn and fp");
+  if (topk < 0 || topk > 64 || topk > L) return fail("topk must be in [0, min(64, L)]");
+  if (topk > 0 && (!topk_values || !topk_indices)) return fail("topk needs output buffers");
+  if (label_kind != 0 || probs) {
+    const int col_blocks = (int)((L + 255) / 256);
+    long long slabs = ((long long)num_sms() * 8 + col_blocks - 1) / col_blocks;
+    long long per = (B + slabs - 1) / slabs;
+    if (per < 8) per = 8;
+    slabs = (B + per - 1) / per;
+    postprocess_counts_kernel<<<dim3(col_blocks, (unsigned)slabs), 256, 0, stream>>>(
+        logits, B, L, ld_logits, labels, label_kind, ld_labels, threshold, probs, ld_probs, per, tp, fn, fp);
+    g_launches++;
+    PN_CUDA(cudaGetLastError());
+  }
+  if (topk > 0) {
+    if (B > 2147483647LL) return fail("too many rows");
+    topk_rows_kernel<<<(unsigned)B, 256, 0, stream>>>(logits, L, ld_logits, topk, topk_values, topk_indices);
+    g_launches++;
+    PN_CUDA(cudaGetLastError());
+  }
+  return 0;
 }
 
 // ---------------------------------------------------------------------------------------- training primitives

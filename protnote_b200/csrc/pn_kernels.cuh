@@ -131,6 +131,26 @@ __global__ void conv_input_kernel(const float* __restrict__ x, const long long* 
   }
 }
 
+// Same from token ids (uint8, one per residue): the one-hot the reference's collator builds on the host
+// (protnote/data/collators.py:123-133, 80 bytes per residue) is generated here from 1 byte per residue.
+// One thread writes 8 channels of one position; ids >= cin or positions >= length give an all-zero column.
+__global__ void conv_input_tokens_kernel(const uint8_t* __restrict__ tokens, const long long* __restrict__ lengths, int B,
+                                         int cin, int T, int cpad, __half* __restrict__ hi, __half* __restrict__ lo) {
+  const int chunks = cpad / 8;
+  const long long total = (long long)B * T * chunks;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long pos = i / chunks;
+    const int c0 = (int)(i % chunks) * 8;
+    const int b = (int)(pos / T), t = (int)(pos % T);
+    const int tok = ((long long)t < lengths[b]) ? (int)tokens[pos] : -1;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (tok == c0 + j && tok < cin) ? 1.f : 0.f;
+    split8_store(v, hi + pos * cpad + c0, lo ? lo + pos * cpad + c0 : nullptr);
+  }
+}
+
 // Layer 1 of the pair scorer after the exact split of Linear(2d -> H) over [p; t]
 // (reference protnote/models/ProtNote.py:112-126,293 materialises [B*L, 2d]; here it never exists):
 //   h1[(b,l)][k] = relu(a[b][k] + c[l][k])      a = BN1-folded protein half, c = BN1-scaled label half
@@ -264,6 +284,101 @@ __global__ void finalize_logits_kernel(const float* __restrict__ partial, int pa
       acc = logf(pm / (1.f - pm));
     }
     logits[b * ld_logits + l] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// evaluation post-processing on the device (what ProtNoteTrainer.evaluate does with the logits of every batch,
+// protnote/models/ProtNoteTrainer.py:522-537 and calculate_tp_fn_fp :61-83): probabilities = sigmoid(logits),
+// predictions = probabilities >= threshold, per-label true positives / false negatives / false positives ADDED to
+// tp / fn / fp (integer-valued floats: exact and order-independent below 2^24).
+// grid (ceil(L/256), row slabs), 256 threads: thread = one label column, rows of the slab in turn (coalesced).
+// label_kind 1: int64 multihots (collators.py), 2: float32.
+// ------------------------------------------------------------------------------------------------
+__global__ void postprocess_counts_kernel(const float* __restrict__ logits, long long B, long long L, long long ld_logits,
+                                          const void* __restrict__ labels, int label_kind, long long ld_labels,
+                                          float threshold, float* __restrict__ probs, long long ld_probs,
+                                          long long rows_per_slab, float* __restrict__ tp, float* __restrict__ fn,
+                                          float* __restrict__ fp) {
+  const long long c = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (c >= L) return;
+  const long long r0 = (long long)blockIdx.y * rows_per_slab;
+  const long long r1 = r0 + rows_per_slab < B ? r0 + rows_per_slab : B;
+  float ntp = 0.f, nfn = 0.f, nfp = 0.f;
+  for (long long r = r0; r < r1; ++r) {
+    const float p = 1.f / (1.f + expf(-logits[r * ld_logits + c]));
+    if (probs) probs[r * ld_probs + c] = p;
+    if (label_kind != 0) {
+      const float y = label_kind == 1 ? (float)reinterpret_cast<const long long*>(labels)[r * ld_labels + c]
+                                      : reinterpret_cast<const float*>(labels)[r * ld_labels + c];
+      const float pred = p >= threshold ? 1.f : 0.f;
+      ntp += pred * y;
+      nfn += (1.f - pred) * y;
+      nfp += pred * (1.f - y);
+    }
+  }
+  if (label_kind != 0) {
+    if (ntp != 0.f) atomicAdd(tp + c, ntp);
+    if (nfn != 0.f) atomicAdd(fn + c, nfn);
+    if (nfp != 0.f) atomicAdd(fp + c, nfp);
+  }
+}
+
+// top-k logits of every row (descending; ties: lower index first), k <= 64: k selection sweeps over the row (L2-resident)
+// by one block per row.  The "identical top-k label indices" check of the north star runs on the device with this.
+__global__ void __launch_bounds__(256) topk_rows_kernel(const float* __restrict__ logits, long long L, long long ld,
+                                                        int k, float* __restrict__ values, int* __restrict__ indices) {
+  __shared__ float sv[8];
+  __shared__ int si[8];
+  __shared__ float last_v;
+  __shared__ int last_i;
+  const float* row = logits + (long long)blockIdx.x * ld;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  if (t == 0) {
+    last_v = __int_as_float(0x7f800000);   // +inf
+    last_i = -1;
+  }
+  __syncthreads();
+  for (int sel = 0; sel < k; ++sel) {
+    const float lv = last_v;
+    const int li = last_i;
+    float best = -__int_as_float(0x7f800000);
+    int besti = 0x7fffffff;
+    for (long long c = t; c < L; c += 256) {
+      const float v = row[c];
+      // candidates strictly after (lv, li) in (value descending, index ascending) order; NaNs are never selected
+      const bool after = v < lv || (v == lv && (int)c > li);
+      if (after && (v > best || (v == best && (int)c < besti))) {
+        best = v;
+        besti = (int)c;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+      if (ov > best || (ov == best && oi < besti)) {
+        best = ov;
+        besti = oi;
+      }
+    }
+    if (lane == 0) {
+      sv[warp] = best;
+      si[warp] = besti;
+    }
+    __syncthreads();
+    if (t == 0) {
+      for (int w = 1; w < 8; ++w)
+        if (sv[w] > best || (sv[w] == best && si[w] < besti)) {
+          best = sv[w];
+          besti = si[w];
+        }
+      values[(long long)blockIdx.x * k + sel] = best;
+      indices[(long long)blockIdx.x * k + sel] = besti == 0x7fffffff ? -1 : besti;
+      last_v = best;
+      last_i = besti;
+    }
+    __syncthreads();
   }
 }
 

@@ -126,6 +126,68 @@ class PackedEncoder:
         return out
 
 
+def _encoder_forward_tokens(self, tokens: torch.Tensor, lengths: torch.Tensor, mode: int = PN_STRICT,
+                            max_workspace_bytes: int = 6 << 30) -> torch.Tensor:
+    """tokens [B, T] integer ids (uint8 on the wire) -> [B, channels]; bit-identical to forward() on their one-hot."""
+    if self.packed is None:
+        raise _lib.ProtnoteB200Error("encoder weights have not been packed")
+    _require_cuda(tokens, "sequence tokens")
+    dev = self.packed.device
+    if tokens.dtype != torch.uint8:
+        if tokens.is_floating_point() or int(tokens.min()) < 0 or int(tokens.max()) > 255:
+            raise ValueError("token ids must be integers in [0, 255]")
+        tokens = tokens.to(torch.uint8)
+    tokens = tokens.contiguous()
+    lengths = lengths.to(device=dev, dtype=torch.int64).contiguous()
+    B, T = tokens.shape
+    out = torch.empty(B, self.cfg.channels, dtype=torch.float32, device=dev)
+    if B == 0:
+        return out
+    need = self.lib.pn_encoder_workspace_bytes(C.byref(self.cfg), B, T)
+    one = self.lib.pn_encoder_workspace_bytes(C.byref(self.cfg), 1, T) + 4096
+    ws = scratch(dev, "encoder", max(min(need + 4096 * B, max_workspace_bytes), one))
+    with torch.cuda.device(dev):
+        check(self.lib.pn_encoder_forward_tokens(C.byref(self.cfg), ptr(self.packed), ptr(tokens), ptr(lengths), B, T,
+                                                 ptr(out), ptr(ws), ws.numel(), mode, stream_ptr()))
+    return out
+
+
+PackedEncoder.forward_tokens = _encoder_forward_tokens
+
+
+def postprocess(logits: torch.Tensor, labels: Optional[torch.Tensor] = None, threshold: float = 0.5,
+                want_probabilities: bool = False, topk: int = 0, counts=None):
+    """Device-side evaluation post-processing of a [B, L] logit batch (ProtNoteTrainer.py:522-537, :61-83).
+    Returns dict(probabilities, tp, fn, fp, topk_values, topk_indices); `counts` = (tp, fn, fp) fp32 [L] tensors to
+    accumulate into across batches (created zeroed when omitted)."""
+    lib = _lib.load()
+    _require_cuda(logits, "logits")
+    if logits.dtype != torch.float32 or logits.stride(1) != 1:
+        logits = logits.float().contiguous()
+    B, L = logits.shape
+    dev = logits.device
+    kind = 0
+    tp = fn = fp = None
+    if labels is not None:
+        _require_cuda(labels, "labels")
+        if labels.dtype == torch.int64:
+            kind = 1
+        else:
+            kind, labels = 2, labels.float()
+        if labels.stride(1) != 1:
+            labels = labels.contiguous()
+        tp, fn, fp = counts if counts is not None else (torch.zeros(L, dtype=torch.float32, device=dev) for _ in range(3))
+    probs = torch.empty(B, L, dtype=torch.float32, device=dev) if want_probabilities else None
+    tv = torch.empty(B, topk, dtype=torch.float32, device=dev) if topk else None
+    ti = torch.empty(B, topk, dtype=torch.int32, device=dev) if topk else None
+    if B > 0:
+        with torch.cuda.device(dev):
+            check(lib.pn_postprocess(ptr(logits), B, L, logits.stride(0), ptr(labels), kind,
+                                     labels.stride(0) if labels is not None else 0, C.c_float(threshold), ptr(probs),
+                                     L, ptr(tp), ptr(fn), ptr(fp), int(topk), ptr(tv), ptr(ti), stream_ptr()))
+    return {"probabilities": probs, "tp": tp, "fn": fn, "fp": fp, "topk_values": tv, "topk_indices": ti}
+
+
 class PackedScorer:
     """Device-resident packed weights of W_p, W_l and the output MLP + the three calls of the scorer."""
 

@@ -109,6 +109,17 @@ class ProteInfer(torch.nn.Module):
         sequence_lengths = sequence_lengths.to(dev, non_blocking=True)
         return self._ensure_packed().forward(x, sequence_lengths, native.MODES[self.precision])
 
+    def get_embeddings_from_tokens(self, tokens, sequence_lengths):
+        """[B, T] integer residue ids (the argmax of the collator's one-hot, collators.py:123-133) -> [B, C]; the result is
+        bit-identical to get_embeddings() on the one-hot, with 1 byte instead of 80 per residue crossing PCIe."""
+        if self.training:
+            raise ProtnoteB200Error("the sm_100a encoder implements eval-mode BatchNorm only; call .eval()")
+        dev = self.conv1.weight.device
+        tokens = tokens.to(torch.uint8) if not tokens.is_cuda and tokens.dtype != torch.uint8 else tokens
+        return self._ensure_packed().forward_tokens(tokens.to(dev, non_blocking=True),
+                                                    sequence_lengths.to(dev, non_blocking=True),
+                                                    native.MODES[self.precision])
+
     def forward(self, x, sequence_lengths):
         features = self.get_embeddings(x, sequence_lengths)
         return native.linear(features, self.output_layer.weight, self.output_layer.bias, native.MODES[self.precision])
