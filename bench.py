@@ -369,8 +369,8 @@ def run_train(args, rank, world, local_rank):
     B = TRAIN_B if args.sequences == B_TOTAL else args.sequences
     T, L = args.seq_len, args.labels
     mode = args.mode if args.train_mode is None else args.train_mode
+    # model.train() as ProtNoteTrainer.train does it: the frozen encoder's BatchNorm layers use batch statistics too
     model = base_config_model(mode).to(dev).train()
-    model.sequence_encoder.eval()           # frozen encoder (TRAIN_SEQUENCE_ENCODER False), running statistics
     params = pn_train.trainable_parameters(model)
     for p in model.sequence_encoder.parameters():
         p.requires_grad_(False)
@@ -459,7 +459,7 @@ def run_train(args, rank, world, local_rank):
                    "mode": mode, "sequences": B, "seq_len": T, "label_rows": L,
                    "parallelism": "1 GPU" if world == 1 else f"label-sharded x{world}: BatchNorm sums and parameter "
                                                               "gradients all-reduced over NCCL",
-                   "encoder": "frozen, eval-mode BatchNorm", "l2": "activations (GBs per layer) are far larger than the L2"},
+                   "encoder": "frozen (no gradient), train-mode BatchNorm (batch statistics) as in the reference", "l2": "activations (GBs per layer) are far larger than the L2"},
         "e2e": {"value": pairs / (ms_e2e * 1e-3), "unit": "pairs/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": int(onehots_h.numel() * 4 + lengths_h.numel() * 8 + labels_h.numel() * 4 + y_h.numel() * 4),
                 "d2h_bytes_per_step": 4 * world},

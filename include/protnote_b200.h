@@ -84,6 +84,22 @@ int pn_encoder_forward(const pn_encoder_cfg* cfg, const void* packed, const floa
                        int batch, int T, float* out, void* workspace, size_t workspace_bytes, int mode,
                        void* stream);
 
+/* Training-mode forward of the (frozen) encoder.  ProtNoteTrainer.train calls model.train(), which also flips the frozen
+ * encoder's BatchNorm1d layers to BATCH statistics (protein_encoders.py:35-37,47-50; ProtNoteTrainer.py:844): every
+ * BatchNorm normalises with the mean / biased variance over all batch x T positions of its input (padding positions are
+ * zeros and count) and updates running_mean / running_var with `momentum` (0.01) and the unbiased variance.
+ * packed_raw: pn_encoder_pack_raw (same parameter list as pn_encoder_pack; no BatchNorm is folded).
+ * bn_params: HOST array of 8 * num_blocks fp32 device pointers, per block bn_activation_1.0.{weight, bias, running_mean,
+ * running_var} then bn_activation_2.0.{...}; running statistics are updated in place when update_running != 0.
+ * The whole batch is one unit (the statistics couple its sequences): workspace >= pn_encoder_train_workspace_bytes. */
+int pn_encoder_pack_raw(const pn_encoder_cfg* cfg, const float* const* params, int num_params, void* packed,
+                        size_t packed_bytes, void* stream);
+size_t pn_encoder_train_workspace_bytes(const pn_encoder_cfg* cfg, int batch, int T);
+int pn_encoder_forward_train(const pn_encoder_cfg* cfg, const void* packed_raw, const float* x, const int64_t* lengths,
+                             int batch, int T, const float* const* bn_params, int num_bn_params, float momentum,
+                             int update_running, float* out, void* workspace, size_t workspace_bytes, int mode,
+                             void* stream);
+
 /* Same from token ids: tokens [batch][T] uint8 (index into the sorted amino-acid vocabulary, i.e. the argmax of the one-hot
  * the reference's collator builds, protnote/data/collators.py:123-133; ids >= input_channels give an all-zero column).
  * 1 byte per residue crosses PCIe instead of 80; the result is bit-identical to pn_encoder_forward on the one-hot. */

@@ -72,3 +72,32 @@ def train_step_oracle(sd: Dict[str, torch.Tensor], P_f, L_f, targets, cfg: Score
 def synth_targets(B: int, L: int, seed: int = 99, density: float = 0.05):
     g = torch.Generator().manual_seed(seed)
     return (torch.rand(B, L, generator=g) < density).float()
+
+
+def proteinfer_embeddings_train(sd: Dict[str, torch.Tensor], x, lengths, cfg, prefix: str = "sequence_encoder.",
+                                dtype=torch.float64, momentum: float = 0.01):
+    """ProteInfer.get_embeddings with the module in .train() mode (protein_encoders.py:109-118 with BatchNorm1d using batch
+    statistics over all B x T positions of the masked tensors, :35-37,47-50,61-67).  Returns (embeddings [B, C],
+    {running-stat key: updated value}).  Pinned against the reference class by tests/test_train_cpu.py."""
+    from .protnote_oracle import masked_conv, zero_padding
+    new_stats: Dict[str, torch.Tensor] = {}
+
+    def bn(t, name):
+        rm = sd[name + ".running_mean"].detach().clone().to(dtype)
+        rv = sd[name + ".running_var"].detach().clone().to(dtype)
+        y = F.batch_norm(t, rm, rv, sd[name + ".weight"].to(dtype), sd[name + ".bias"].to(dtype), True, momentum, cfg.bn_eps)
+        new_stats[name + ".running_mean"], new_stats[name + ".running_var"] = rm, rv
+        return y
+
+    with torch.no_grad():
+        f = masked_conv(x.to(dtype), lengths, sd[prefix + "conv1.weight"].to(dtype), sd[prefix + "conv1.bias"].to(dtype), 1)
+        for i in range(cfg.num_resnet_blocks):
+            q = f"{prefix}resnet_blocks.{i}"
+            out = torch.relu(bn(f, q + ".bn_activation_1.0"))
+            out = masked_conv(out, lengths, sd[q + ".masked_conv1.weight"].to(dtype), sd[q + ".masked_conv1.bias"].to(dtype),
+                              cfg.dilation_base ** i)
+            out = torch.relu(bn(out, q + ".bn_activation_2.0"))
+            out = masked_conv(out, lengths, sd[q + ".masked_conv2.weight"].to(dtype), sd[q + ".masked_conv2.bias"].to(dtype), 1)
+            f = out + f
+        f = zero_padding(f, lengths)
+        return f.sum(-1) / lengths.reshape(-1, 1).to(dtype), new_stats

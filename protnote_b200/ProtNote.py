@@ -221,6 +221,10 @@ class ProtNote(nn.Module):
         else:
             raise ValueError("Incompatible sequence parameters passed to forward method.")
         logits = pn_train.train_logits(self, P_f, L_f)
+        # BatchNorm running statistics were updated by the kernels through raw pointers (and the optimizer is about to
+        # change the weights): the eval-mode pack and the cached label projection are stale from here on
+        self._packed_key = None
+        self._label_cache = None
         return logits, {"output_layer_embeddings": [], "joint_embeddings": []}
 
     # ------------------------------------------------------------------ reference interface

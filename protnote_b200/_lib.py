@@ -54,6 +54,10 @@ SIGNATURES = {
     "pn_encoder_pack": (_I, [C.POINTER(EncoderCfg), C.POINTER(_P), _I, _P, _SZ, _P]),
     "pn_encoder_workspace_bytes": (_SZ, [C.POINTER(EncoderCfg), _I, _I]),
     "pn_encoder_forward": (_I, [C.POINTER(EncoderCfg), _P, _P, _P, _I, _I, _P, _P, _SZ, _I, _P]),
+    "pn_encoder_pack_raw": (_I, [C.POINTER(EncoderCfg), C.POINTER(_P), _I, _P, _SZ, _P]),
+    "pn_encoder_train_workspace_bytes": (_SZ, [C.POINTER(EncoderCfg), _I, _I]),
+    "pn_encoder_forward_train": (_I, [C.POINTER(EncoderCfg), _P, _P, _P, _I, _I, C.POINTER(_P), _I, C.c_float, _I, _P, _P,
+                                      _SZ, _I, _P]),
     "pn_encoder_forward_tokens": (_I, [C.POINTER(EncoderCfg), _P, _P, _P, _I, _I, _P, _P, _SZ, _I, _P]),
     "pn_postprocess": (_I, [_P, _LL, _LL, _LL, _P, _I, _LL, C.c_float, _P, _LL, _P, _P, _P, _I, _P, _P, _P]),
     "pn_scorer_num_params": (_I, [C.POINTER(ScorerCfg)]),

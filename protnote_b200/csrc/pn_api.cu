@@ -764,8 +764,21 @@ size_t pn_encoder_packed_bytes(const pn_encoder_cfg* cfg) {
   return encoder_layout(*cfg).bytes;
 }
 
+static int encoder_pack_impl(const pn_encoder_cfg* cfg, const float* const* params, int num_params, void* packed,
+                             size_t packed_bytes, bool fold_bn, void* stream_);
+
 int pn_encoder_pack(const pn_encoder_cfg* cfg, const float* const* params, int num_params, void* packed,
                     size_t packed_bytes, void* stream_) {
+  return encoder_pack_impl(cfg, params, num_params, packed, packed_bytes, true, stream_);
+}
+
+int pn_encoder_pack_raw(const pn_encoder_cfg* cfg, const float* const* params, int num_params, void* packed,
+                        size_t packed_bytes, void* stream_) {
+  return encoder_pack_impl(cfg, params, num_params, packed, packed_bytes, false, stream_);
+}
+
+static int encoder_pack_impl(const pn_encoder_cfg* cfg, const float* const* params, int num_params, void* packed,
+                             size_t packed_bytes, bool fold_bn, void* stream_) {
   PN_TRY(check_encoder_cfg(cfg));
   const pn_encoder_cfg& c = *cfg;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -787,8 +800,10 @@ int pn_encoder_pack(const pn_encoder_cfg* cfg, const float* const* params, int n
     g_launches++;
     PN_CUDA(cudaGetLastError());
     // dilated conv (Cb, C, k) + bias, then bn_activation_2 folded into its epilogue
-    PN_TRY(pack_linear(pk, b.conv_d, q[4], (long long)c.channels * k, k, 1, (long long)c.channels * k, q[5], q[6], q[7],
-                       q[8], q[9], c.bn_eps, stream));
+    // (training mode uses batch statistics: fold_bn == false keeps only the conv bias in the epilogue)
+    PN_TRY(pack_linear(pk, b.conv_d, q[4], (long long)c.channels * k, k, 1, (long long)c.channels * k, q[5],
+                       fold_bn ? q[6] : nullptr, fold_bn ? q[7] : nullptr, fold_bn ? q[8] : nullptr,
+                       fold_bn ? q[9] : nullptr, c.bn_eps, stream));
     // pointwise conv (C, Cb, 1) + bias
     PN_TRY(pack_linear(pk, b.conv_p, q[10], c.bottleneck, 1, 0, c.bottleneck, q[11], nullptr, nullptr, nullptr, nullptr,
                        0.f, stream));
@@ -907,6 +922,127 @@ static int encoder_forward_impl(const pn_encoder_cfg* cfg, const void* packed, c
     g_launches++;
     PN_CUDA(cudaGetLastError());
   }
+  return 0;
+}
+
+// Training-mode encoder forward: every BatchNorm1d uses the statistics of THIS batch over all batch x T positions
+// (padding positions are zeros and are counted, exactly as torch.nn.BatchNorm1d sees the [B, C, T] tensor in
+// Residual.forward, protein_encoders.py:61-67) and updates its running statistics (momentum 0.01).  This is what the
+// reference's frozen encoder does inside ProtNoteTrainer.train (model.train() reaches every submodule,
+// ProtNoteTrainer.py:844).  The batch cannot be cut into sub-batches (the statistics couple all sequences).
+struct EncoderTrainWs {
+  size_t in_hi, in_lo, x, hraw, act_hi, act_lo, hid_hi, hid_lo, stats, state;
+  int cin_pad, ldc, ldb;
+  size_t bytes;
+};
+
+static EncoderTrainWs encoder_train_ws(const pn_encoder_cfg& c, long long batch, long long T) {
+  Arena ar(nullptr, 0);
+  EncoderTrainWs w;
+  w.cin_pad = (int)round_up(c.input_channels, 64);
+  w.ldc = (int)round_up(c.channels, 64);
+  w.ldb = (int)round_up(c.bottleneck, 64);
+  const size_t pos = (size_t)batch * T;
+  w.in_hi = ar.take(pos * w.cin_pad * 2);
+  w.in_lo = ar.take(pos * w.cin_pad * 2);
+  w.x = ar.take(pos * w.ldc * 4);
+  w.hraw = ar.take(pos * w.ldb * 4);
+  w.act_hi = ar.take(pos * w.ldc * 2);
+  w.act_lo = ar.take(pos * w.ldc * 2);
+  w.hid_hi = ar.take(pos * w.ldb * 2);
+  w.hid_lo = ar.take(pos * w.ldb * 2);
+  w.stats = ar.take(sizeof(double) * 2 * (size_t)w.ldc);
+  w.state = ar.take(sizeof(float) * 4 * (size_t)w.ldc);
+  w.bytes = ar.off;
+  return w;
+}
+
+size_t pn_encoder_train_workspace_bytes(const pn_encoder_cfg* cfg, int batch, int T) {
+  if (check_encoder_cfg(cfg)) return 0;
+  return encoder_train_ws(*cfg, batch, T).bytes;
+}
+
+int pn_encoder_forward_train(const pn_encoder_cfg* cfg, const void* packed_raw, const float* x, const int64_t* lengths,
+                             int batch, int T, const float* const* bn_params, int num_bn_params, float momentum,
+                             int update_running, float* out, void* workspace, size_t workspace_bytes, int mode,
+                             void* stream_) {
+  PN_TRY(check_encoder_cfg(cfg));
+  const pn_encoder_cfg& c = *cfg;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (batch <= 0 || T <= 0 || !x) return fail("empty encoder input (batch %d, T %d)", batch, T);
+  if (num_bn_params != 8 * c.num_blocks) return fail("training-mode encoder expects %d BatchNorm pointers, got %d", 8 * c.num_blocks, num_bn_params);
+  const EncoderLayout L = encoder_layout(c);
+  Arena pk(const_cast<void*>(packed_raw), L.bytes);
+  const EncoderTrainWs W = encoder_train_ws(c, batch, T);
+  if (W.bytes > workspace_bytes) return fail("training-mode encoder workspace too small: %zu < %zu", workspace_bytes, W.bytes);
+  Arena ws(workspace, workspace_bytes);
+  const long long* len = reinterpret_cast<const long long*>(lengths);
+  const long long pos = (long long)batch * T;
+  const bool strict = mode == PN_STRICT;
+  conv_input_kernel<<<ew_grid(pos), 256, 0, stream>>>(x, len, batch, c.input_channels, T, W.cin_pad, ws.at<__half>(W.in_hi),
+                                                      ws.at<__half>(W.in_lo));
+  g_launches++;
+  PN_CUDA(cudaGetLastError());
+  float* X = ws.at<float>(W.x);
+  float* Hraw = ws.at<float>(W.hraw);
+  double* stats = ws.at<double>(W.stats);
+  float* state = ws.at<float>(W.state);
+  ConvView cv;
+  cv.batch = batch; cv.T = T; cv.lengths = len;
+  {   // conv1: x0 = mask(conv(x) + bias)
+    Planes A;
+    A.hi = ws.at<__half>(W.in_hi); A.lo = ws.at<__half>(W.in_lo);
+    A.rows = pos; A.cols = c.input_channels; A.ld = W.cin_pad;
+    cv.taps = c.kernel_size; cv.dil = 1; cv.cpad = L.conv1.cpad;
+    Epilogue e;
+    e.scale = pk.at<float>(L.conv1.scale); e.shift = pk.at<float>(L.conv1.shift);
+    e.out_f32 = X; e.ld_out = W.ldc;
+    PN_TRY(launch_gemm(A, cv, weight_planes(pk, L.conv1), c.channels, e, mode, stream, kStageEncoder));
+  }
+  // BatchNorm (batch statistics over all batch*T positions) + ReLU + input mask of the next conv, fp32 -> planes
+  auto bn_relu = [&](const float* src, int cols, long long ld_src, const float* const* q, __half* hi, __half* lo,
+                     long long ld_dst) -> int {
+    PN_TRY(pn_t_col_stats(nullptr, nullptr, src, pos, cols, ld_src, stats, stream));
+    PN_TRY(pn_t_bn_finalize(stats, (double)pos, nullptr, 0.0, q[0], q[1], c.bn_eps, momentum,
+                            update_running ? const_cast<float*>(q[2]) : nullptr,
+                            update_running ? const_cast<float*>(q[3]) : nullptr, cols, state, stream));
+    BnReluMaskF32Producer p{src, pos, cols, ld_src, state, len, T};
+    return launch_emit(p, pos, cols, hi, strict ? lo : nullptr, ld_dst, nullptr, nullptr, 0, stream);
+  };
+  long long dil = 1;
+  for (int i = 0; i < c.num_blocks; ++i) {
+    const EncoderLayout::Block& b = L.blocks[i];
+    const float* const* q = bn_params + 8 * i;
+    PN_TRY(bn_relu(X, c.channels, W.ldc, q, ws.at<__half>(W.act_hi), ws.at<__half>(W.act_lo), W.ldc));
+    {   // hraw = mask(dilated_conv(act) + bias)
+      Planes A;
+      A.hi = ws.at<__half>(W.act_hi); A.lo = ws.at<__half>(W.act_lo);
+      A.rows = pos; A.cols = c.channels; A.ld = W.ldc;
+      cv.taps = c.kernel_size; cv.dil = (int)dil; cv.cpad = b.conv_d.cpad;
+      Epilogue e;
+      e.scale = pk.at<float>(b.conv_d.scale); e.shift = pk.at<float>(b.conv_d.shift);
+      e.out_f32 = Hraw; e.ld_out = W.ldb;
+      PN_TRY(launch_gemm(A, cv, weight_planes(pk, b.conv_d), c.bottleneck, e, mode, stream, kStageEncoder));
+    }
+    PN_TRY(bn_relu(Hraw, c.bottleneck, W.ldb, q + 4, ws.at<__half>(W.hid_hi), ws.at<__half>(W.hid_lo), W.ldb));
+    {   // x = x + mask(conv1x1(hid) + bias)
+      Planes A;
+      A.hi = ws.at<__half>(W.hid_hi); A.lo = ws.at<__half>(W.hid_lo);
+      A.rows = pos; A.cols = c.bottleneck; A.ld = W.ldb;
+      cv.taps = 1; cv.dil = 1; cv.cpad = b.conv_p.cpad;
+      Epilogue e;
+      e.scale = pk.at<float>(b.conv_p.scale); e.shift = pk.at<float>(b.conv_p.shift);
+      e.resid = X; e.ld_resid = W.ldc;
+      e.out_f32 = X; e.ld_out = W.ldc;
+      PN_TRY(launch_gemm(A, cv, weight_planes(pk, b.conv_p), c.channels, e, mode, stream, kStageEncoder));
+    }
+    dil *= c.dilation_base;
+    if (dil > (1 << 24)) return fail("dilation overflow");
+  }
+  pool_mean_kernel<<<dim3((c.channels + 31) / 32, batch), dim3(32, 8), 0, stream>>>(X, W.ldc, len, T, c.channels, out,
+                                                                                    c.channels);
+  g_launches++;
+  PN_CUDA(cudaGetLastError());
   return 0;
 }
 

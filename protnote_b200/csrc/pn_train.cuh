@@ -168,6 +168,46 @@ struct BnReluProducer {         // relu(z * scale + shift)
   }
 };
 
+// relu(x * scale + shift) of an fp32 channels-last activation tensor [B*T][ld], zeroed at positions >= length:
+// BatchNorm1d (batch statistics) + ReLU of the sequence encoder followed by the input mask of the next MaskedConv1D
+// (protein_encoders.py:35-37,47-50 then :14)
+struct BnReluMaskF32Producer {
+  const float* x; long long rows; int cols; long long ldx; const float* state; const long long* lengths; int T;
+  struct Ctx { float sc[8], sf[8]; };
+  struct Raw { float a[8], b[8]; };
+  __device__ __forceinline__ void init(int c0, Ctx& k) const {
+    zero8(k.sc);
+    zero8(k.sf);
+    if (c0 < cols) {
+      load8_f32(state + c0, cols - c0, k.sc);
+      load8_f32(state + cols + c0, cols - c0, k.sf);
+    }
+  }
+  __device__ __forceinline__ bool valid(long long r) const {
+    return r < rows && (lengths == nullptr || (r % T) < lengths[r / T]);
+  }
+  template <bool LO>
+  __device__ __forceinline__ void load(long long r, int c0, Raw& q) const {
+    if (c0 >= cols) return;
+    if (valid(r)) load8_f32(x + r * ldx + c0, cols - c0, q.a);
+    if (valid(r + 1)) load8_f32(x + (r + 1) * ldx + c0, cols - c0, q.b);
+  }
+  template <bool LO>
+  __device__ __forceinline__ void eval(const Ctx& k, const Raw& q, long long r, int c0, float (&va)[8], float (&vb)[8]) const {
+    zero8(va);
+    zero8(vb);
+    if (c0 >= cols) return;
+    if (valid(r)) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) va[j] = c0 + j < cols ? fmaxf(fmaf(q.a[j], k.sc[j], k.sf[j]), 0.f) : 0.f;
+    }
+    if (valid(r + 1)) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) vb[j] = c0 + j < cols ? fmaxf(fmaf(q.b[j], k.sc[j], k.sf[j]), 0.f) : 0.f;
+    }
+  }
+};
+
 struct PairHiddenProducer {     // relu((a[b] + c[l]) * scale + shift), row r = b * L + l   (ProtNote.py:112-126 + layer 1)
   const float* a; const float* c; long long L; long long rows; int cols; const float* state;
   struct Ctx { float sc[8], sf[8]; };

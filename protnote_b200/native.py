@@ -155,6 +155,47 @@ def _encoder_forward_tokens(self, tokens: torch.Tensor, lengths: torch.Tensor, m
 PackedEncoder.forward_tokens = _encoder_forward_tokens
 
 
+def _encoder_pack_raw(self, params: Sequence[torch.Tensor]):
+    """Weights for the training-mode forward: nothing folded (BatchNorm uses batch statistics there)."""
+    dev = params[0].device
+    keep = [_f32c(p.detach()) for p in params]
+    nbytes = self.lib.pn_encoder_packed_bytes(C.byref(self.cfg))
+    if getattr(self, "packed_raw", None) is None or self.packed_raw.numel() < nbytes or self.packed_raw.device != dev:
+        self.packed_raw = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(self.lib.pn_encoder_pack_raw(C.byref(self.cfg), pointer_array(keep), len(keep), ptr(self.packed_raw),
+                                           self.packed_raw.numel(), stream_ptr()))
+
+
+def _encoder_forward_train(self, x: torch.Tensor, lengths: torch.Tensor, bn_params: Sequence[torch.Tensor],
+                           momentum: float, update_running: bool = True, mode: int = PN_STRICT) -> torch.Tensor:
+    """Batch-statistic BatchNorm forward of the encoder (pn_encoder_forward_train); bn_params: per block
+    bn1.{weight, bias, running_mean, running_var}, bn2.{...} - the running statistics are updated in place."""
+    _require_cuda(x, "sequence_onehots")
+    dev = self.packed_raw.device
+    x = _f32c(x)
+    lengths = lengths.to(device=dev, dtype=torch.int64).contiguous()
+    B, cin, T = x.shape
+    if cin != self.cfg.input_channels:
+        raise ValueError(f"expected {self.cfg.input_channels} input channels, got {cin}")
+    for p in bn_params:
+        if p.dtype != torch.float32 or not p.is_contiguous() or not p.is_cuda:
+            raise _lib.ProtnoteB200Error("BatchNorm parameters / buffers must be contiguous fp32 CUDA tensors")
+    out = torch.empty(B, self.cfg.channels, dtype=torch.float32, device=dev)
+    if B == 0:
+        return out
+    ws = scratch(dev, "encoder_train", self.lib.pn_encoder_train_workspace_bytes(C.byref(self.cfg), B, T))
+    with torch.cuda.device(dev):
+        check(self.lib.pn_encoder_forward_train(C.byref(self.cfg), ptr(self.packed_raw), ptr(x), ptr(lengths), B, T,
+                                                pointer_array(bn_params), len(bn_params), C.c_float(momentum),
+                                                int(update_running), ptr(out), ptr(ws), ws.numel(), mode, stream_ptr()))
+    return out
+
+
+PackedEncoder.pack_raw = _encoder_pack_raw
+PackedEncoder.forward_train = _encoder_forward_train
+
+
 def postprocess(logits: torch.Tensor, labels: Optional[torch.Tensor] = None, threshold: float = 0.5,
                 want_probabilities: bool = False, topk: int = 0, counts=None):
     """Device-side evaluation post-processing of a [B, L] logit batch (ProtNoteTrainer.py:522-537, :61-83).

@@ -89,6 +89,9 @@ class ProteInfer(torch.nn.Module):
     def _ensure_packed(self):
         srcs = self._pack_sources()
         key = _versions(srcs)
+        if self._packed is not None and self._packed_key is None:      # invalidated by a training-mode forward
+            self._packed.pack(srcs)
+            self._packed_key = key
         if self._packed is None or key != self._packed_key:
             bottleneck = self.resnet_blocks[0].masked_conv1.out_channels if len(self.resnet_blocks) else 1
             enc = native.PackedEncoder(self.conv1.in_channels, self.conv1.out_channels, bottleneck,
@@ -101,13 +104,47 @@ class ProteInfer(torch.nn.Module):
     # ------------------------------------------------------------------ reference interface
     def get_embeddings(self, x, sequence_lengths):
         """[B, Cin, T] float + [B] lengths -> [B, C] masked mean of the residual stream (protein_encoders.py:109-118)."""
-        if self.training:
-            raise ProtnoteB200Error("the sm_100a encoder implements eval-mode BatchNorm only (the reference freezes the "
-                                    "sequence encoder: TRAIN_SEQUENCE_ENCODER False, base_config.yaml:71); call .eval()")
         dev = self.conv1.weight.device
         x = x.to(dev, non_blocking=True)
         sequence_lengths = sequence_lengths.to(dev, non_blocking=True)
+        if self.training:
+            return self._get_embeddings_train(x, sequence_lengths)
         return self._ensure_packed().forward(x, sequence_lengths, native.MODES[self.precision])
+
+    def _get_embeddings_train(self, x, sequence_lengths):
+        """.train() mode: every BatchNorm1d normalises with the statistics of this batch (over all B x T positions, padding
+        included) and updates its running statistics - what the reference's frozen encoder does during training, because
+        ProtNoteTrainer.train's model.train() reaches it (ProtNoteTrainer.py:844; protein_encoders.py:35-37,47-50).
+        Forward only: the encoder is frozen (TRAIN_SEQUENCE_ENCODER False, base_config.yaml:71), no gradient is produced."""
+        if len(self.resnet_blocks) == 0:
+            return self._ensure_packed().forward(x, sequence_lengths, native.MODES[self.precision])
+        if self._packed is None:
+            self._ensure_packed()
+        enc = self._packed
+        convs = [self.conv1.weight, self.conv1.bias]
+        for blk in self.resnet_blocks:
+            convs += [blk.masked_conv1.weight, blk.masked_conv1.bias, blk.masked_conv2.weight, blk.masked_conv2.bias]
+        key = _versions(convs)      # the raw pack holds conv weights only: running-statistic updates do not invalidate it
+        if getattr(self, "_raw_key", None) != key or getattr(enc, "packed_raw", None) is None:
+            enc.pack_raw(self._pack_sources())
+            self._raw_key = key
+        bns, momentum = [], None
+        for blk in self.resnet_blocks:
+            for bn in (blk.bn_activation_1[0], blk.bn_activation_2[0]):
+                if bn.momentum is None or not bn.track_running_stats:
+                    raise ProtnoteB200Error("the encoder's BatchNorm layers must track running statistics with a momentum")
+                momentum = bn.momentum if momentum is None else momentum
+                if bn.momentum != momentum:
+                    raise ProtnoteB200Error("one momentum for all encoder BatchNorm layers is assumed")
+                bns += [bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var]
+        out = enc.forward_train(x, sequence_lengths, bns, momentum, True, native.MODES[self.precision])
+        # the kernels updated the running statistics through raw pointers (torch's version counters did not move):
+        # the eval-mode pack, which folds those statistics, is stale from here on
+        self._packed_key = None
+        for blk in self.resnet_blocks:
+            for bn in (blk.bn_activation_1[0], blk.bn_activation_2[0]):
+                bn.num_batches_tracked += 1
+        return out
 
     def get_embeddings_from_tokens(self, tokens, sequence_lengths):
         """[B, T] integer residue ids (the argmax of the collator's one-hot, collators.py:123-133) -> [B, C]; the result is

@@ -297,3 +297,65 @@ def test_training_step_matches_reference_golden(name):
     bufs = dict(model.named_buffers())
     for k, v in g["running"].items():
         assert float((bufs[k].cpu().double() - v).abs().max()) <= 1e-5 * max(1.0, float(v.abs().max())), k
+
+
+@pytest.mark.parametrize("case,B,T", [("tiny_concat", 5, 150), ("tiny_long", 3, 400), ("base_small", 3, 200)])
+def test_train_mode_encoder_matches_oracle(case, B, T):
+    """model.train() also reaches the frozen encoder (ProtNoteTrainer.py:844): batch-statistic BatchNorm over all B x T
+    positions, running statistics updated with momentum 0.01."""
+    from oracle.protnote_oracle import synth_inputs
+    from oracle.train_oracle import proteinfer_embeddings_train
+    ecfg, scfg, *_ = CASES[case]
+    sd = synth_state_dict(ecfg, scfg, seed=CASES[case][6], calib_T=64)
+    onehots, lengths, _ = synth_inputs(B, T, 4, ecfg, scfg, ragged=True, seed=5)
+    want, stats = proteinfer_embeddings_train(sd, onehots, lengths, ecfg)
+    model = build_b200_model(ecfg, scfg, sd, device="cuda").train()
+    with torch.no_grad():
+        got = model.sequence_encoder.get_embeddings(onehots.cuda(), lengths.cuda())
+    assert float((got.cpu().double() - want).abs().max()) < 5e-6 * max(1.0, float(want.abs().max()))
+    bufs = dict(model.named_buffers())
+    for k, v in stats.items():
+        assert float((bufs[k].cpu().double() - v).abs().max()) <= 2e-6 * max(1.0, float(v.abs().max())), k
+    assert int(bufs["sequence_encoder.resnet_blocks.0.bn_activation_1.0.num_batches_tracked"]) == 1
+    # eval mode afterwards uses the updated running statistics (the eval pack is refreshed)
+    model.eval()
+    with torch.no_grad():
+        e_eval = model.sequence_encoder.get_embeddings(onehots.cuda(), lengths.cuda())
+    from oracle.protnote_oracle import proteinfer_embeddings
+    sd2 = dict(sd)
+    sd2.update({k: v.float() for k, v in stats.items()})
+    want_eval = proteinfer_embeddings(sd2, onehots, lengths, ecfg, "sequence_encoder.", dtype=torch.float64)
+    assert float((e_eval.cpu().double() - want_eval).abs().max()) < 5e-6 * max(1.0, float(want_eval.abs().max()))
+
+
+def test_whole_model_train_mode_with_onehot_input():
+    """The unchanged trainer calls model.train() and passes sequence_onehots: the step must run end to end."""
+    from oracle.protnote_oracle import synth_inputs
+    from oracle.train_oracle import proteinfer_embeddings_train
+    ecfg, scfg, *_ = CASES["tiny_concat"]
+    sd = synth_state_dict(ecfg, scfg, seed=42, calib_T=64)
+    onehots, lengths, labels = synth_inputs(6, 120, 40, ecfg, scfg, ragged=True, seed=9)
+    y = synth_targets(6, 40, 9)
+    model = build_b200_model(ecfg, scfg, sd, device="cuda").train()
+    logits, _ = model(sequence_onehots=onehots.cuda(), sequence_lengths=lengths.cuda(), label_embeddings=labels.cuda())
+    loss = torch.nn.functional.binary_cross_entropy_with_logits(logits, y.cuda())
+    loss.backward()
+    P_f, enc_stats = proteinfer_embeddings_train(sd, onehots, lengths, ecfg)
+    o_logits, o_loss, o_grads, head_stats = train_step_oracle(sd, P_f, labels, y, scfg)
+    assert float((logits.detach().cpu().double() - o_logits).abs().max()) < 2e-4
+    assert abs(float(loss.detach()) - float(o_loss)) < 1e-5
+    named = dict(model.named_parameters())
+    for k, gref in o_grads.items():
+        err = (named[k].grad.cpu().double() - gref).abs()
+        if float(err.max()) > 1e-4 * float(gref.abs().max()) + 1e-9:
+            assert float(err.norm() / gref.norm().clamp_min(1e-30)) <= 1e-3, k
+    # back in eval mode the fused kernels must see the running statistics this step just updated (no stale weight pack)
+    from oracle.protnote_oracle import protnote_forward
+    sd2 = dict(sd)
+    sd2.update({k: v.float() for k, v in enc_stats.items()})
+    sd2.update({k: v.float() for k, v in head_stats.items()})
+    model.eval()
+    with torch.no_grad():
+        e_logits, _ = model(sequence_onehots=onehots.cuda(), sequence_lengths=lengths.cuda(), label_embeddings=labels.cuda())
+    want = protnote_forward(sd2, onehots, lengths, labels, ecfg, scfg, dtype=torch.float64)
+    assert float((e_logits.cpu().double() - want).abs().max()) < 2e-4

@@ -117,3 +117,23 @@ def test_train_oracle_matches_committed_golden(name):
         assert (grads[k] - v).abs().max() <= 1e-9 * max(1.0, float(v.abs().max())), k
     for k, v in g["running"].items():
         assert (stats[k] - v).abs().max() < 1e-9, k
+
+
+@pytest.mark.skipif(not reference_available(), reason="needs /root/reference (build container only)")
+def test_train_mode_encoder_oracle_matches_reference():
+    """The frozen encoder in .train() mode (batch-statistic BatchNorm, running statistics updated) - reference class vs oracle."""
+    from oracle.make_golden import build_reference_model
+    from oracle.protnote_oracle import synth_inputs
+    from oracle.train_oracle import proteinfer_embeddings_train
+    ecfg, scfg, *_ = CASES["tiny_concat"]
+    sd = synth_state_dict(ecfg, scfg, seed=42, calib_T=64)
+    onehots, lengths, _ = synth_inputs(5, 90, 4, ecfg, scfg, ragged=True, seed=31)
+    ref = build_reference_model(ecfg, scfg, sd).double().train()
+    with torch.no_grad():
+        want = ref.sequence_encoder.get_embeddings(onehots.double(), lengths)
+    got, stats = proteinfer_embeddings_train(sd, onehots, lengths, ecfg)
+    assert (got - want).abs().max() < 1e-10
+    bufs = dict(ref.named_buffers())
+    assert len(stats) == 4 * ecfg.num_resnet_blocks
+    for k, v in stats.items():
+        assert (bufs[k] - v).abs().max() < 1e-10, k
