@@ -29,6 +29,12 @@ long long g_chunk_rows = 0;      // 0 = auto
 int g_fuse_features = 0;
 // 1: run the engine as CTA pairs (tcgen05 cta_group::2, 256-row tiles, each CTA loads half of the weight tile)
 int g_cta2 = 0;
+// 1: strict-mode encoder convolutions keep the hi*hi products and the lo corrections in separate TMEM buffers
+// (GemmParams::split_corr); the main chain then needs a promotion only every 64 K-elements and its drain is hidden
+// behind the correction MMAs.  Measured on B200 (profiles/r01_split_corr_probe.txt): encoder 10 % faster (tensor pipe
+// 50 % -> 57 % on the dilated conv), but the end-to-end logit error grows from 5.1e-5 to 7.2e-5 on base_small (bar:
+// 1e-4).  The parity margin is worth more than 0.75 % of the headline step: off by default.
+int g_split_corr = 0;
 // strict mode: K elements accumulated in TMEM between fp32 promotions, per stage of the path
 enum { kStageEncoder = 0, kStageHeads = 1, kStageScorer = 2, kStageOther = 3 };
 int g_promote_k[4] = {32, 32, 256, 64};
@@ -287,6 +293,13 @@ int launch_gemm(const Planes& A, const ConvView& cv, const Planes& B, long long 
   const int promote_k = promote_override >= 0 ? promote_override : g_promote_k[stage_kind];
   if ((mode == PN_STRICT || promote_override > 0) && promote_k > 0) {
     p.chunk_kblocks = promote_k / bk > 0 ? promote_k / bk : 1;
+    if (p.chunk_kblocks > p.num_kblocks) p.chunk_kblocks = p.num_kblocks;
+  }
+  if (g_split_corr && mode == PN_STRICT && stage_kind == kStageEncoder && !gen && !cta2 && bk == 32 && promote_override < 0) {
+    // main chain: 2 truncating adds per k-block instead of 6 -> twice the K per promotion at fewer adds per chunk (4 vs 6)
+    p.split_corr = 1;
+    p.chunk_kblocks = 2 * promote_k / bk > 0 ? 2 * promote_k / bk : 1;
+    if (p.chunk_kblocks > 3) p.chunk_kblocks = 3;      // the chunk's operand stages stay resident: < pipeline depth (4)
     if (p.chunk_kblocks > p.num_kblocks) p.chunk_kblocks = p.num_kblocks;
   }
   if (B.kblocked) {
@@ -744,6 +757,10 @@ int pn_set_option(const char* name, long long value) {
   }
   if (strcmp(name, "cta2") == 0) {
     g_cta2 = value != 0;
+    return 0;
+  }
+  if (strcmp(name, "split_corr") == 0) {
+    g_split_corr = value != 0;
     return 0;
   }
   if (strcmp(name, "fuse_features") == 0) {

@@ -63,6 +63,12 @@ struct alignas(64) GemmParams {
   // K-blocked operands (wgrad): the operand is stored as [K/64][rows][64] so that the 128-byte row pieces of one k-block
   // are contiguous; its tensor map is 3-D (k within block, row, block) and the K coordinate is split accordingly
   int a_kblk, b_kblk;
+  // strict mode, split accumulators: the large hi*hi products of a chunk go to TMEM buffer 0 and are promoted to fp32
+  // registers chunk by chunk, the small lo*hi + hi*lo corrections of the WHOLE tile accumulate in TMEM buffer 1 (their
+  // truncation error is 2^-11 of the main term's) and are added once at the end of the tile.  The promotion of buffer 0
+  // overlaps the correction MMAs of the same chunk, so the tensor core never waits for a drain.  Needs
+  // chunk_kblocks < pipeline stages (the chunk's operand stages stay resident until its corrections are issued).
+  int split_corr;
   const long long* lengths;      // [B] valid positions per sequence (conv) or nullptr
   // pair-row addressing for the additive row terms: row r -> (r / pair_nl, r % pair_nl)
   int pair_nl;
@@ -425,6 +431,67 @@ __global__ void __launch_bounds__(GEN ? kGenThreads : kGemmThreads, 1) gemm_kern
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      if (NPASS == 3 && p.split_corr) {
+        // ---- split accumulators: buffer 0 = hi*hi of the current chunk, buffer 1 = corrections of the whole tile
+        uint32_t n_main = 0, n_corr = 0;   // uses of each buffer so far (mbarrier parities)
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+          const int m_tile = tile / p.tiles_n;
+          if (tile_is_padding(m_tile)) continue;
+          const uint32_t d_main = tmem_base, d_corr = tmem_base + kMaxBN;
+          mbar_wait(tempty_bar(1), (n_corr & 1u) ^ 1u);   // the previous tile's corrections have been read
+          tc_fence_after();
+          bool first_corr = true;
+          int kb = 0;
+          for (int chunk = 0; chunk < num_chunks; ++chunk) {
+            const int kb_end = min(kb + p.chunk_kblocks, p.num_kblocks);
+            mbar_wait(tempty_bar(0), (n_main & 1u) ^ 1u);   // the previous chunk has been promoted
+            tc_fence_after();
+            int st = stage;
+            uint32_t ph = phase;
+            bool first = true;
+            for (int k2 = kb; k2 < kb_end; ++k2) {            // phase 1: the large products
+              mbar_wait(full_bar(st), ph);
+              tc_fence_after();
+              const uint32_t sa = smem_base + st * Cfg::kStageBytes;
+              const uint32_t sb = sa + Cfg::kPlanes * Cfg::kATile;
+#pragma unroll
+              for (int ks = 0; ks < BK / 16; ++ks) {
+                umma_f16(d_main, make_kmajor_desc<Cfg::kSwizzle>(sa + ks * 32), make_kmajor_desc<Cfg::kSwizzle>(sb + ks * 32),
+                         idesc, first ? 0u : 1u);
+                first = false;
+              }
+              if (++st == Cfg::kStages) {
+                st = 0;
+                ph ^= 1;
+              }
+            }
+            umma_commit(tfull_bar(0));                        // epilogue warps promote buffer 0 ...
+            ++n_main;
+            for (int k2 = kb; k2 < kb_end; ++k2) {            // ... while phase 2 issues the chunk's corrections
+              const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+              const uint32_t sb = sa + Cfg::kPlanes * Cfg::kATile;
+#pragma unroll
+              for (int ks = 0; ks < BK / 16; ++ks) {
+                const uint64_t a_hi = make_kmajor_desc<Cfg::kSwizzle>(sa + ks * 32);
+                const uint64_t b_hi = make_kmajor_desc<Cfg::kSwizzle>(sb + ks * 32);
+                const uint64_t a_lo = make_kmajor_desc<Cfg::kSwizzle>(sa + Cfg::kATile + ks * 32);
+                const uint64_t b_lo = make_kmajor_desc<Cfg::kSwizzle>(sb + Cfg::kBTile + ks * 32);
+                umma_f16(d_corr, a_lo, b_hi, idesc, first_corr ? 0u : 1u);
+                umma_f16(d_corr, a_hi, b_lo, idesc, 1);
+                first_corr = false;
+              }
+              umma_commit(empty_bar(stage));                  // frees the smem slot once every MMA that reads it is done
+              if (++stage == Cfg::kStages) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
+            kb = kb_end;
+          }
+          umma_commit(tfull_bar(1));                          // corrections of the tile complete
+          ++n_corr;
+        }
+      } else {
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int m_tile = tile / p.tiles_n;
         if (tile_is_padding(m_tile)) continue;
@@ -473,6 +540,7 @@ __global__ void __launch_bounds__(GEN ? kGenThreads : kGemmThreads, 1) gemm_kern
             acc_phase ^= 1;
           }
         }
+      }
       }
     }
   } else if (GEN && warp >= 12) {
@@ -558,6 +626,7 @@ __global__ void __launch_bounds__(GEN ? kGenThreads : kGemmThreads, 1) gemm_kern
     const int r_in_tile = q * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
+    uint32_t n_main = 0, n_corr = 0;   // split_corr: uses of TMEM buffer 0 / 1 so far (mbarrier parities)
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m_tile = tile / p.tiles_n, n_tile = tile % p.tiles_n;
       const bool padding_tile = tile_is_padding(m_tile);
@@ -602,14 +671,36 @@ __global__ void __launch_bounds__(GEN ? kGenThreads : kGemmThreads, 1) gemm_kern
       for (int g = 0; g < 4; ++g)
 #pragma unroll
         for (int j = 0; j < 32; ++j) sums[g][j] = 0.f;
+      // Every drain adds one TMEM buffer into the fp32 register sums: this warp's (up to four) 32-column groups two at a
+      // time; the buffer is handed back to the MMA issuer as soon as the last load has landed in registers, BEFORE the
+      // additions, so the round trip commit -> drain -> release that bounds short chunks stays as short as possible.
+      // split_corr: num_chunks drains of buffer 0 (the hi*hi products of each chunk), then one of buffer 1 (the tile's
+      // corrections); otherwise the chunks alternate between the two buffers.
       if (!padding_tile) {
-        for (int chunk = 0; chunk < num_chunks; ++chunk) {
-          mbar_wait(tfull_bar(acc), acc_phase);
+        const bool split = NPASS == 3 && p.split_corr;
+        const int n_drains = split ? num_chunks + 1 : num_chunks;
+        for (int d = 0; d < n_drains; ++d) {
+          int buf;
+          uint32_t parity;
+          if (split) {
+            if (d < num_chunks) {
+              buf = 0;
+              parity = (n_main++) & 1u;
+            } else {
+              buf = 1;
+              parity = (n_corr++) & 1u;
+            }
+          } else {
+            buf = acc;
+            parity = acc_phase;
+            if (++acc == 2) {
+              acc = 0;
+              acc_phase ^= 1;
+            }
+          }
+          mbar_wait(tfull_bar(buf), parity);
           tc_fence_after();
-          // Drain this warp's (up to four) 32-column groups two at a time; the TMEM buffer is handed back to the MMA
-          // issuer as soon as the last load has landed in registers, BEFORE the additions, so the round trip
-          // commit -> drain -> release that bounds short chunks stays as short as possible.
-          const uint32_t t_addr = tmem_base + acc * kMaxBN + g_lo * 32 + ((uint32_t)(q * 32) << 16);
+          const uint32_t t_addr = tmem_base + buf * kMaxBN + g_lo * 32 + ((uint32_t)(q * 32) << 16);
           const int ng = g_hi - g_lo;   // warp-uniform
           uint32_t v0[32], v1[32];
           if (ng > 0) tmem_ld32(t_addr, v0);
@@ -618,7 +709,7 @@ __global__ void __launch_bounds__(GEN ? kGenThreads : kGemmThreads, 1) gemm_kern
           if (ng <= 2) {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (lane == 0) mbar_arrive(tempty_bar(buf));
           }
           if (ng > 0) {
 #pragma unroll
@@ -634,17 +725,13 @@ __global__ void __launch_bounds__(GEN ? kGenThreads : kGemmThreads, 1) gemm_kern
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (lane == 0) mbar_arrive(tempty_bar(buf));
 #pragma unroll
             for (int j = 0; j < 32; ++j) sums[2][j] += __uint_as_float(v0[j]);
             if (ng > 3) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) sums[3][j] += __uint_as_float(v1[j]);
             }
-          }
-          if (++acc == 2) {
-            acc = 0;
-            acc_phase ^= 1;
           }
         }
       }

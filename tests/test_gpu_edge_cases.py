@@ -203,3 +203,18 @@ def test_cta_pair_kernels_match_single_cta_kernels():
             native.set_option("cta2", 0)
         assert torch.equal(pair, base)
         assert (pair - g["logits"]).abs().max().item() <= TOL
+
+
+def test_split_accumulator_encoder_option_stays_within_tolerance():
+    """Option split_corr=1: strict-mode encoder convolutions keep the hi*hi products and the lo corrections in separate
+    TMEM buffers (faster, slightly less accurate; off by default)."""
+    from protnote_b200 import native
+    for case in ("tiny_long", "base_small"):
+        ecfg, scfg, sd, onehots, lengths, labels, g = load_case(case)
+        model = build_b200_model(ecfg, scfg, sd)
+        native.set_option("split_corr", 1)
+        try:
+            got = run(model, onehots, lengths, labels)
+        finally:
+            native.set_option("split_corr", 0)
+        assert (got - g["logits"]).abs().max().item() <= TOL
