@@ -275,7 +275,8 @@ typedef struct pn_bwd_src {
 } pn_bwd_src;
 /* sums[0][c] = sum_r g_y, sums[1][c] = sum_r g_y * xhat  with g_y = g * [z*scale+shift > 0], xhat = (z - mean) * invstd
  * (true scale, fp64 [2][cols], overwritten) = the gradients of BatchNorm's beta and gamma over these rows;
- * maxes[2] = max|g_y|, max|xhat|; kind 1 only: dw[c] = sum_r g_logit[r] * relu(z*scale+shift)[r][c], db = sum_r g_logit[r]
+ * maxes[2] = max|g| (before the mask: a bound of max|g_y|), max|z| (pn_t_bwd_scale turns it into a bound of max|xhat|),
+ * both read off the hi planes; kind 1 only: dw[c] = sum_r g_logit[r] * relu(z*scale+shift)[r][c], db = sum_r g_logit[r]
  * (gradients of the final Linear). */
 int pn_t_bwd_stats(const pn_bwd_src* src, double* sums, float* maxes, double* dw, double* db, void* stream);
 /* means[2][cols] (fp32) = sums / count, the two per-column means pass 2 subtracts; sc_out (nullable) = power-of-two scale

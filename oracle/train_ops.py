@@ -57,7 +57,7 @@ class TPair:
 @dataclass
 class TBwdStats:
     sums: torch.Tensor           # float64 [2, cols]: sum g_y, sum g_y * xhat   (true scale)
-    maxes: torch.Tensor          # [2]: max |g_y|, max |xhat|
+    maxes: torch.Tensor          # [2]: max |g| (bounds |g_y|), max |z| (bounds |xhat| through invstd and mean)
     local: Optional[torch.Tensor] = None
     dw: Optional[torch.Tensor] = None
     db: Optional[torch.Tensor] = None
@@ -169,8 +169,9 @@ class TorchOps:
         pre = Z * st.scale + st.shift
         gy = G * (pre > 0)
         xh = (Z - st.mean) * st.invstd
+        # maxes: max |g| before the mask (a bound of max |g_y|) and max |z| (bwd_scale bounds |xhat| with it)
         s = TBwdStats(torch.stack([gy.double().sum(0), (gy * xh).double().sum(0)]),
-                      torch.stack([gy.abs().max(), xh.abs().max()]))
+                      torch.stack([G.abs().max(), Z.abs().max()]))
         s.local = s.sums.clone()
         if isinstance(g, TOuter):
             s.dw = (g.g_logit[:, None] * torch.relu(pre)).double().sum(0)
@@ -193,8 +194,9 @@ class TorchOps:
 
     def bwd_apply(self, g, z, st: TBN, s: TBwdStats, count, want_T=False):
         gz = self._gz(g, z, st, s, float(count))
+        xmax = float(st.invstd.abs().max()) * (float(s.maxes[1]) + float(st.mean.abs().max()))
         bound = float(st.scale.abs().max()) * (float(s.maxes[0]) + float(s.sums[0].abs().max()) / count
-                                               + float(s.maxes[1]) * float(s.sums[1].abs().max()) / count)
+                                               + xmax * float(s.sums[1].abs().max()) / count)
         sc = pow2_scale(bound)
         return TAct(gz * sc, sc, want_T)
 

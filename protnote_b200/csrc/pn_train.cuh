@@ -553,6 +553,19 @@ __global__ void __launch_bounds__(256) bn_relu_dot_kernel(const __half* __restri
 // A thread walks its rows two at a time (both rows' loads in flight), keeps fp32 partial sums over 16 rows and flushes
 // them into fp64 accumulators in shared memory, so few registers are live and many blocks fit an SM.
 // ------------------------------------------------------------------------------------------------
+// max |x| over the 8 halves of a raw 16-byte piece, as packed half2 operations (1 instruction per 2 elements)
+__device__ __forceinline__ void absmax_raw(const uint4& h, __half2& m) {
+  const __half2* h2 = reinterpret_cast<const __half2*>(&h);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) m = __hmax2(m, __habs2(h2[j]));
+}
+
+// The pass is bound by instruction issue, not by HBM (about 25 instructions per element in its first version), so the
+// inner loop does the minimum per element: mask, sum g, sum g*z.  Everything that is per column or per tensor is
+// applied once at the end:  s1 = inv_gsc * S_g,  s2 = inv_gsc * invstd * (S_gz - mean * S_g)  (fp64), and the two
+// magnitudes the scale bound needs come from packed-half maxima of the raw planes:
+//   maxes[0] = max |g| (before the ReLU mask, a bound of max |g_y|),  maxes[1] = max |z| (bwd_scale turns it into a
+//   bound of max |xhat|).
 template <int KIND, bool LO>
 __global__ void __launch_bounds__(256) bwd_stats_kernel(const BwdSrc s, long long per_slab, double* __restrict__ sums,
                                                         unsigned* __restrict__ maxes, double* __restrict__ dw,
@@ -578,9 +591,9 @@ __global__ void __launch_bounds__(256) bwd_stats_kernel(const BwdSrc s, long lon
   zero8(p1);
   zero8(p2);
   zero8(p3);
-  float gmax = 0.f, xmax = 0.f;
+  __half2 gm2 = __float2half2_rn(0.f), zm2 = __float2half2_rn(0.f);
+  float glmax = 0.f, zmaxf = 0.f;
   double dbs = 0.0;
-  const float inv_gsc = s.g_sc ? 1.f / __ldg(s.g_sc) : 1.f;
   auto flush = [&]() {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -590,12 +603,20 @@ __global__ void __launch_bounds__(256) bwd_stats_kernel(const BwdSrc s, long lon
       p1[j] = p2[j] = p3[j] = 0.f;
     }
   };
+  float wmax = 0.f;
+  const bool full_chunk = c0 + 8 <= s.cols;
   if (c0 < s.cols && i_begin + ty < i_end) {
-    BnVec b;
-    load_bn(s.state, s.cols, c0, b);
-    float wv[8];
-    if (KIND == 1) load8_f32(s.w + c0, s.cols - c0, wv);
-    else zero8(wv);
+    float sc[8], sf[8], wv[8];
+    load8_f32(s.state + c0, s.cols - c0, sc);
+    load8_f32(s.state + s.cols + c0, s.cols - c0, sf);
+    if (KIND == 1) {
+      load8_f32(s.w + c0, s.cols - c0, wv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) wmax = fmaxf(wmax, fabsf(wv[j]));
+    } else {
+      zero8(wv);
+    }
+    // columns beyond `cols` (only in the last chunk of a row): scale = shift = 0 -> mask false -> no contribution
     // software pipeline over (protein, row) steps of kRif rows: the next step's loads are issued before this step's math
     long long bb = 0, i = i_begin + ty;
     BwdRaw cur[kRif], nxt[kRif];
@@ -619,17 +640,50 @@ __global__ void __launch_bounds__(256) bwd_stats_kernel(const BwdSrc s, long lon
 #pragma unroll
       for (int k = 0; k < kRif; ++k) {
         if (i + 8 * k >= i_end) continue;
-        float gy[8], xh[8], pre[8];
-        bwd_eval<KIND, LO>(s, cur[k], bb * extent + i + 8 * k, c0, b, wv, inv_gsc, gy, xh, pre);
+        float g[8], z[8];
+        if (KIND == 1) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) g[j] = cur[k].gl * wv[j];
+          glmax = fmaxf(glmax, fabsf(cur[k].gl));
+          if (blockIdx.x == 0 && tx == 0) dbs += (double)cur[k].gl;
+        } else {
+          raw_to_f32<LO>(cur[k].g, g);
+          if (full_chunk) {
+            absmax_raw(cur[k].g.h, gm2);
+          } else {       // the columns beyond `cols` of a partial chunk hold whatever the allocation held
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (c0 + j < s.cols) glmax = fmaxf(glmax, fabsf(g[j]));
+          }
+        }
+        if (KIND == 2) {
+          const long long r = bb * extent + i + 8 * k;
+          float av[8], cv[8];
+          load8_f32(s.a + (r / s.L) * s.cols + c0, s.cols - c0, av);
+          load8_f32(s.c + (r % s.L) * s.cols + c0, s.cols - c0, cv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            z[j] = av[j] + cv[j];
+            zmaxf = fmaxf(zmaxf, fabsf(z[j]));
+          }
+        } else {
+          raw_to_f32<LO>(cur[k].z, z);
+          if (full_chunk) {
+            absmax_raw(cur[k].z.h, zm2);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (c0 + j < s.cols) zmaxf = fmaxf(zmaxf, fabsf(z[j]));
+          }
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          p1[j] += gy[j];
-          p2[j] = fmaf(gy[j], xh[j], p2[j]);
-          if (KIND == 1) p3[j] = fmaf(cur[k].gl, fmaxf(pre[j], 0.f), p3[j]);
-          gmax = fmaxf(gmax, fabsf(gy[j]));
-          xmax = fmaxf(xmax, fabsf(xh[j]));
+          const float pre = fmaf(z[j], sc[j], sf[j]);
+          const float gmk = pre > 0.f ? g[j] : 0.f;
+          p1[j] += gmk;
+          p2[j] = fmaf(gmk, z[j], p2[j]);
+          if (KIND == 1) p3[j] = fmaf(cur[k].gl, fmaxf(pre, 0.f), p3[j]);
         }
-        if (KIND == 1 && blockIdx.x == 0 && tx == 0) dbs += (double)cur[k].gl;
       }
       if ((++it & 7) == 0) flush();   // fp32 partial sums cover at most 8 * kRif rows
 #pragma unroll
@@ -641,6 +695,7 @@ __global__ void __launch_bounds__(256) bwd_stats_kernel(const BwdSrc s, long lon
     flush();
   }
   __syncthreads();
+  const float inv_gsc = (KIND != 1 && s.g_sc) ? 1.f / __ldg(s.g_sc) : 1.f;
   const int i = ty * 32 + tx;
   const int c = blockIdx.x * 256 + i;
   if (c < s.cols) {
@@ -651,18 +706,23 @@ __global__ void __launch_bounds__(256) bwd_stats_kernel(const BwdSrc s, long lon
       t1 += sh[1][y][i];
       if (KIND == 1) t2 += sh[KIND == 1 ? 2 : 0][y][i];
     }
-    atomicAdd(sums + c, t0);
-    atomicAdd(sums + s.cols + c, t1);
+    const double mean = (double)s.state[2 * (long long)s.cols + c], invstd = (double)s.state[3 * (long long)s.cols + c];
+    atomicAdd(sums + c, t0 * (double)inv_gsc);
+    atomicAdd(sums + s.cols + c, (t1 - mean * t0) * invstd * (double)inv_gsc);
     if (KIND == 1 && dw) atomicAdd(dw + c, t2);
   }
+  float gmax, zmax;
+  if (KIND == 1) gmax = glmax * wmax;
+  else gmax = fmaxf(glmax, fmaxf(__low2float(gm2), __high2float(gm2))) * inv_gsc;
+  zmax = fmaxf(zmaxf, fmaxf(__low2float(zm2), __high2float(zm2)));
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
-    xmax = fmaxf(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+    zmax = fmaxf(zmax, __shfl_xor_sync(0xffffffffu, zmax, o));
   }
   if (tx == 0) {
     atomicMax(maxes, __float_as_uint(gmax));
-    atomicMax(maxes + 1, __float_as_uint(xmax));
+    atomicMax(maxes + 1, __float_as_uint(zmax));
     if (KIND == 1 && blockIdx.x == 0 && db) atomicAdd(db, dbs);
   }
 }
@@ -678,12 +738,12 @@ __device__ __forceinline__ float grad_scale_from_bound(float bound) {
 
 // means[0][c] = sums[0][c] / n, means[1][c] = sums[1][c] / n (fp32, what pass 2 subtracts) and, when sc_out is given,
 // the scale for the g_z tensor pass 2 writes, from an upper bound of |g_z|:
-//   max|scale| * (max|g_y| + max|s1|/n + max|xhat| * max|s2|/n)
+//   max|scale| * (max|g| + max|s1|/n + bound(|xhat|) * max|s2|/n)
 __global__ void bwd_scale_kernel(const double* __restrict__ sums, const unsigned* __restrict__ maxes,
                                  const float* __restrict__ state, double count, int cols, float* __restrict__ sc_out,
                                  float* __restrict__ means) {
-  __shared__ float red[3][32];
-  float ms = 0.f, m1 = 0.f, m2 = 0.f;
+  __shared__ float red[5][32];
+  float ms = 0.f, m1 = 0.f, m2 = 0.f, mi = 0.f, mm = 0.f;
   for (int c = threadIdx.x; c < cols; c += blockDim.x) {
     const float a1 = (float)(sums[c] / count), a2 = (float)(sums[cols + c] / count);
     means[c] = a1;
@@ -691,17 +751,23 @@ __global__ void bwd_scale_kernel(const double* __restrict__ sums, const unsigned
     ms = fmaxf(ms, fabsf(state[c]));
     m1 = fmaxf(m1, fabsf(a1));
     m2 = fmaxf(m2, fabsf(a2));
+    mm = fmaxf(mm, fabsf(state[2 * (long long)cols + c]));
+    mi = fmaxf(mi, fabsf(state[3 * (long long)cols + c]));
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     ms = fmaxf(ms, __shfl_xor_sync(0xffffffffu, ms, o));
     m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, o));
     m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, o));
+    mi = fmaxf(mi, __shfl_xor_sync(0xffffffffu, mi, o));
+    mm = fmaxf(mm, __shfl_xor_sync(0xffffffffu, mm, o));
   }
   if ((threadIdx.x & 31) == 0) {
     red[0][threadIdx.x >> 5] = ms;
     red[1][threadIdx.x >> 5] = m1;
     red[2][threadIdx.x >> 5] = m2;
+    red[3][threadIdx.x >> 5] = mi;
+    red[4][threadIdx.x >> 5] = mm;
   }
   __syncthreads();
   if (threadIdx.x == 0 && sc_out) {
@@ -709,8 +775,11 @@ __global__ void bwd_scale_kernel(const double* __restrict__ sums, const unsigned
       ms = fmaxf(ms, red[0][w]);
       m1 = fmaxf(m1, red[1][w]);
       m2 = fmaxf(m2, red[2][w]);
+      mi = fmaxf(mi, red[3][w]);
+      mm = fmaxf(mm, red[4][w]);
     }
-    const float gmax = __uint_as_float(maxes[0]), xmax = __uint_as_float(maxes[1]);
+    // maxes[0] = max |g| (bounds |g_y|), maxes[1] = max |z|  ->  |xhat| <= max invstd * (max |z| + max |mean|)
+    const float gmax = __uint_as_float(maxes[0]), xmax = mi * (__uint_as_float(maxes[1]) + mm);
     *sc_out = grad_scale_from_bound(ms * (gmax + m1 + xmax * m2));
   }
 }

@@ -178,13 +178,13 @@ def test_bn_backward_primitives(kind):
     s = nat.bwd_stats(ga, z, state)
     s_r = ref.bwd_stats(gr, zr, sr)
     assert _rel(s.sums.cpu(), s_r.sums) < 1e-5
-    assert _rel(s.maxes.cpu().double(), s_r.maxes) < 1e-5
+    assert _rel(s.maxes.cpu().double(), s_r.maxes) < 2e-3       # read off the fp16 hi planes
     if kind == "outer":
         assert _rel(s.dw.cpu(), s_r.dw) < 1e-5
         assert _rel(s.db.cpu(), s_r.db) < 1e-6
     gz = nat.bwd_apply(ga, z, state, s, rows, want_T=True)
     gzr = ref.bwd_apply(gr, zr, sr, s_r, rows)
-    assert 16 <= float(_val(gz).abs().max()) * float(gz.sc[0]) < 64
+    assert 0.5 <= float(_val(gz).abs().max()) * float(gz.sc[0]) < 64      # scaled by a power of two from a BOUND of max|g_z|
     assert _rel(_val(gz), gzr.val / gzr.sc) < 1e-5
     assert torch.equal(_val(gz), _valT(gz))
 
