@@ -158,7 +158,10 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "inference 4096 x 1024 aa x 32768 label rows, fp32 (bounded CPU sample per step)"},
+            "config": {"workload": f"inference {B_TOTAL} x {T_LEN} aa x {L_ROWS} label rows, fp32 in/out (BASELINE.json configs[1])",
+                       "mode": "reference arithmetic, fp32, CPU", "sequences": B_TOTAL, "seq_len": T_LEN, "label_rows": L_ROWS,
+                       "descriptions_per_label": 1, "parallelism": "host cores of rank 0",
+                       "sample": "each step is a bounded sample of the workload: " + sample},
             "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
