@@ -41,7 +41,7 @@ int pn_device_check(int device);
 /* Engine knobs: "bk" = 32 | 64 (k-block / swizzle width, 0 = auto); "promote_k_encoder" | "promote_k_heads" |
  * "promote_k_scorer" | "promote_k" (all): strict mode, K elements summed in TMEM between fp32 promotions
  * (0 = never); "chunk_rows" (pairs per scorer chunk, 0 = auto); "cta2" (1: CTA-pair kernels, tcgen05 cta_group::2,
- * 256-row tiles; 0: single-CTA kernels); "split_corr" (1: strict-mode encoder convolutions accumulate the hi*hi
+ * 256-row tiles; 0: single-CTA kernels; -1, the default: pairs in PN_FAST mode only, where they are faster); "split_corr" (1: strict-mode encoder convolutions accumulate the hi*hi
  * products and the lo corrections in separate TMEM buffers, 10 % faster encoder at a smaller parity margin; 0, the
  * default: one accumulator, promotion every 32 K); "fuse_features" (1: layer 1 of the pair scorer is built
  * inside the first GEMM's operand producer; 0, the default: separate kernel with an HBM round trip - faster today). */

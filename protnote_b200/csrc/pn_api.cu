@@ -27,8 +27,11 @@ long long g_chunk_rows = 0;      // 0 = auto
 // the generator's extra shared-memory traffic (+32 KB per k-block on top of ~120 KB) competes with the tensor core's
 // operand reads; it needs the 2-CTA operand sharing planned for the next round to pay off.  Off by default.
 int g_fuse_features = 0;
-// 1: run the engine as CTA pairs (tcgen05 cta_group::2, 256-row tiles, each CTA loads half of the weight tile)
-int g_cta2 = 0;
+// run the engine as CTA pairs (tcgen05 cta_group::2, 256-row tiles, each CTA loads half of the weight tile):
+// 1 always, 0 never, -1 (default) in fast mode only.  Measured on B200 (profiles/r01_cta_pair_probe.txt): fast mode is
+// bound by the L2 -> SM operand traffic, which the pair halves for B: encoder +10 %, scorer GEMM +1.6 %; strict mode
+// (three MMAs per operand byte) is tensor-bound and 2 % slower as pairs.
+int g_cta2 = -1;
 // 1: strict-mode encoder convolutions keep the hi*hi products and the lo corrections in separate TMEM buffers
 // (GemmParams::split_corr); the main chain then needs a promotion only every 64 K-elements and its drain is hidden
 // behind the correction MMAs.  Measured on B200 (profiles/r01_split_corr_probe.txt): encoder 10 % faster (tensor pipe
@@ -235,10 +238,10 @@ int launch_gemm2_t(const GemmParams& p, cudaStream_t stream) {
 
 // D = A * B^T with the fused epilogue.  A: plain [M][K] or conv view; B: packed weights [N][K_total].
 int launch_gemm(const Planes& A, const ConvView& cv, const Planes& B, long long N, const Epilogue& e, int mode,
-                cudaStream_t stream, int stage_kind = kStageOther, int promote_override = -1) {
+                cudaStream_t stream, int stage_kind = kStageOther, int promote_override = -1, bool allow_pairs = true) {
   if (mode != PN_STRICT && mode != PN_FAST) return fail("mode must be PN_STRICT or PN_FAST");
   const bool gen = e.gen_a != nullptr;
-  const bool cta2 = g_cta2 && !gen && !A.kblocked && !B.kblocked;
+  const bool cta2 = (g_cta2 == 1 || (g_cta2 < 0 && mode == PN_FAST && allow_pairs)) && !gen && !A.kblocked && !B.kblocked;
   const int tile_rows = cta2 ? 2 * kBM : kBM;
   const int bk = gen ? 32 : pick_bk(mode);
   GemmParams p;
@@ -759,7 +762,7 @@ int pn_set_option(const char* name, long long value) {
     return 0;
   }
   if (strcmp(name, "cta2") == 0) {
-    g_cta2 = value != 0;
+    g_cta2 = value < 0 ? -1 : (value != 0);
     return 0;
   }
   if (strcmp(name, "split_corr") == 0) {
@@ -1536,8 +1539,9 @@ int pn_t_gemm(const void* a_hi, const void* a_lo, long long M, long long K, long
   if (out_hi) {
     e.out_hi = static_cast<__half*>(out_hi); e.out_lo = static_cast<__half*>(out_lo); e.ld_split = ld_split;
   }
+  // (the training GEMMs measured 4 % slower as CTA pairs in fast mode: single-CTA kernels unless cta2 == 1 is forced)
   if (split_k == 0 || K <= split_k)
-    return launch_gemm(A, ConvView(), B, N, e, mode, stream, kStageHeads, promote_k > 0 ? promote_k : -1);
+    return launch_gemm(A, ConvView(), B, N, e, mode, stream, kStageHeads, promote_k > 0 ? promote_k : -1, false);
   // K in slices, one launch each, accumulating in the fp32 output: CTAs of one launch stay within `split_k` of each other
   // along K, so the operand panels they share are still in L2 when the next CTA asks for them (a single launch over
   // K = millions of rows lets the CTAs drift apart and re-reads the panels from HBM ~8x, measured).
@@ -1551,7 +1555,7 @@ int pn_t_gemm(const void* a_hi, const void* a_lo, long long M, long long K, long
     if (Bs.lo) Bs.lo += ob;
     As.cols = kk; Bs.cols = kk;
     if (k0 > 0) { e.resid = out_f32; e.ld_resid = ld_out; }
-    PN_TRY(launch_gemm(As, ConvView(), Bs, N, e, mode, stream, kStageHeads, promote_k > 0 ? promote_k : -1));
+    PN_TRY(launch_gemm(As, ConvView(), Bs, N, e, mode, stream, kStageHeads, promote_k > 0 ? promote_k : -1, false));
   }
   return 0;
 }

@@ -194,14 +194,23 @@ def test_cta_pair_kernels_match_single_cta_kernels():
     for case in ("tiny_long", "base_small"):
         ecfg, scfg, sd, onehots, lengths, labels, g = load_case(case)
         model = build_b200_model(ecfg, scfg, sd)
-        base = run(model, onehots, lengths, labels)
-        native.set_option("cta2", 1)
+        native.set_option("cta2", 0)
         try:
+            base = run(model, onehots, lengths, labels)
+            native.set_option("cta2", 1)
             model._label_cache = None
             pair = run(model, onehots, lengths, labels)
-        finally:
+            # fast mode (where pairs are the default): same arithmetic per output element as well
+            model.precision = model.sequence_encoder.precision = "fast"
+            model._label_cache = None
+            pair_fast = run(model, onehots, lengths, labels)
             native.set_option("cta2", 0)
+            model._label_cache = None
+            base_fast = run(model, onehots, lengths, labels)
+        finally:
+            native.set_option("cta2", -1)
         assert torch.equal(pair, base)
+        assert torch.equal(pair_fast, base_fast)
         assert (pair - g["logits"]).abs().max().item() <= TOL
 
 
