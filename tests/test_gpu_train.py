@@ -359,3 +359,45 @@ def test_whole_model_train_mode_with_onehot_input():
         e_logits, _ = model(sequence_onehots=onehots.cuda(), sequence_lengths=lengths.cuda(), label_embeddings=labels.cuda())
     want = protnote_forward(sd2, onehots, lengths, labels, ecfg, scfg, dtype=torch.float64)
     assert float((e_logits.cpu().double() - want).abs().max()) < 2e-4
+
+
+def test_training_under_autocast_and_gradscaler_like_the_trainer():
+    """ProtNoteTrainer.train_one_epoch: `with autocast(): logits = model(...); loss = ...`, `scaler.scale(loss).backward()`,
+    `scaler.unscale_`, clip, `scaler.step` (ProtNoteTrainer.py:728-755).  The loss scale (65536) must pass through the
+    power-of-two gradient scaling of the kernels unchanged; label noise (LABEL_EMBEDDING_NOISING_ALPHA) must be applied."""
+    ecfg, scfg, *_ = CASES["tiny_concat"]
+    sd = synth_state_dict(ecfg, scfg, seed=42, calib_T=64)
+    g = torch.Generator().manual_seed(31)
+    P_f, L_f = torch.randn(6, 72, generator=g).cuda(), torch.randn(50, 40, generator=g).cuda()
+    y = synth_targets(6, 50, 31).cuda()
+    grads = []
+    for use_scaler in (False, True):
+        model = build_b200_model(ecfg, scfg, sd, device="cuda").train()
+        params = [p for n, p in model.named_parameters() if not n.startswith("sequence_encoder.")]
+        opt = torch.optim.Adam(params, lr=1e-3)
+        if use_scaler:
+            scaler = torch.amp.GradScaler("cuda", init_scale=65536.0)
+            with torch.autocast("cuda"):
+                logits, _ = model(sequence_embeddings=P_f, label_embeddings=L_f)
+                loss = torch.nn.functional.binary_cross_entropy_with_logits(logits, y)
+            assert logits.dtype == torch.float32
+            scaler.scale(loss).backward()
+            scaler.unscale_(opt)
+            torch.nn.utils.clip_grad_norm_(params, max_norm=1.0)
+            scaler.step(opt)
+            scaler.update()
+            assert float(scaler.get_scale()) == 65536.0          # no inf / nan was produced
+        else:
+            logits, _ = model(sequence_embeddings=P_f, label_embeddings=L_f)
+            torch.nn.functional.binary_cross_entropy_with_logits(logits, y).backward()
+            torch.nn.utils.clip_grad_norm_(params, max_norm=1.0)
+        grads.append([p.grad.clone() for p in params])
+    for a, b in zip(*grads):
+        assert float((a - b).norm() / b.norm().clamp_min(1e-30)) < 1e-5
+    # label-embedding noise: only in training mode and only with token counts (ProtNote.py:219-240)
+    model = build_b200_model(ecfg, scfg, sd, device="cuda").train()
+    model.label_embedding_noising_alpha = 20.0
+    torch.manual_seed(0)
+    noisy, _ = model(sequence_embeddings=P_f, label_embeddings=L_f, label_token_counts=torch.ones(50, device="cuda"))
+    clean, _ = model(sequence_embeddings=P_f, label_embeddings=L_f)
+    assert float((noisy - clean).abs().max()) > 1e-3
