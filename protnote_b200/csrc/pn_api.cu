@@ -32,6 +32,8 @@ int g_fuse_features = 0;
 // bound by the L2 -> SM operand traffic, which the pair halves for B: encoder +10 %, scorer GEMM +1.6 %; strict mode
 // (three MMAs per operand byte) is tensor-bound and 2 % slower as pairs.
 int g_cta2 = -1;
+// threads along the columns of a reduction block (TX * TY == 256; TX * 8 consecutive columns per block row)
+int g_stats_tx = 32;
 // 1: strict-mode encoder convolutions keep the hi*hi products and the lo corrections in separate TMEM buffers
 // (GemmParams::split_corr); the main chain then needs a promotion only every 64 K-elements and its drain is hidden
 // behind the correction MMAs.  Measured on B200 (profiles/r01_split_corr_probe.txt): encoder 10 % faster (tensor pipe
@@ -763,6 +765,11 @@ int pn_set_option(const char* name, long long value) {
   }
   if (strcmp(name, "cta2") == 0) {
     g_cta2 = value < 0 ? -1 : (value != 0);
+    return 0;
+  }
+  if (strcmp(name, "stats_tx") == 0) {
+    if (value != 32 && value != 64 && value != 128 && value != 256) return fail("stats_tx must be 32, 64, 128 or 256");
+    g_stats_tx = (int)value;
     return 0;
   }
   if (strcmp(name, "split_corr") == 0) {
@@ -1566,10 +1573,10 @@ int pn_t_col_stats(const void* hi, const void* lo, const float* x, long long row
   if (rows <= 0 || cols <= 0) return fail("empty tensor");
   if (!x && (!hi || ld % 8 != 0)) return fail("column statistics: planes missing or pitch not a multiple of 8");
   PN_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * 2 * cols, stream));
-  const int col_blocks = (cols + 255) / 256;
+  const int col_blocks = (cols + g_stats_tx * 8 - 1) / (g_stats_tx * 8);
   const long long per = slab_rows(rows, col_blocks);
   const long long slabs = (rows + per - 1) / per;
-  col_stats_kernel<<<dim3(col_blocks, (unsigned)slabs), dim3(32, 8), 0, stream>>>(
+  col_stats_kernel<<<dim3(col_blocks, (unsigned)slabs), dim3(g_stats_tx, 256 / g_stats_tx), 0, stream>>>(
       static_cast<const __half*>(hi), static_cast<const __half*>(lo), x, rows, cols, ld, per, out);
   g_launches++;
   PN_CUDA(cudaGetLastError());
@@ -1625,7 +1632,7 @@ int pn_t_bwd_stats(const pn_bwd_src* src, double* sums, float* maxes, double* dw
     PN_CUDA(cudaMemsetAsync(dw, 0, sizeof(double) * s.cols, stream));
     PN_CUDA(cudaMemsetAsync(db, 0, sizeof(double), stream));
   }
-  const int col_blocks = (s.cols + 255) / 256;
+  const int col_blocks = (s.cols + g_stats_tx * 8 - 1) / (g_stats_tx * 8);
   // kind 2 walks a slab of LABELS for every protein (pn_train.cuh): 128 labels keep the slab's c rows cache-resident
   const long long extent = s.kind == 2 ? s.L : s.rows;
   long long per = s.kind == 2 ? 128 : slab_rows(s.rows, col_blocks);
@@ -1635,7 +1642,7 @@ int pn_t_bwd_stats(const pn_bwd_src* src, double* sums, float* maxes, double* dw
     per = (per + 31) / 32 * 32;
     slabs = (extent + per - 1) / per;
   }
-  const dim3 grid(col_blocks, (unsigned)slabs), block(32, 8);
+  const dim3 grid(col_blocks, (unsigned)slabs), block(g_stats_tx, 256 / g_stats_tx);
   unsigned* mx = reinterpret_cast<unsigned*>(maxes);
   const bool lo = src_has_lo(s);
   if (s.kind == 0 && lo) bwd_stats_kernel<0, true><<<grid, block, 0, stream>>>(s, per, sums, mx, dw, db);

@@ -211,7 +211,7 @@ struct BnReluMaskF32Producer {
 struct PairHiddenProducer {     // relu((a[b] + c[l]) * scale + shift), row r = b * L + l   (ProtNote.py:112-126 + layer 1)
   const float* a; const float* c; long long L; long long rows; int cols; const float* state;
   struct Ctx { float sc[8], sf[8]; };
-  struct Raw { float ca[8], cb[8]; };
+  struct Raw { float ca[8], cb[8]; int b0, b1; };      // label halves of the two rows + their protein indices
   __device__ __forceinline__ void init(int c0, Ctx& k) const {
     zero8(k.sc);
     zero8(k.sf);
@@ -222,23 +222,29 @@ struct PairHiddenProducer {     // relu((a[b] + c[l]) * scale + shift), row r = 
   }
   template <bool LO>
   __device__ __forceinline__ void load(long long r, int c0, Raw& q) const {
-    if (c0 >= cols) return;
-    if (r < rows) load8_f32(c + (r % L) * cols + c0, cols - c0, q.ca);
-    if (r + 1 < rows) load8_f32(c + ((r + 1) % L) * cols + c0, cols - c0, q.cb);
+    if (c0 >= cols || r >= rows) return;
+    const long long b0 = r / L;                  // one division per thread and tile; the second row follows from it
+    long long l0 = r - b0 * L, l1 = l0 + 1, b1 = b0;
+    if (l1 == L) {
+      l1 = 0;
+      ++b1;
+    }
+    q.b0 = (int)b0;
+    q.b1 = (int)b1;
+    load8_f32(c + l0 * cols + c0, cols - c0, q.ca);
+    if (r + 1 < rows) load8_f32(c + l1 * cols + c0, cols - c0, q.cb);
   }
   template <bool LO>
   __device__ __forceinline__ void eval(const Ctx& k, const Raw& q, long long r, int c0, float (&va)[8], float (&vb)[8]) const {
     zero8(va);
     zero8(vb);
-    if (c0 >= cols) return;
+    if (c0 >= cols || r >= rows) return;
     float av[8];
-    if (r < rows) {
-      load8_f32(a + (r / L) * cols + c0, cols - c0, av);     // 64 rows of a: L1 / L2 resident
+    load8_f32(a + (long long)q.b0 * cols + c0, cols - c0, av);     // B rows of a: L1 / L2 resident
 #pragma unroll
-      for (int j = 0; j < 8; ++j) va[j] = c0 + j < cols ? fmaxf(fmaf(av[j] + q.ca[j], k.sc[j], k.sf[j]), 0.f) : 0.f;
-    }
+    for (int j = 0; j < 8; ++j) va[j] = c0 + j < cols ? fmaxf(fmaf(av[j] + q.ca[j], k.sc[j], k.sf[j]), 0.f) : 0.f;
     if (r + 1 < rows) {
-      load8_f32(a + ((r + 1) / L) * cols + c0, cols - c0, av);
+      if (q.b1 != q.b0) load8_f32(a + (long long)q.b1 * cols + c0, cols - c0, av);
 #pragma unroll
       for (int j = 0; j < 8; ++j) vb[j] = c0 + j < cols ? fmaxf(fmaf(av[j] + q.cb[j], k.sc[j], k.sf[j]), 0.f) : 0.f;
     }
@@ -449,16 +455,20 @@ __global__ void __launch_bounds__(256) emit_tile_kernel(const P prod, long long 
 __global__ void __launch_bounds__(256) col_stats_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo,
                                                         const float* __restrict__ x, long long rows, int cols,
                                                         long long ld, long long rows_per_slab, double* __restrict__ out) {
-  __shared__ double sh[2][256];
-  const int tx = threadIdx.x, ty = threadIdx.y;
-  const int c0 = blockIdx.x * 256 + tx * 8;
+  // block (TX, TY), TX * TY == 256: TX threads cover TX * 8 consecutive columns of a row (the wider, the longer the
+  // contiguous run each row contributes to the DRAM stream), TY row phases
+  __shared__ double sh[2][2048];
+  const int tx = threadIdx.x, ty = threadIdx.y, TX = blockDim.x, TY = blockDim.y;
+  const int tid = ty * TX + tx;
+  const int cpb = TX * 8;
+  const int c0 = blockIdx.x * cpb + tx * 8;
   const long long r_begin = (long long)blockIdx.y * rows_per_slab;
   const long long r_end = r_begin + rows_per_slab < rows ? r_begin + rows_per_slab : rows;
   double s[8], ss[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.0;
   if (c0 < cols) {
-    for (long long r = r_begin + ty; r < r_end; r += 8) {
+    for (long long r = r_begin + ty; r < r_end; r += TY) {
       float v[8];
       if (x) load8_f32(x + r * ld + c0, cols - c0, v);
       else load8(hi + r * ld + c0, lo ? lo + r * ld + c0 : nullptr, v);
@@ -470,7 +480,7 @@ __global__ void __launch_bounds__(256) col_stats_kernel(const __half* __restrict
       }
     }
   }
-  for (int i = ty * 32 + tx; i < 512; i += 256) (&sh[0][0])[i] = 0.0;
+  for (int i = tid; i < 2 * 2048; i += 256) (&sh[0][0])[i] = 0.0;
   __syncthreads();
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -478,11 +488,12 @@ __global__ void __launch_bounds__(256) col_stats_kernel(const __half* __restrict
     atomicAdd(&sh[1][tx * 8 + j], ss[j]);
   }
   __syncthreads();
-  const int i = ty * 32 + tx;
-  const int c = blockIdx.x * 256 + i;
-  if (c < cols) {
-    atomicAdd(out + c, sh[0][i]);
-    atomicAdd(out + cols + c, sh[1][i]);
+  for (int i = tid; i < cpb; i += 256) {
+    const int c = blockIdx.x * cpb + i;
+    if (c < cols) {
+      atomicAdd(out + c, sh[0][i]);
+      atomicAdd(out + cols + c, sh[1][i]);
+    }
   }
 }
 
@@ -572,9 +583,14 @@ __global__ void __launch_bounds__(256) bwd_stats_kernel(const BwdSrc s, long lon
                                                         double* __restrict__ db) {
   // fp64 accumulators: one private slot per thread and column (no atomics while streaming), reduced over the 8 row
   // phases at the end.  [sum][ty][256 columns] doubles = 32 KB (48 KB for kind 1).
-  __shared__ double sh[KIND == 1 ? 3 : 2][8][256];
-  const int tx = threadIdx.x, ty = threadIdx.y;
-  const int c0 = blockIdx.x * 256 + tx * 8;
+  __shared__ double sh[KIND == 1 ? 3 : 2][2048];
+  // block (TX, TY), TX * TY == 256: TX threads cover TX * 8 consecutive columns of a row, TY row phases
+  const int tx = threadIdx.x, ty = threadIdx.y, TX = blockDim.x, TY = blockDim.y;
+  const int cpb = TX * 8;
+  // this thread's 8 private fp64 slots of every sum live at (ty * 8 + j) * TX + tx: consecutive lanes -> consecutive
+  // doubles (the first layout, 8 consecutive doubles per thread, was a 16-way bank conflict: 1.1e9 conflicts per launch)
+  const int slot0 = ty * 8 * TX + tx;
+  const int c0 = blockIdx.x * cpb + tx * 8;
   // kind 0/1: a slab is a range of rows.  kind 2 (rows = b * L + l): a slab is a range of LABELS walked for every
   // protein in turn, so the slab's rows of c (per_slab x 256 columns, fp32) are re-read from L1/L2, not from HBM.
   const long long n_outer = KIND == 2 ? s.rows / s.L : 1;
@@ -583,9 +599,9 @@ __global__ void __launch_bounds__(256) bwd_stats_kernel(const BwdSrc s, long lon
   const long long i_end = i_begin + per_slab < extent ? i_begin + per_slab : extent;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    sh[0][ty][tx * 8 + j] = 0.0;
-    sh[1][ty][tx * 8 + j] = 0.0;
-    if (KIND == 1) sh[KIND == 1 ? 2 : 0][ty][tx * 8 + j] = 0.0;
+    sh[0][slot0 + j * TX] = 0.0;
+    sh[1][slot0 + j * TX] = 0.0;
+    if (KIND == 1) sh[KIND == 1 ? 2 : 0][slot0 + j * TX] = 0.0;
   }
   float p1[8], p2[8], p3[8];
   zero8(p1);
@@ -597,9 +613,9 @@ __global__ void __launch_bounds__(256) bwd_stats_kernel(const BwdSrc s, long lon
   auto flush = [&]() {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      sh[0][ty][tx * 8 + j] += (double)p1[j];
-      sh[1][ty][tx * 8 + j] += (double)p2[j];
-      if (KIND == 1) sh[KIND == 1 ? 2 : 0][ty][tx * 8 + j] += (double)p3[j];
+      sh[0][slot0 + j * TX] += (double)p1[j];
+      sh[1][slot0 + j * TX] += (double)p2[j];
+      if (KIND == 1) sh[KIND == 1 ? 2 : 0][slot0 + j * TX] += (double)p3[j];
       p1[j] = p2[j] = p3[j] = 0.f;
     }
   };
@@ -622,11 +638,11 @@ __global__ void __launch_bounds__(256) bwd_stats_kernel(const BwdSrc s, long lon
     BwdRaw cur[kRif], nxt[kRif];
 #pragma unroll
     for (int k = 0; k < kRif; ++k)
-      if (i + 8 * k < i_end) bwd_raw_load<KIND, LO>(s, i + 8 * k, c0, cur[k]);
+      if (i + TY * k < i_end) bwd_raw_load<KIND, LO>(s, i + TY * k, c0, cur[k]);
     int it = 0;
     bool have = true;
     while (have) {
-      long long nbb = bb, ni = i + 8 * kRif;
+      long long nbb = bb, ni = i + TY * kRif;
       if (ni >= i_end) {
         ni = i_begin + ty;
         ++nbb;
@@ -635,11 +651,11 @@ __global__ void __launch_bounds__(256) bwd_stats_kernel(const BwdSrc s, long lon
       if (have_next) {
 #pragma unroll
         for (int k = 0; k < kRif; ++k)
-          if (ni + 8 * k < i_end) bwd_raw_load<KIND, LO>(s, nbb * extent + ni + 8 * k, c0, nxt[k]);
+          if (ni + TY * k < i_end) bwd_raw_load<KIND, LO>(s, nbb * extent + ni + TY * k, c0, nxt[k]);
       }
 #pragma unroll
       for (int k = 0; k < kRif; ++k) {
-        if (i + 8 * k >= i_end) continue;
+        if (i + TY * k >= i_end) continue;
         float g[8], z[8];
         if (KIND == 1) {
 #pragma unroll
@@ -657,10 +673,9 @@ __global__ void __launch_bounds__(256) bwd_stats_kernel(const BwdSrc s, long lon
           }
         }
         if (KIND == 2) {
-          const long long r = bb * extent + i + 8 * k;
-          float av[8], cv[8];
-          load8_f32(s.a + (r / s.L) * s.cols + c0, s.cols - c0, av);
-          load8_f32(s.c + (r % s.L) * s.cols + c0, s.cols - c0, cv);
+          float av[8], cv[8];      // row r = bb * L + l: the protein and label indices are the loop variables
+          load8_f32(s.a + bb * s.cols + c0, s.cols - c0, av);
+          load8_f32(s.c + (i + TY * k) * s.cols + c0, s.cols - c0, cv);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             z[j] = av[j] + cv[j];
@@ -696,15 +711,15 @@ __global__ void __launch_bounds__(256) bwd_stats_kernel(const BwdSrc s, long lon
   }
   __syncthreads();
   const float inv_gsc = (KIND != 1 && s.g_sc) ? 1.f / __ldg(s.g_sc) : 1.f;
-  const int i = ty * 32 + tx;
-  const int c = blockIdx.x * 256 + i;
-  if (c < s.cols) {
+  for (int i = ty * TX + tx; i < cpb; i += 256) {
+    const int c = blockIdx.x * cpb + i;
+    if (c >= s.cols) continue;
     double t0 = 0.0, t1 = 0.0, t2 = 0.0;
-#pragma unroll
-    for (int y = 0; y < 8; ++y) {
-      t0 += sh[0][y][i];
-      t1 += sh[1][y][i];
-      if (KIND == 1) t2 += sh[KIND == 1 ? 2 : 0][y][i];
+    for (int y = 0; y < TY; ++y) {
+      const int sl = (y * 8 + (i & 7)) * TX + (i >> 3);      // column i of the block = thread i / 8, element i % 8
+      t0 += sh[0][sl];
+      t1 += sh[1][sl];
+      if (KIND == 1) t2 += sh[KIND == 1 ? 2 : 0][sl];
     }
     const double mean = (double)s.state[2 * (long long)s.cols + c], invstd = (double)s.state[3 * (long long)s.cols + c];
     atomicAdd(sums + c, t0 * (double)inv_gsc);
@@ -720,10 +735,10 @@ __global__ void __launch_bounds__(256) bwd_stats_kernel(const BwdSrc s, long lon
     gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
     zmax = fmaxf(zmax, __shfl_xor_sync(0xffffffffu, zmax, o));
   }
-  if (tx == 0) {
+  if ((tx & 31) == 0) {   // lane 0 of every warp
     atomicMax(maxes, __float_as_uint(gmax));
     atomicMax(maxes + 1, __float_as_uint(zmax));
-    if (KIND == 1 && blockIdx.x == 0 && db) atomicAdd(db, dbs);
+    if (KIND == 1 && blockIdx.x == 0 && tx == 0 && db) atomicAdd(db, dbs);
   }
 }
 
@@ -807,14 +822,21 @@ __global__ void scale_vector_kernel(float* __restrict__ out, int n, const float*
 //   da[b][n] = sum_l g_z1[b,l,n]   a column sum over the L rows of protein b (same structure as pass 1), fp64 atomics
 // Reading g_h1 twice at streaming speed is cheaper than synchronising a block once per protein.
 // ------------------------------------------------------------------------------------------------
+// g_z of row (protein bb, label l); no row-index division
 template <bool LO>
-__device__ __forceinline__ void pair_gz(const BwdSrc& s, const BwdRaw& q, long long r, int c0, const BnVec& b,
+__device__ __forceinline__ void pair_gz(const BwdSrc& s, const BwdRaw& q, long long bb, long long l, int c0, const BnVec& b,
                                         const float (&m1)[8], const float (&m2)[8], float inv_gsc, float (&gz)[8]) {
-  float gy[8], xh[8], pre[8], wv[8];
-  zero8(wv);
-  bwd_eval<2, LO>(s, q, r, c0, b, wv, inv_gsc, gy, xh, pre);
+  float g[8], av[8], cv[8];
+  raw_to_f32<LO>(q.g, g);
+  load8_f32(s.a + bb * s.cols + c0, s.cols - c0, av);
+  load8_f32(s.c + l * s.cols + c0, s.cols - c0, cv);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) gz[j] = c0 + j < s.cols ? b.scale[j] * (gy[j] - m1[j] - xh[j] * m2[j]) : 0.f;
+  for (int j = 0; j < 8; ++j) {
+    const float z = av[j] + cv[j];
+    const float gy = fmaf(z, b.scale[j], b.shift[j]) > 0.f ? g[j] * inv_gsc : 0.f;
+    const float xh = (z - b.mean[j]) * b.invstd[j];
+    gz[j] = c0 + j < s.cols ? b.scale[j] * (gy - m1[j] - xh * m2[j]) : 0.f;
+  }
 }
 
 // grid (ceil(cols/256), ceil(L/8)), block (32, 8)
@@ -843,7 +865,7 @@ __global__ void __launch_bounds__(256) pair_dc_kernel(const BwdSrc s, const floa
     for (int k = 0; k < kRif; ++k) {
       if (bb + k >= B) continue;
       float gz[8];
-      pair_gz<LO>(s, cur[k], (bb + k) * s.L + l, c0, b, m1, m2, inv_gsc, gz);
+      pair_gz<LO>(s, cur[k], bb + k, l, c0, b, m1, m2, inv_gsc, gz);
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] += gz[j];
     }
@@ -903,7 +925,7 @@ __global__ void __launch_bounds__(256) pair_da_kernel(const BwdSrc s, const floa
         for (int k = 0; k < kRif; ++k) {
           if (l + 8 * k >= l_end) continue;
           float gz[8];
-          pair_gz<LO>(s, cur[k], bb * s.L + l + 8 * k, c0, b, m1, m2, inv_gsc, gz);
+          pair_gz<LO>(s, cur[k], bb, l + 8 * k, c0, b, m1, m2, inv_gsc, gz);
 #pragma unroll
           for (int j = 0; j < 8; ++j) acc[j] += gz[j];
         }
