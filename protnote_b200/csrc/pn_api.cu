@@ -1633,11 +1633,13 @@ int pn_t_bwd_stats(const pn_bwd_src* src, double* sums, float* maxes, double* dw
     PN_CUDA(cudaMemsetAsync(db, 0, sizeof(double), stream));
   }
   const int col_blocks = (s.cols + g_stats_tx * 8 - 1) / (g_stats_tx * 8);
-  // kind 2 walks a slab of LABELS for every protein (pn_train.cuh): 128 labels keep the slab's c rows cache-resident
+  // kind 2 walks a slab of LABELS for every protein (pn_train.cuh)
   const long long extent = s.kind == 2 ? s.L : s.rows;
-  long long per = s.kind == 2 ? 128 : slab_rows(s.rows, col_blocks);
+  // kind 2: one step of labels per thread (TY row phases x kRif rows), see bwd_stats_kernel
+  long long per = s.kind == 2 ? (256 / g_stats_tx) * kRif : slab_rows(s.rows, col_blocks);
   long long slabs = (extent + per - 1) / per;
   if (slabs > 65535) {
+    if (s.kind == 2) return fail("too many label rows for one launch (%lld)", s.L);
     per = (extent + 65534) / 65535;
     per = (per + 31) / 32 * 32;
     slabs = (extent + per - 1) / per;

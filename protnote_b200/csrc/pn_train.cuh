@@ -632,6 +632,14 @@ __global__ void __launch_bounds__(256) bwd_stats_kernel(const BwdSrc s, long lon
     } else {
       zero8(wv);
     }
+    float creg[KIND == 2 ? kRif : 1][8];
+    if (KIND == 2) {
+#pragma unroll
+      for (int k = 0; k < kRif; ++k) {
+        zero8(creg[k]);
+        if (i_begin + ty + TY * k < i_end) load8_f32(s.c + (i_begin + ty + TY * k) * s.cols + c0, s.cols - c0, creg[k]);
+      }
+    }
     // columns beyond `cols` (only in the last chunk of a row): scale = shift = 0 -> mask false -> no contribution
     // software pipeline over (protein, row) steps of kRif rows: the next step's loads are issued before this step's math
     long long bb = 0, i = i_begin + ty;
@@ -673,12 +681,13 @@ __global__ void __launch_bounds__(256) bwd_stats_kernel(const BwdSrc s, long lon
           }
         }
         if (KIND == 2) {
-          float av[8], cv[8];      // row r = bb * L + l: the protein and label indices are the loop variables
+          // row r = bb * L + l.  The slab is exactly one step of labels per thread (host: per_slab = TY * kRif), so the
+          // thread's label halves c[l] sit in registers for the whole walk over the proteins; a[bb] is an L1 hit
+          float av[8];
           load8_f32(s.a + bb * s.cols + c0, s.cols - c0, av);
-          load8_f32(s.c + (i + TY * k) * s.cols + c0, s.cols - c0, cv);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            z[j] = av[j] + cv[j];
+            z[j] = av[j] + creg[k][j];
             zmaxf = fmaxf(zmaxf, fabsf(z[j]));
           }
         } else {
