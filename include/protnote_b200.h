@@ -278,7 +278,9 @@ typedef struct pn_bwd_src {
  * maxes[2] = max|g| (before the mask: a bound of max|g_y|), max|z| (pn_t_bwd_scale turns it into a bound of max|xhat|),
  * both read off the hi planes; kind 1 only: dw[c] = sum_r g_logit[r] * relu(z*scale+shift)[r][c], db = sum_r g_logit[r]
  * (gradients of the final Linear). */
-int pn_t_bwd_stats(const pn_bwd_src* src, double* sums, float* maxes, double* dw, double* db, void* stream);
+/* kind 2 only, optional by-product: gyl[l][n] = sum_b g_y[b,l,n] (fp32 [L][cols]); with it pn_t_bwd_apply_pair derives dc
+ * analytically instead of reading g a second time. */
+int pn_t_bwd_stats(const pn_bwd_src* src, double* sums, float* maxes, double* dw, double* db, float* gyl, void* stream);
 /* means[2][cols] (fp32) = sums / count, the two per-column means pass 2 subtracts; sc_out (nullable) = power-of-two scale
  * for the g_z tensor pn_t_bwd_apply will write (from an upper bound of |g_z|).  `sums` are the totals over ALL rows of
  * the batch (all-reduced over ranks when the rows are sharded), count = that number of rows. */
@@ -289,8 +291,10 @@ int pn_t_bwd_apply(const pn_bwd_src* src, const float* means, const float* sc_ou
                    void* hiT, void* loT, long long blocksT, void* stream);
 /* kind 2 only: the same g_z reduced on the fly to da[b] = sum_l g_z[b, l] (fp64 scratch da64 [B][H] -> fp32 da) and
  * dc[l] = sum_b g_z[b, l] (fp32 [L][H]), true scale. */
-int pn_t_bwd_apply_pair(const pn_bwd_src* src, const float* means, long long B, double* da64, float* da, float* dc,
-                        void* stream);
+/* gyl (from pn_t_bwd_stats) and a_stats (pn_t_col_stats of a: fp64 [2][cols]) are optional: when both are given
+ * dc[l] = scale * (gyl[l] - B m1 - m2 * invstd * (sum_b a[b] + B c[l] - B mean)) without a pass over g. */
+int pn_t_bwd_apply_pair(const pn_bwd_src* src, const float* means, long long B, const float* gyl, const double* a_stats,
+                        double* da64, float* da, float* dc, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1621,7 +1621,7 @@ int pn_t_pair_hidden(const float* a, long long B, const float* c, long long L, i
   return launch_emit(p, B * L, H, hi, lo, ld, hiT, loT, blocksT, static_cast<cudaStream_t>(stream));
 }
 
-int pn_t_bwd_stats(const pn_bwd_src* src, double* sums, float* maxes, double* dw, double* db, void* stream_) {
+int pn_t_bwd_stats(const pn_bwd_src* src, double* sums, float* maxes, double* dw, double* db, float* gyl, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   PN_TRY(check_src(src));
   const BwdSrc s = to_src(*src);
@@ -1647,12 +1647,12 @@ int pn_t_bwd_stats(const pn_bwd_src* src, double* sums, float* maxes, double* dw
   const dim3 grid(col_blocks, (unsigned)slabs), block(g_stats_tx, 256 / g_stats_tx);
   unsigned* mx = reinterpret_cast<unsigned*>(maxes);
   const bool lo = src_has_lo(s);
-  if (s.kind == 0 && lo) bwd_stats_kernel<0, true><<<grid, block, 0, stream>>>(s, per, sums, mx, dw, db);
-  else if (s.kind == 0) bwd_stats_kernel<0, false><<<grid, block, 0, stream>>>(s, per, sums, mx, dw, db);
-  else if (s.kind == 1 && lo) bwd_stats_kernel<1, true><<<grid, block, 0, stream>>>(s, per, sums, mx, dw, db);
-  else if (s.kind == 1) bwd_stats_kernel<1, false><<<grid, block, 0, stream>>>(s, per, sums, mx, dw, db);
-  else if (lo) bwd_stats_kernel<2, true><<<grid, block, 0, stream>>>(s, per, sums, mx, dw, db);
-  else bwd_stats_kernel<2, false><<<grid, block, 0, stream>>>(s, per, sums, mx, dw, db);
+  if (s.kind == 0 && lo) bwd_stats_kernel<0, true><<<grid, block, 0, stream>>>(s, per, sums, mx, dw, db, gyl);
+  else if (s.kind == 0) bwd_stats_kernel<0, false><<<grid, block, 0, stream>>>(s, per, sums, mx, dw, db, gyl);
+  else if (s.kind == 1 && lo) bwd_stats_kernel<1, true><<<grid, block, 0, stream>>>(s, per, sums, mx, dw, db, gyl);
+  else if (s.kind == 1) bwd_stats_kernel<1, false><<<grid, block, 0, stream>>>(s, per, sums, mx, dw, db, gyl);
+  else if (lo) bwd_stats_kernel<2, true><<<grid, block, 0, stream>>>(s, per, sums, mx, dw, db, gyl);
+  else bwd_stats_kernel<2, false><<<grid, block, 0, stream>>>(s, per, sums, mx, dw, db, gyl);
   g_launches++;
   PN_CUDA(cudaGetLastError());
   return 0;
@@ -1679,8 +1679,8 @@ int pn_t_bwd_apply(const pn_bwd_src* src, const float* means, const float* sc_ou
   return launch_emit(BwdApplyProducer<2>{s, means, sc_out}, s.rows, s.cols, hi, lo, ld, hiT, loT, blocksT, stream);
 }
 
-int pn_t_bwd_apply_pair(const pn_bwd_src* src, const float* means, long long B, double* da64, float* da, float* dc,
-                        void* stream_) {
+int pn_t_bwd_apply_pair(const pn_bwd_src* src, const float* means, long long B, const float* gyl, const double* a_stats,
+                        double* da64, float* da, float* dc, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   PN_TRY(check_src(src));
   if (src->kind != 2 || B <= 0 || B * src->L != src->rows) return fail("pair backward needs a kind-2 source with rows == B * L");
@@ -1692,8 +1692,13 @@ int pn_t_bwd_apply_pair(const pn_bwd_src* src, const float* means, long long B, 
   const long long l_blocks = (s.L + 7) / 8;
   if (l_blocks > 65535) return fail("too many label rows for one launch (%lld)", s.L);
   const bool lo = src_has_lo(s);
-  if (lo) pair_dc_kernel<true><<<dim3(col_blocks, (unsigned)l_blocks), dim3(32, 8), 0, stream>>>(s, means, B, dc);
-  else pair_dc_kernel<false><<<dim3(col_blocks, (unsigned)l_blocks), dim3(32, 8), 0, stream>>>(s, means, B, dc);
+  if (gyl && a_stats) {   // dc from the statistics pass's by-product: no second pass over g
+    pair_dc_fixup_kernel<<<ew_grid(s.L * s.cols), 256, 0, stream>>>(gyl, s.c, a_stats, s.state, means, B, s.L, s.cols, dc);
+  } else if (lo) {
+    pair_dc_kernel<true><<<dim3(col_blocks, (unsigned)l_blocks), dim3(32, 8), 0, stream>>>(s, means, B, dc);
+  } else {
+    pair_dc_kernel<false><<<dim3(col_blocks, (unsigned)l_blocks), dim3(32, 8), 0, stream>>>(s, means, B, dc);
+  }
   long long per = 128;
   long long slabs = (s.L + per - 1) / per;
   if (slabs > 65535) return fail("too many label rows for one launch (%lld)", s.L);

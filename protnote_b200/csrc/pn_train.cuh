@@ -580,7 +580,7 @@ __device__ __forceinline__ void absmax_raw(const uint4& h, __half2& m) {
 template <int KIND, bool LO>
 __global__ void __launch_bounds__(256) bwd_stats_kernel(const BwdSrc s, long long per_slab, double* __restrict__ sums,
                                                         unsigned* __restrict__ maxes, double* __restrict__ dw,
-                                                        double* __restrict__ db) {
+                                                        double* __restrict__ db, float* __restrict__ gyl) {
   // fp64 accumulators: one private slot per thread and column (no atomics while streaming), reduced over the 8 row
   // phases at the end.  [sum][ty][256 columns] doubles = 32 KB (48 KB for kind 1).
   __shared__ double sh[KIND == 1 ? 3 : 2][2048];
@@ -632,11 +632,14 @@ __global__ void __launch_bounds__(256) bwd_stats_kernel(const BwdSrc s, long lon
     } else {
       zero8(wv);
     }
-    float creg[KIND == 2 ? kRif : 1][8];
+    // kind 2 by-product: gyl[l][n] = sum_b g_y[b,l,n] for the labels this thread owns - with it dc[l] = sum_b g_z[b,l]
+    // follows analytically (pair_dc_fixup_kernel) and the separate pass over g_h1 for dc is not needed
+    float creg[KIND == 2 ? kRif : 1][8], gacc[KIND == 2 ? kRif : 1][8];
     if (KIND == 2) {
 #pragma unroll
       for (int k = 0; k < kRif; ++k) {
         zero8(creg[k]);
+        zero8(gacc[k]);
         if (i_begin + ty + TY * k < i_end) load8_f32(s.c + (i_begin + ty + TY * k) * s.cols + c0, s.cols - c0, creg[k]);
       }
     }
@@ -706,6 +709,7 @@ __global__ void __launch_bounds__(256) bwd_stats_kernel(const BwdSrc s, long lon
           const float gmk = pre > 0.f ? g[j] : 0.f;
           p1[j] += gmk;
           p2[j] = fmaf(gmk, z[j], p2[j]);
+          if (KIND == 2) gacc[k][j] += gmk;
           if (KIND == 1) p3[j] = fmaf(cur[k].gl, fmaxf(pre, 0.f), p3[j]);
         }
       }
@@ -717,6 +721,17 @@ __global__ void __launch_bounds__(256) bwd_stats_kernel(const BwdSrc s, long lon
       have = have_next;
     }
     flush();
+    if (KIND == 2 && gyl) {
+      const float inv = s.g_sc ? 1.f / __ldg(s.g_sc) : 1.f;
+#pragma unroll
+      for (int k = 0; k < kRif; ++k) {
+        const long long l = i_begin + ty + TY * k;
+        if (l >= i_end) continue;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (c0 + j < s.cols) gyl[l * s.cols + c0 + j] = gacc[k][j] * inv;
+      }
+    }
   }
   __syncthreads();
   const float inv_gsc = (KIND != 1 && s.g_sc) ? 1.f / __ldg(s.g_sc) : 1.f;
@@ -845,6 +860,22 @@ __device__ __forceinline__ void pair_gz(const BwdSrc& s, const BwdRaw& q, long l
     const float gy = fmaf(z, b.scale[j], b.shift[j]) > 0.f ? g[j] * inv_gsc : 0.f;
     const float xh = (z - b.mean[j]) * b.invstd[j];
     gz[j] = c0 + j < s.cols ? b.scale[j] * (gy - m1[j] - xh * m2[j]) : 0.f;
+  }
+}
+
+// dc[l][n] = sum_b g_z1[b,l,n] from the per-label masked sums gyl = sum_b g_y (by-product of the statistics pass):
+//   sum_b g_z = scale * (gyl - B m1 - m2 * sum_b xhat),   sum_b xhat = invstd * (A + B c[l] - B mean),  A = sum_b a[b]
+__global__ void pair_dc_fixup_kernel(const float* __restrict__ gyl, const float* __restrict__ c,
+                                     const double* __restrict__ a_stats, const float* __restrict__ state,
+                                     const float* __restrict__ means, long long B, long long L, int cols,
+                                     float* __restrict__ dc) {
+  const long long total = L * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i % cols);
+    const float scale = state[n], mean = state[2 * (long long)cols + n], invstd = state[3 * (long long)cols + n];
+    const float m1 = means[n], m2 = means[cols + n];
+    const float sumx = invstd * ((float)a_stats[n] + (float)B * (c[i] - mean));
+    dc[i] = scale * (gyl[i] - (float)B * m1 - m2 * sumx);
   }
 }
 

@@ -45,7 +45,7 @@ class Packed:
 
 
 class BwdStats:
-    __slots__ = ("sums", "maxes", "local", "dw", "db")
+    __slots__ = ("sums", "maxes", "local", "dw", "db", "gyl")
 
 
 class Outer:
@@ -56,6 +56,7 @@ class Outer:
 class PairSrc:
     def __init__(self, a, c):
         self.a, self.c = a, c
+        self.a_stats = None       # column sums of a (fp64 [2, H]), filled lazily for the analytic dc
 
 
 class NativeOps:
@@ -254,13 +255,15 @@ class NativeOps:
         out = BwdStats()
         out.sums = torch.empty(2, src.cols, dtype=torch.float64, device=dev)
         out.maxes = torch.empty(2, dtype=torch.float32, device=dev)
-        out.dw = out.db = None
+        out.dw = out.db = out.gyl = None
+        if src.kind == 2:          # by-product of the pass: per-label masked gradient sums (see bwd_apply_pair)
+            out.gyl = torch.empty(z.c.shape[0], src.cols, dtype=torch.float32, device=dev)
         if src.kind == 1:
             out.dw = torch.empty(src.cols, dtype=torch.float64, device=dev)
             out.db = torch.empty(1, dtype=torch.float64, device=dev)
         with torch.cuda.device(dev):
             check(self.lib.pn_t_bwd_stats(C.byref(src), ptr(out.sums), ptr(out.maxes), ptr(out.dw), ptr(out.db),
-                                          stream_ptr()))
+                                          ptr(out.gyl), stream_ptr()))
         out.local = out.sums.clone()
         return out
 
@@ -292,8 +295,13 @@ class NativeOps:
         da = torch.empty(B, H, dtype=torch.float32, device=dev)
         dc = torch.empty(L, H, dtype=torch.float32, device=dev)
         means = torch.empty(2, src.cols, dtype=torch.float32, device=dev)
+        gyl = getattr(s, "gyl", None)
+        if gyl is not None and zp.a_stats is None:
+            zp.a_stats = self.col_stats_f32(zp.a)
         with torch.cuda.device(dev):
             check(self.lib.pn_t_bwd_scale(ptr(s.sums), ptr(s.maxes), ptr(st), float(count), src.cols, None, ptr(means),
                                           stream_ptr()))
-            check(self.lib.pn_t_bwd_apply_pair(C.byref(src), ptr(means), B, ptr(da64), ptr(da), ptr(dc), stream_ptr()))
+            check(self.lib.pn_t_bwd_apply_pair(C.byref(src), ptr(means), B, ptr(gyl),
+                                               ptr(zp.a_stats) if gyl is not None else None, ptr(da64), ptr(da), ptr(dc),
+                                               stream_ptr()))
         return da, dc
