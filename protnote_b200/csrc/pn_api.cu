@@ -1289,7 +1289,8 @@ int pn_score_pairs_ex(const pn_scorer_cfg* cfg, const void* packed, const float*
       }
       const bool fuse_features = fuse_ok && nl % kBM == 0;   // a tile = one protein x 128 consecutive label rows
       if (c.fusion != PN_FUSION_CONCAT_PROD && !fuse_features) {
-        pair_features_kernel<<<ew_grid(rows * (ld_h / 8)), 256, 0, stream>>>(a, H, c_in, H, (int)b0, (int)l0, (int)nl, rows,
+        const int pf_threads = (int)(round_up(ld_h / 8, 32) < 1024 ? round_up(ld_h / 8, 32) : 1024);
+        pair_features_kernel<<<(unsigned)((rows + kPairRows - 1) / kPairRows), pf_threads, 0, stream>>>(a, H, c_in, H, (int)b0, (int)l0, (int)nl, rows,
                                                                              H, buf_hi[0], mode == PN_STRICT ? buf_lo[0] : nullptr,
                                                                              ld_h);
         g_launches++;

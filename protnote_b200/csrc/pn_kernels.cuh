@@ -155,30 +155,44 @@ __global__ void conv_input_tokens_kernel(const uint8_t* __restrict__ tokens, con
 // (reference protnote/models/ProtNote.py:112-126,293 materialises [B*L, 2d]; here it never exists):
 //   h1[(b,l)][k] = relu(a[b][k] + c[l][k])      a = BN1-folded protein half, c = BN1-scaled label half
 // rows of the chunk are pairs (b0 + r / nl, l0 + r % nl); output fp16 planes [nb*nl][ld].
+// One block = kPairRows consecutive pair rows; thread t = 8-column chunk t of every one of them (row and protein
+// indices are per-block scalars: the first version spent four 64-bit div/mod per 8 elements and was bound by
+// instruction issue at the power-capped clock, not by HBM).  grid (ceil(rows / kPairRows)), block = ld / 8 threads
+// rounded up to a warp (<= 1024).
+constexpr int kPairRows = 16;
 __global__ void pair_features_kernel(const float* __restrict__ a, long long lda, const float* __restrict__ c,
                                      long long ldc, int b0, int l0, int nl, long long rows, int H,
                                      __half* __restrict__ hi, __half* __restrict__ lo, int ld) {
   const int chunks = ld / 8;
-  const long long total = rows * chunks;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / chunks;
-    const int k0 = (int)(i % chunks) * 8;
-    const float* ap = a + (b0 + r / nl) * lda + k0;
-    const float* cp = c + (l0 + r % nl) * ldc + k0;
-    float v[8];
-    if (k0 + 8 <= H && ((lda | ldc) & 3) == 0) {
-      const float4 a0 = *reinterpret_cast<const float4*>(ap), a1 = *reinterpret_cast<const float4*>(ap + 4);
-      const float4 c0 = *reinterpret_cast<const float4*>(cp), c1 = *reinterpret_cast<const float4*>(cp + 4);
-      v[0] = a0.x + c0.x; v[1] = a0.y + c0.y; v[2] = a0.z + c0.z; v[3] = a0.w + c0.w;
-      v[4] = a1.x + c1.x; v[5] = a1.y + c1.y; v[6] = a1.z + c1.z; v[7] = a1.w + c1.w;
-    } else {
+  const bool vec = ((lda | ldc) & 3) == 0;
+  const long long r_begin = (long long)blockIdx.x * kPairRows;
+  long long bb = r_begin / nl;                 // one division per block
+  int l = (int)(r_begin - bb * nl);
+  for (int rr = 0; rr < kPairRows; ++rr) {
+    const long long r = r_begin + rr;
+    if (r >= rows) break;
+    const float* arow = a + (b0 + bb) * lda;
+    const float* crow = c + (long long)(l0 + l) * ldc;
+    for (int ch = threadIdx.x; ch < chunks; ch += blockDim.x) {
+      const int k0 = ch * 8;
+      float v[8];
+      if (k0 + 8 <= H && vec) {
+        const float4 a0 = __ldg(reinterpret_cast<const float4*>(arow + k0)), a1 = __ldg(reinterpret_cast<const float4*>(arow + k0 + 4));
+        const float4 c0 = __ldg(reinterpret_cast<const float4*>(crow + k0)), c1 = __ldg(reinterpret_cast<const float4*>(crow + k0 + 4));
+        v[0] = a0.x + c0.x; v[1] = a0.y + c0.y; v[2] = a0.z + c0.z; v[3] = a0.w + c0.w;
+        v[4] = a1.x + c1.x; v[5] = a1.y + c1.y; v[6] = a1.z + c1.z; v[7] = a1.w + c1.w;
+      } else {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = (k0 + j < H) ? ap[j] + cp[j] : 0.f;
+        for (int j = 0; j < 8; ++j) v[j] = (k0 + j < H) ? arow[k0 + j] + crow[k0 + j] : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+      split8_store(v, hi + r * ld + k0, lo ? lo + r * ld + k0 : nullptr);
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
-    split8_store(v, hi + r * ld + k0, lo ? lo + r * ld + k0 : nullptr);
+    if (++l == nl) {
+      l = 0;
+      ++bb;
+    }
   }
 }
 
