@@ -137,3 +137,40 @@ def test_train_mode_encoder_oracle_matches_reference():
     assert len(stats) == 4 * ecfg.num_resnet_blocks
     for k, v in stats.items():
         assert (bufs[k] - v).abs().max() < 1e-10, k
+
+
+def test_training_path_refuses_what_it_does_not_implement():
+    """Unsupported options fail loudly (no silent fallback): dropout > 0, a fusion other than 'concatenation', an output MLP
+    without BatchNorm; and the product module itself has no CPU path in training mode either."""
+    from protnote_b200._lib import ProtnoteB200Error
+    ecfg, scfg, sd, P_f, L_f, y = _problem()
+    model = build_b200_model(ecfg, scfg, sd, device="cpu").double().train()
+    ops = TorchOps(torch.float64)
+    for m in model.output_layer.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.1
+    with pytest.raises(NotImplementedError):
+        pn_train.forward_train(ops, None, model, P_f.double(), L_f.double())
+    for m in model.output_layer.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    prod_cfg = ScorerCfg(protein_embedding_dim=72, label_embedding_dim=40, latent_dim=32,
+                         output_mlp_hidden_dim_scale_factor=3, output_mlp_num_layers=3, projection_head_num_layers=4,
+                         projection_head_hidden_dim_scale_factor=3, feature_fusion="concatenation_prod")
+    sd_prod = synth_state_dict(ecfg, prod_cfg, seed=3, calib_T=64)
+    prod = build_b200_model(ecfg, prod_cfg, sd_prod, device="cpu").double().train()
+    with pytest.raises(NotImplementedError):
+        pn_train.forward_train(ops, None, prod, P_f.double(), L_f.double())
+    nobn_cfg = ScorerCfg(protein_embedding_dim=72, label_embedding_dim=40, latent_dim=32,
+                         output_mlp_hidden_dim_scale_factor=3, output_mlp_num_layers=3, projection_head_num_layers=4,
+                         projection_head_hidden_dim_scale_factor=3, output_mlp_batchnorm=False)
+    sd_nobn = synth_state_dict(ecfg, nobn_cfg, seed=4, calib_T=64)
+    nobn = build_b200_model(ecfg, nobn_cfg, sd_nobn, device="cpu").double().train()
+    with pytest.raises(NotImplementedError):
+        pn_train.forward_train(ops, None, nobn, P_f.double(), L_f.double())
+    # the product module: CPU tensors in training mode -> error, never a torch fallback
+    cpu_model = build_b200_model(ecfg, scfg, sd, device="cpu").train()
+    with pytest.raises(ProtnoteB200Error):
+        cpu_model(sequence_embeddings=P_f, label_embeddings=L_f)
+    with pytest.raises(ValueError):
+        cpu_model(sequence_embeddings=P_f)
