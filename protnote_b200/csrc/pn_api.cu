@@ -1700,11 +1700,12 @@ int pn_t_bwd_apply_pair(const pn_bwd_src* src, const float* means, long long B, 
   } else {
     pair_dc_kernel<false><<<dim3(col_blocks, (unsigned)l_blocks), dim3(32, 8), 0, stream>>>(s, means, B, dc);
   }
-  long long per = 128;
+  long long per = 1024;
   long long slabs = (s.L + per - 1) / per;
   if (slabs > 65535) return fail("too many label rows for one launch (%lld)", s.L);
-  if (lo) pair_da_kernel<true><<<dim3(col_blocks, (unsigned)slabs), dim3(32, 8), 0, stream>>>(s, means, B, per, da64);
-  else pair_da_kernel<false><<<dim3(col_blocks, (unsigned)slabs), dim3(32, 8), 0, stream>>>(s, means, B, per, da64);
+  const dim3 da_grid((unsigned)B, col_blocks, (unsigned)slabs);
+  if (lo) pair_da_kernel<true><<<da_grid, dim3(32, 8), 0, stream>>>(s, means, B, per, da64);
+  else pair_da_kernel<false><<<da_grid, dim3(32, 8), 0, stream>>>(s, means, B, per, da64);
   f64_to_f32_kernel<<<ew_grid(B * s.cols), 256, 0, stream>>>(da64, da, B * s.cols);
   g_launches += 3;
   PN_CUDA(cudaGetLastError());

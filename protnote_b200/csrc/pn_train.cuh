@@ -917,74 +917,59 @@ __global__ void __launch_bounds__(256) pair_dc_kernel(const BwdSrc s, const floa
     if (c0 + j < s.cols) dc[l * s.cols + c0 + j] = acc[j];
 }
 
-// grid (ceil(cols/256), label slabs), block (32, 8): the slab's labels are walked once per protein (c stays in L1/L2);
-// after each protein the block's 8 row phases are reduced through shared memory and added to da[b] (fp64 atomics).
+// grid (B, ceil(cols/256), label slabs), block (32, 8): one protein and one slab of labels per block, walked two rows at
+// a time with the next step's loads in flight; a single block reduction and 256 fp64 atomics at the end.  The protein
+// index is the FASTEST grid dimension, so the B blocks that share a slab's rows of c run together and find them in L2.
 template <bool LO>
 __global__ void __launch_bounds__(256) pair_da_kernel(const BwdSrc s, const float* __restrict__ means, long long B,
                                                       long long labels_per_slab, double* __restrict__ da) {
-  __shared__ float sh[8][256];
+  __shared__ float sh[8][8][32];   // [row phase][element][lane]: conflict-free
   const int tx = threadIdx.x, ty = threadIdx.y;
-  const int c0 = blockIdx.x * 256 + tx * 8;
-  const long long l_begin = (long long)blockIdx.y * labels_per_slab;
+  const long long bb = blockIdx.x;
+  const int c0 = blockIdx.y * 256 + tx * 8;
+  const long long l_begin = (long long)blockIdx.z * labels_per_slab;
   const long long l_end = l_begin + labels_per_slab < s.L ? l_begin + labels_per_slab : s.L;
-  const bool active = c0 < s.cols && l_begin + ty < l_end;
-  BnVec b;
-  float m1[8], m2[8];
-  zero8(m1);
-  zero8(m2);
-  if (active) {
+  float acc[8];
+  zero8(acc);
+  if (c0 < s.cols && l_begin + ty < l_end) {
+    BnVec b;
+    float m1[8], m2[8];
     load_bn(s.state, s.cols, c0, b);
     load8_f32(means + c0, s.cols - c0, m1);
     load8_f32(means + s.cols + c0, s.cols - c0, m2);
-  }
-  const float inv_gsc = s.g_sc ? 1.f / __ldg(s.g_sc) : 1.f;
-  // pipeline over (protein, label) steps; `acc` is handed to the block reduction whenever the protein changes
-  long long bb = 0, l = l_begin + ty;
-  BwdRaw cur[kRif], nxt[kRif];
-  if (active) {
+    const float inv_gsc = s.g_sc ? 1.f / __ldg(s.g_sc) : 1.f;
+    BwdRaw cur[kRif], nxt[kRif];
+    long long l = l_begin + ty;
 #pragma unroll
     for (int k = 0; k < kRif; ++k)
-      if (l + 8 * k < l_end) bwd_raw_load<2, LO>(s, l + 8 * k, c0, cur[k]);
-  }
-  for (bb = 0; bb < B; ++bb) {
-    float acc[8];
-    zero8(acc);
-    if (active) {
-      for (l = l_begin + ty; l < l_end; l += 8 * kRif) {
-        long long nbb = bb, nl = l + 8 * kRif;
-        if (nl >= l_end) {
-          nl = l_begin + ty;
-          ++nbb;
-        }
-        if (nbb < B) {
+      if (l + 8 * k < l_end) bwd_raw_load<2, LO>(s, bb * s.L + l + 8 * k, c0, cur[k]);
+    for (; l < l_end; l += 8 * kRif) {
+      const long long nl = l + 8 * kRif;
 #pragma unroll
-          for (int k = 0; k < kRif; ++k)
-            if (nl + 8 * k < l_end) bwd_raw_load<2, LO>(s, nbb * s.L + nl + 8 * k, c0, nxt[k]);
-        }
+      for (int k = 0; k < kRif; ++k)
+        if (nl + 8 * k < l_end) bwd_raw_load<2, LO>(s, bb * s.L + nl + 8 * k, c0, nxt[k]);
 #pragma unroll
-        for (int k = 0; k < kRif; ++k) {
-          if (l + 8 * k >= l_end) continue;
-          float gz[8];
-          pair_gz<LO>(s, cur[k], bb, l + 8 * k, c0, b, m1, m2, inv_gsc, gz);
+      for (int k = 0; k < kRif; ++k) {
+        if (l + 8 * k >= l_end) continue;
+        float gz[8];
+        pair_gz<LO>(s, cur[k], bb, l + 8 * k, c0, b, m1, m2, inv_gsc, gz);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] += gz[j];
-        }
-#pragma unroll
-        for (int k = 0; k < kRif; ++k) cur[k] = nxt[k];
+        for (int j = 0; j < 8; ++j) acc[j] += gz[j];
       }
-    }
-    __syncthreads();   // the previous protein's readers are done with sh
 #pragma unroll
-    for (int j = 0; j < 8; ++j) sh[ty][tx * 8 + j] = acc[j];
-    __syncthreads();
-    const int i = ty * 32 + tx;
-    const int c = blockIdx.x * 256 + i;
-    if (c < s.cols) {
-      float tot = 0.f;
-#pragma unroll
-      for (int y = 0; y < 8; ++y) tot += sh[y][i];
-      atomicAdd(da + bb * s.cols + c, (double)tot);
+      for (int k = 0; k < kRif; ++k) cur[k] = nxt[k];
     }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sh[ty][j][tx] = acc[j];
+  __syncthreads();
+  const int i = ty * 32 + tx;            // column i of the block = lane i / 8, element i % 8
+  const int c = blockIdx.y * 256 + i;
+  if (c < s.cols) {
+    float tot = 0.f;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) tot += sh[y][i & 7][i >> 3];
+    atomicAdd(da + bb * s.cols + c, (double)tot);
   }
 }
 
