@@ -40,6 +40,14 @@ B_TOTAL, T_LEN, L_ROWS = 4096, 1024, 32768
 CPU_SAMPLE = (8, 1024, 4096)        # sequences, residues, label rows of the bounded CPU sample
 
 
+def config_tag(B, T, L, k):
+    if (B, T, L, k) == (B_TOTAL, T_LEN, L_ROWS, 1):
+        return "BASELINE.json configs[1]"
+    if (B, L, k) == (10000, 10268, 2):
+        return "BASELINE.json configs[3]: zero-shot EC shape, 5134 EC numbers x 2 descriptions"
+    return "non-headline shape"
+
+
 def base_config_model(precision: str, descriptions_per_label: int = 1):
     """Random-init ProtNote with the published architecture (configs/base_config.yaml)."""
     from protnote_b200.ProtNote import ProtNote
@@ -305,7 +313,7 @@ def run_ours(args, rank, world, local_rank):
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32 (fp16 hi/lo planes, 3 tcgen05 passes, fp32 accumulate)" if passes == 3
         else "f16 operands, fp32 accumulate", "data": "synthetic",
-        "config": {"workload": f"inference {B} x {T} aa x {L} label rows, fp32 in/out (BASELINE.json configs[1])",
+        "config": {"workload": f"inference {B} x {T} aa x {L} label rows, fp32 in/out ({config_tag(B, T, L, kdesc)})",
                    "mode": args.mode, "sequences": B, "seq_len": T, "label_rows": L, "descriptions_per_label": kdesc,
                    "parallelism": "1 GPU" if world == 1 else f"label-sharded x{world} (proteins sharded for the encoder), "
                                                               "NCCL all-gather of P_f and of the logit slab",
