@@ -185,6 +185,60 @@ class ProtNote(nn.Module):
         self._label_cache = (key, out, L_f)
         return out
 
+    # ------------------------------------------------------------------ label-projection cache on disk
+    def _label_fingerprint(self, L_f):
+        """What the projected label halves depend on: W_l, layer 1 of the output MLP (+ its BatchNorm), the label
+        embeddings themselves and the arithmetic mode - as cheap device-side checksums."""
+        parts = list(self._head_sources(self.W_l))
+        if self.feature_fusion != "similarity":
+            mods = list(self.output_layer)
+            parts.append(mods[0].weight)
+            if isinstance(mods[1], nn.BatchNorm1d):
+                parts += [mods[1].weight, mods[1].bias, mods[1].running_mean, mods[1].running_var]
+            elif mods[0].bias is not None:
+                parts.append(mods[0].bias)
+        sums = [float(t.detach().double().sum()) for t in parts] + [float(t.detach().double().abs().sum()) for t in parts]
+        return {"weights": sums, "labels": [float(L_f.double().sum()), float(L_f.double().abs().sum())],
+                "label_shape": list(L_f.shape), "precision": self.precision, "fusion": self.feature_fusion}
+
+    def save_label_projection(self, path, label_embeddings):
+        """Runs W_l and the label half of output layer 1 once for `label_embeddings` [L, label_dim] and stores the result
+        (c [L, H] and, for the fusions that need it, L_e [L, latent]) with a fingerprint of everything it depends on.  The
+        cached-embedding file of the reference (bin/generate_label_embeddings.py:149-164) only holds the raw text
+        embeddings, so W_l is recomputed by every process and every batch (ProtNote.py:271)."""
+        if self.training:
+            raise ProtnoteB200Error("label projections are cached for evaluation (model.eval())")
+        dev = next(self.W_p.parameters()).device
+        L_f = label_embeddings.to(dev)
+        scorer = self._ensure_packed()
+        need_emb = self.feature_fusion in ("concatenation_prod", "similarity")
+        L_e, c = scorer.project_labels(L_f, native.MODES[self.precision], want_embedding=need_emb)
+        torch.save({"fingerprint": self._label_fingerprint(L_f), "c": None if c is None else c.cpu(),
+                    "L_e": None if L_e is None else L_e.cpu()}, path)
+
+    def load_label_projection(self, path, label_embeddings):
+        """Installs a stored projection for `label_embeddings` (same tensor object must then be passed to forward());
+        raises if the weights, the embeddings or the mode differ from the ones it was computed with."""
+        dev = next(self.W_p.parameters()).device
+        L_f = label_embeddings.to(dev)
+        blob = torch.load(path)
+        want = self._label_fingerprint(L_f)
+        got = blob["fingerprint"]
+        same = (got["label_shape"] == want["label_shape"] and got["precision"] == want["precision"]
+                and got["fusion"] == want["fusion"]
+                and all(abs(a - b) <= 1e-9 * max(1.0, abs(b)) for a, b in zip(got["weights"] + got["labels"],
+                                                                                want["weights"] + want["labels"])))
+        if not same or len(got["weights"]) != len(want["weights"]):
+            raise ProtnoteB200Error("stored label projection does not match this model / these label embeddings")
+        self._ensure_packed()
+        mode = native.MODES[self.precision]
+        need_emb = self.feature_fusion in ("concatenation_prod", "similarity")
+        out = (None if blob["L_e"] is None else blob["L_e"].to(dev), None if blob["c"] is None else blob["c"].to(dev))
+        for want_embedding in {need_emb, True} if out[0] is not None else {need_emb}:
+            key = (L_f.data_ptr(), L_f._version, tuple(L_f.shape), self._packed_key, mode, want_embedding)
+            self._label_cache = (key, out, L_f)
+        return L_f
+
     # ------------------------------------------------------------------ training mode
     def _forward_train(self, sequence_onehots, sequence_embeddings, sequence_lengths, label_embeddings,
                        label_token_counts, save_embeddings):

@@ -103,3 +103,33 @@ def test_plumbing_configuration_through_an_evaluation_loop():
     assert torch.equal(counts[0].cpu(), tp) and torch.equal(counts[1].cpu(), fn) and torch.equal(counts[2].cpu(), fp)
     rtp, rfn, rfp = _tp_fn_fp(probs, multihots.float(), 0.5)
     assert float((tp - rtp).abs().sum() + (fn - rfn).abs().sum() + (fp - rfp).abs().sum()) <= 2 * float((~decided).sum())
+
+
+def test_label_projection_round_trip_on_disk(tmp_path):
+    """N3: the projected label halves stored on disk reproduce the logits bit for bit, skip W_l, and are refused for
+    other weights or other embeddings."""
+    from protnote_b200 import native
+    from protnote_b200._lib import ProtnoteB200Error
+    ecfg, scfg, sd, onehots, lengths, labels, g = load_case("tiny_concat")
+    model = build_b200_model(ecfg, scfg, sd)
+    path = str(tmp_path / "labels.proj.pt")
+    with torch.no_grad():
+        ref, _ = model(sequence_onehots=onehots.cuda(), sequence_lengths=lengths.cuda(), label_embeddings=labels.cuda())
+        model.save_label_projection(path, labels)
+        fresh = build_b200_model(ecfg, scfg, sd)
+        lab_dev = fresh.load_label_projection(path, labels)
+        P_f = fresh.sequence_encoder.get_embeddings(onehots.cuda(), lengths.cuda())
+        before = native.launch_count()
+        got, _ = fresh(sequence_embeddings=P_f, label_embeddings=lab_dev)
+        cached_launches = native.launch_count() - before
+        fresh._label_cache = None
+        before = native.launch_count()
+        again, _ = fresh(sequence_embeddings=P_f, label_embeddings=lab_dev)
+        uncached_launches = native.launch_count() - before
+    assert torch.equal(got, ref) and torch.equal(again, ref)
+    assert cached_launches < uncached_launches          # W_l and the label half of layer 1 were not launched
+    other = build_b200_model(ecfg, scfg, {k: (v * 1.01 if k.startswith("W_l.0") else v) for k, v in sd.items()})
+    with pytest.raises(ProtnoteB200Error):
+        other.load_label_projection(path, labels)
+    with pytest.raises(ProtnoteB200Error):
+        fresh.load_label_projection(path, labels * 1.5)
