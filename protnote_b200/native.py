@@ -6,7 +6,7 @@ and handing data pointers to the library.  No arithmetic on tensor data happens 
 from __future__ import annotations
 
 import ctypes as C
-from typing import List, Optional, Sequence
+from typing import Optional, Sequence
 
 import torch
 

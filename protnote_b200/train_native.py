@@ -11,7 +11,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import PN_FAST, PN_STRICT, BwdSrc, check, ptr, stream_ptr
+from ._lib import PN_STRICT, BwdSrc, check, ptr, stream_ptr
 from .native import MODES, _require_cuda
 
 
