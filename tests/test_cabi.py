@@ -78,3 +78,34 @@ def test_module_interface_matches_reference_contract():
     model.train()
     with pytest.raises(_lib.ProtnoteB200Error):
         model(sequence_onehots=x, sequence_lengths=torch.tensor([12, 7]), label_embeddings=torch.zeros(4, 16))
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/protnote_b200.h is the boundary a non-Python host binds: it must compile as C99 on its own, and a C
+    translation unit that calls the entry points must link against the shared library."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "host.c"
+    src.write_text(
+        '#include "protnote_b200.h"\n'
+        '#include <stdio.h>\n'
+        'int main(void) {\n'
+        '  pn_scorer_cfg cfg = {1100, 1024, 1024, 3072, 4, 3072, 3, 1, PN_FUSION_CONCAT, 1, 1e-5f};\n'
+        '  pn_encoder_cfg enc = {20, 1100, 550, 9, 3, 5, 1e-3f};\n'
+        '  printf("%d %zu %zu %d\\n", pn_version(), pn_scorer_packed_bytes(&cfg), pn_encoder_packed_bytes(&enc),\n'
+        '         pn_scorer_num_params(&cfg));\n'
+        '  return pn_score_pairs(&cfg, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, PN_STRICT, 0) == 0;   /* empty input -> error status */\n'
+        '}\n')
+    exe = tmp_path / "host"
+    lib_dir = os.path.join(root, "protnote_b200", "lib")
+    res = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(root, "include"), str(src), "-o", str(exe),
+                          "-L", lib_dir, "-lprotnote_b200", "-Wl,-rpath," + lib_dir], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    run = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert run.returncode == 0, run.stderr           # sizes are host arithmetic; the empty call returns an error status
+    version, scorer_bytes, encoder_bytes, nparams = run.stdout.split()
+    assert int(version) >= 1 and int(scorer_bytes) > 100e6 and int(encoder_bytes) > 50e6 and int(nparams) == 49
