@@ -80,6 +80,9 @@ def _split_sequential(seq: nn.Module) -> List[Tuple[nn.Linear, Optional[nn.Batch
 # projection heads W_p / W_l  (ProtNote.py:63-81):  [Linear(no bias), BN, ReLU] x (n-1), Linear(no bias)
 # --------------------------------------------------------------------------------------------------------------------
 def head_forward(ops, comm, x_f32, layers, rows_total: int, sharded: bool, update_running: bool):
+    if rows_total <= 1 and any(bn is not None for _, bn in layers):
+        # same error as torch.nn.BatchNorm1d in training mode, which the reference module raises here
+        raise ValueError(f"Expected more than 1 value per channel when training, got input size {tuple(x_f32.shape)}")
     x = ops.split(x_f32, want_T=True)
     saved, out = [], None
     for lin, bn in layers:

@@ -401,3 +401,20 @@ def test_training_under_autocast_and_gradscaler_like_the_trainer():
     noisy, _ = model(sequence_embeddings=P_f, label_embeddings=L_f, label_token_counts=torch.ones(50, device="cuda"))
     clean, _ = model(sequence_embeddings=P_f, label_embeddings=L_f)
     assert float((noisy - clean).abs().max()) > 1e-3
+
+
+@pytest.mark.parametrize("B,L", [(1, 1), (2, 3), (1, 130), (9, 1), (2, 2)])
+def test_training_step_degenerate_shapes(B, L):
+    """Tiny pair grids (a 64x64 tile holds a couple of rows).  A BatchNorm that would see a single row raises ValueError,
+    exactly as torch.nn.BatchNorm1d does inside the reference's W_p (one protein) or W_l (one label row)."""
+    ecfg, scfg, *_ = CASES["tiny_concat"]
+    if min(B, L) < 2:
+        model = build_b200_model(ecfg, scfg, synth_state_dict(ecfg, scfg, seed=42, calib_T=64), device="cuda").train()
+        with pytest.raises(ValueError, match="Expected more than 1 value per channel"):
+            model(sequence_embeddings=torch.randn(B, 72).cuda(), label_embeddings=torch.randn(L, 40).cuda())
+        return
+    model, logits, loss, o_logits, o_loss, o_grads, _ = _step((ecfg, scfg, 42), B, L, "strict", 100 + B + L)
+    # BatchNorm over two or three rows amplifies rounding by up to 1/sqrt(eps): finite, and close where it is well-posed
+    assert logits.shape == o_logits.shape and torch.isfinite(logits).all()
+    assert all(torch.isfinite(p.grad).all() for p in model.parameters() if p.grad is not None)
+    assert float((logits - o_logits).abs().max()) < 5e-2

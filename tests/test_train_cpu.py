@@ -174,3 +174,12 @@ def test_training_path_refuses_what_it_does_not_implement():
         cpu_model(sequence_embeddings=P_f, label_embeddings=L_f)
     with pytest.raises(ValueError):
         cpu_model(sequence_embeddings=P_f)
+
+
+def test_single_row_batchnorm_raises_like_torch():
+    ecfg, scfg, sd, P_f, L_f, y = _problem()
+    model = build_b200_model(ecfg, scfg, sd, device="cpu").double().train()
+    with pytest.raises(ValueError, match="Expected more than 1 value per channel"):
+        pn_train.forward_train(TorchOps(torch.float64), None, model, P_f[:1].double(), L_f.double())
+    with pytest.raises(ValueError, match="Expected more than 1 value per channel"):
+        pn_train.forward_train(TorchOps(torch.float64), None, model, P_f.double(), L_f[:1].double())
