@@ -2,7 +2,7 @@
 the library-kernel number SURVEY.md section 8(d) asks to beat.  The model is the oracle restatement of the reference
 forward (oracle/protnote_oracle.py, test infrastructure) moved to the GPU; fp32 with TF32 off, fp32 with TF32 on, and
 under torch.autocast(fp16) as ProtNoteTrainer.evaluation_step runs it (ProtNoteTrainer.py:287).
-Usage (GPU box): python tools/torch_gpu_baseline.py [sequences] [labels]"""
+Usage (GPU box): python tests/probes/torch_gpu_baseline.py [sequences] [labels]"""
 import json
 import sys
 import time

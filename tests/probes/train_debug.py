@@ -1,6 +1,6 @@
 """GPU probe: runs one training step with the CUDA primitives and with their fp64 torch statement side by side and prints,
 call by call, how far each primitive's output is from the fp64 one (relative to the tensor's largest entry).
-Usage (GPU box): python tools/train_debug.py [case] [B] [L] [precision]"""
+Usage (GPU box): python tests/probes/train_debug.py [case] [B] [L] [precision]"""
 import sys
 
 import torch

@@ -209,7 +209,7 @@ def _step(case_cfg, B, L, precision, seed):
 def _check_grads(model, o_grads, fp32_grads):
     """strict mode is fp32-grade: every gradient entry within 1e-4 of the tensor's largest entry.
     The gradient of a ReLU network is discontinuous in the pre-activations: a pre-activation within rounding distance of
-    zero flips its mask under ANY change of summation order.  tools/train_debug.py shows every primitive of the step
+    zero flips its mask under ANY change of summation order.  tests/probes/train_debug.py shows every primitive of the step
     within ~1e-6 of fp64 until the first BatchNorm-backward whose 768 x 3072 pre-activations (rounded to ~8e-7) contain a
     handful of such elements; one flip moves a column sum by 1/rows and everything downstream by ~1e-4 relative.  The
     kernels themselves are pinned flip-free by the per-primitive tests above (same plane values on both sides); for the
