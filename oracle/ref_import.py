@@ -18,7 +18,21 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("PROTNOTE_REFERENCE_ROOT", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def _default_root() -> str:
+    """/root/reference in the build container; the copy staged by oracle/build_ref.py (oracle/_ref, git-ignored, travels
+    with the gpurun snapshot) on the GPU box."""
+    env = os.environ.get("PROTNOTE_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isdir(os.path.join("/root/reference", "protnote", "models")):
+        return "/root/reference"
+    return _STAGED
+
+
+REFERENCE_ROOT = _default_root()
 
 _STUBS = (
     "loralib",

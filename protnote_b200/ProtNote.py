@@ -165,7 +165,7 @@ class ProtNote(nn.Module):
 
     def _ensure_packed(self):
         srcs = self._pack_sources()
-        key = _versions(srcs) + (self.feature_fusion, self.inference_descriptions_per_label)
+        key = _versions(srcs) + (self.feature_fusion, self.inference_descriptions_per_label, native.options_epoch())
         if self._packed is None or key != self._packed_key:
             own = [self.W_p, self.W_l] + ([self.output_layer] if hasattr(self, "output_layer") else [])
             bn_eps = next((m.eps for part in own for m in part.modules() if isinstance(m, nn.BatchNorm1d)), 1e-5)
@@ -186,20 +186,33 @@ class ProtNote(nn.Module):
         return out
 
     # ------------------------------------------------------------------ label-projection cache on disk
+    @staticmethod
+    def _digest(t):
+        """Order-sensitive device-side checksum of a tensor: plain sum, sum of magnitudes and a sum weighted by a fixed
+        pseudo-random function of the element POSITION (a permutation of rows, columns or entries changes it)."""
+        v = t.detach().double().flatten()
+        idx = torch.arange(v.numel(), dtype=torch.int64, device=v.device)
+        w = ((idx * 2654435761) & 0xFFFFFFFF).double() / 4294967296.0 + 0.5
+        return [float(v.sum()), float(v.abs().sum()), float((v * w).sum())]
+
     def _label_fingerprint(self, L_f):
-        """What the projected label halves depend on: W_l, layer 1 of the output MLP (+ its BatchNorm), the label
-        embeddings themselves and the arithmetic mode - as cheap device-side checksums."""
+        """What the projected label halves depend on: W_l, layer 1 of the output MLP (+ its BatchNorm, incl. eps), the
+        label embeddings themselves IN ORDER (rows are labels: a re-sorted vocabulary must not match), the number of
+        descriptions per label and the arithmetic mode."""
         parts = list(self._head_sources(self.W_l))
+        eps = [m.eps for m in self.W_l.modules() if isinstance(m, nn.BatchNorm1d)]
         if self.feature_fusion != "similarity":
             mods = list(self.output_layer)
             parts.append(mods[0].weight)
             if isinstance(mods[1], nn.BatchNorm1d):
                 parts += [mods[1].weight, mods[1].bias, mods[1].running_mean, mods[1].running_var]
+                eps.append(mods[1].eps)
             elif mods[0].bias is not None:
                 parts.append(mods[0].bias)
-        sums = [float(t.detach().double().sum()) for t in parts] + [float(t.detach().double().abs().sum()) for t in parts]
-        return {"weights": sums, "labels": [float(L_f.double().sum()), float(L_f.double().abs().sum())],
-                "label_shape": list(L_f.shape), "precision": self.precision, "fusion": self.feature_fusion}
+        sums = [x for t in parts for x in self._digest(t)]
+        return {"weights": sums, "labels": self._digest(L_f), "label_shape": list(L_f.shape), "precision": self.precision,
+                "fusion": self.feature_fusion, "bn_eps": [float(e) for e in eps],
+                "descriptions_per_label": int(self.inference_descriptions_per_label)}
 
     def save_label_projection(self, path, label_embeddings):
         """Runs W_l and the label half of output layer 1 once for `label_embeddings` [L, label_dim] and stores the result
@@ -225,10 +238,12 @@ class ProtNote(nn.Module):
         want = self._label_fingerprint(L_f)
         got = blob["fingerprint"]
         same = (got["label_shape"] == want["label_shape"] and got["precision"] == want["precision"]
-                and got["fusion"] == want["fusion"]
+                and got["fusion"] == want["fusion"] and got.get("bn_eps") == want["bn_eps"]
+                and got.get("descriptions_per_label") == want["descriptions_per_label"]
+                and len(got["weights"]) == len(want["weights"]) and len(got["labels"]) == len(want["labels"])
                 and all(abs(a - b) <= 1e-9 * max(1.0, abs(b)) for a, b in zip(got["weights"] + got["labels"],
                                                                                 want["weights"] + want["labels"])))
-        if not same or len(got["weights"]) != len(want["weights"]):
+        if not same:
             raise ProtnoteB200Error("stored label projection does not match this model / these label embeddings")
         self._ensure_packed()
         mode = native.MODES[self.precision]

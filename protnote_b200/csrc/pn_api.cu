@@ -41,8 +41,16 @@ int g_stats_tx = 32;
 // 1e-4).  The parity margin is worth more than 0.75 % of the headline step: off by default.
 int g_split_corr = 0;
 // strict mode: K elements accumulated in TMEM between fp32 promotions, per stage of the path
-enum { kStageEncoder = 0, kStageHeads = 1, kStageScorer = 2, kStageOther = 3 };
-int g_promote_k[4] = {32, 32, 256, 64};
+// (kStagePointwise: the 1x1 convolutions of the encoder's residual blocks, K = bottleneck width)
+enum { kStageEncoder = 0, kStageHeads = 1, kStageScorer = 2, kStageOther = 3, kStagePointwise = 4, kNumStages = 5 };
+int g_promote_k[kNumStages] = {32, 32, 256, 64, 32};
+// strict mode: compensation of the accumulator's round-toward-zero bias (GemmParams::trunc_comp).  The factor applied to a
+// launch is (c1 * K-elements per chunk + c0) * 1e-12; both coefficients are hardware properties measured with
+// tools/trunc_comp_probe.py.  c1 == 0 and c0 == 0 switch the compensation off.
+long long g_trunc_c1 = 0, g_trunc_c0 = 0;
+// strict mode: per-K-position compensation folded into the packed weights (pack_weight_kernel, TruncComp), in units of
+// 1e-12 per truncating add.  Weights must be re-packed after this or a promote_k / bk option changes.
+long long g_trunc_beta_ppt = 33000;
 
 // optional per-launch CUDA-event timing of the pair scorer's GEMM launches (bench.py's roofline numbers)
 struct TimedLaunch {
@@ -168,6 +176,17 @@ int tiles_n_for(long long N) { return (int)((N + choose_bn(N) - 1) / choose_bn(N
 int pick_bk(int mode) {
   if (g_bk_option == 32 || g_bk_option == 64) return g_bk_option;
   return mode == PN_STRICT ? 32 : 64;
+}
+
+// k-blocks per accumulator chunk of a strict-mode launch of stage `stage_kind` (launch_gemm and pack_linear must agree)
+int strict_chunk_kblocks(int stage_kind, int bk, int num_kblocks, int promote_override = -1) {
+  const int promote_k = promote_override >= 0 ? promote_override : g_promote_k[stage_kind];
+  int chunk = num_kblocks;
+  if (promote_k > 0) {
+    chunk = promote_k / bk > 0 ? promote_k / bk : 1;
+    if (chunk > num_kblocks) chunk = num_kblocks;
+  }
+  return chunk;
 }
 
 int g_num_sms = 0;
@@ -296,16 +315,18 @@ int launch_gemm(const Planes& A, const ConvView& cv, const Planes& B, long long 
   // promote_override > 0 forces a promotion period in either mode (wgrad: K = rows of the batch, far too long a chain
   // for the truncating tensor-core accumulator even at fp16 operand precision)
   const int promote_k = promote_override >= 0 ? promote_override : g_promote_k[stage_kind];
-  if ((mode == PN_STRICT || promote_override > 0) && promote_k > 0) {
-    p.chunk_kblocks = promote_k / bk > 0 ? promote_k / bk : 1;
-    if (p.chunk_kblocks > p.num_kblocks) p.chunk_kblocks = p.num_kblocks;
-  }
+  if (mode == PN_STRICT || promote_override > 0) p.chunk_kblocks = strict_chunk_kblocks(stage_kind, bk, p.num_kblocks, promote_override);
   if (g_split_corr && mode == PN_STRICT && stage_kind == kStageEncoder && !gen && !cta2 && bk == 32 && promote_override < 0) {
     // main chain: 2 truncating adds per k-block instead of 6 -> twice the K per promotion at fewer adds per chunk (4 vs 6)
     p.split_corr = 1;
     p.chunk_kblocks = 2 * promote_k / bk > 0 ? 2 * promote_k / bk : 1;
     if (p.chunk_kblocks > 3) p.chunk_kblocks = 3;      // the chunk's operand stages stay resident: < pipeline depth (4)
     if (p.chunk_kblocks > p.num_kblocks) p.chunk_kblocks = p.num_kblocks;
+  }
+  if (mode == PN_STRICT && !p.split_corr && (g_trunc_c1 != 0 || g_trunc_c0 != 0)) {
+    const double kc = (double)p.chunk_kblocks * bk;
+    const double f = ((double)g_trunc_c1 * kc + (double)g_trunc_c0) * 1e-12;
+    p.trunc_comp = f > 0 ? (float)f : 0.f;
   }
   if (B.kblocked) {
     const cuuint64_t dims[3] = {64, (cuuint64_t)B.rows, (cuuint64_t)((B.cols + 63) / 64)};
@@ -417,7 +438,14 @@ Planes weight_planes(const Arena& ar, const PackedLinear& pl) {
 // is not needed: concatenation_diff is folded by two packs into separate buffers (see pack_scorer).
 int pack_linear(const Arena& ar, const PackedLinear& pl, const float* w, long long sn, long long sc, long long st,
                 long long span, const float* bias, const float* gamma, const float* beta, const float* mean,
-                const float* var, float eps, cudaStream_t stream) {
+                const float* var, float eps, cudaStream_t stream, int stage_kind) {
+  // the K walk the strict-mode engine will use for this layer (see launch_gemm)
+  TruncComp tc;
+  tc.bk = pick_bk(PN_STRICT);
+  tc.cblocks = (pl.cin + tc.bk - 1) / tc.bk;
+  tc.num_kblocks = pl.taps * tc.cblocks;
+  tc.chunk_kblocks = strict_chunk_kblocks(stage_kind, tc.bk, tc.num_kblocks);
+  tc.beta = (float)((double)g_trunc_beta_ppt * 1e-12);
   unsigned* am = ar.at<unsigned>(pl.absmax);
   PN_CUDA(cudaMemsetAsync(am, 0, 4, stream));
   // absmax over the rows' used span (row n covers w[n*sn .. n*sn + span))
@@ -426,7 +454,7 @@ int pack_linear(const Arena& ar, const PackedLinear& pl, const float* w, long lo
   PN_CUDA(cudaGetLastError());
   pack_weight_kernel<<<ew_grid((long long)pl.N * pl.ld), 256, 0, stream>>>(
       w, pl.N, pl.cin, pl.taps, sn, sc, st, pl.cpad, pl.ld, am, ar.at<float>(pl.wscale), ar.at<__half>(pl.hi),
-      ar.at<__half>(pl.lo));
+      ar.at<__half>(pl.lo), tc);
   g_launches++;
   PN_CUDA(cudaGetLastError());
   fold_affine_kernel<<<(pl.N + 255) / 256, 256, 0, stream>>>(pl.N, bias, gamma, beta, mean, var, eps,
@@ -751,16 +779,33 @@ int pn_set_option(const char* name, long long value) {
     if (value < 0) return fail("promote_k must be >= 0 (0 = never promote)");
     const char* which = name + 9;
     if (*which == 0) {
-      for (int i = 0; i < 4; ++i) g_promote_k[i] = (int)value;
+      for (int i = 0; i < kNumStages; ++i) g_promote_k[i] = (int)value;
     } else if (strcmp(which, "_encoder") == 0) {
       g_promote_k[kStageEncoder] = (int)value;
     } else if (strcmp(which, "_heads") == 0) {
       g_promote_k[kStageHeads] = (int)value;
     } else if (strcmp(which, "_scorer") == 0) {
       g_promote_k[kStageScorer] = (int)value;
+    } else if (strcmp(which, "_other") == 0) {
+      g_promote_k[kStageOther] = (int)value;
+    } else if (strcmp(which, "_pointwise") == 0) {
+      g_promote_k[kStagePointwise] = (int)value;
     } else {
       return fail("unknown option '%s'", name);
     }
+    return 0;
+  }
+  if (strcmp(name, "trunc_beta_ppt") == 0) {
+    if (value < 0) return fail("trunc_beta_ppt must be >= 0");
+    g_trunc_beta_ppt = value;
+    return 0;
+  }
+  if (strcmp(name, "trunc_comp_c1") == 0) {
+    g_trunc_c1 = value;
+    return 0;
+  }
+  if (strcmp(name, "trunc_comp_c0") == 0) {
+    g_trunc_c0 = value;
     return 0;
   }
   if (strcmp(name, "cta2") == 0) {
@@ -819,7 +864,7 @@ static int encoder_pack_impl(const pn_encoder_cfg* cfg, const float* const* para
   const int k = c.kernel_size;
   // conv1 (C, Cin, k) + bias; no BatchNorm behind it
   PN_TRY(pack_linear(pk, L.conv1, params[0], (long long)c.input_channels * k, k, 1, (long long)c.input_channels * k,
-                     params[1], nullptr, nullptr, nullptr, nullptr, 0.f, stream));
+                     params[1], nullptr, nullptr, nullptr, nullptr, 0.f, stream, kStageEncoder));
   for (int i = 0; i < c.num_blocks; ++i) {
     const float* const* q = params + 2 + 12 * i;
     const EncoderLayout::Block& b = L.blocks[i];
@@ -833,10 +878,10 @@ static int encoder_pack_impl(const pn_encoder_cfg* cfg, const float* const* para
     // (training mode uses batch statistics: fold_bn == false keeps only the conv bias in the epilogue)
     PN_TRY(pack_linear(pk, b.conv_d, q[4], (long long)c.channels * k, k, 1, (long long)c.channels * k, q[5],
                        fold_bn ? q[6] : nullptr, fold_bn ? q[7] : nullptr, fold_bn ? q[8] : nullptr,
-                       fold_bn ? q[9] : nullptr, c.bn_eps, stream));
+                       fold_bn ? q[9] : nullptr, c.bn_eps, stream, kStageEncoder));
     // pointwise conv (C, Cb, 1) + bias
     PN_TRY(pack_linear(pk, b.conv_p, q[10], c.bottleneck, 1, 0, c.bottleneck, q[11], nullptr, nullptr, nullptr, nullptr,
-                       0.f, stream));
+                       0.f, stream, kStagePointwise));
   }
   return 0;
 }
@@ -941,7 +986,7 @@ static int encoder_forward_impl(const pn_encoder_cfg* cfg, const void* packed, c
           e.relu = 1;
           e.out_hi = ws.at<__half>(W.act_hi); e.out_lo = ws.at<__half>(W.act_lo); e.ld_split = W.ldc;
         }
-        PN_TRY(launch_gemm(A, cv, weight_planes(pk, b.conv_p), c.channels, e, mode, stream, kStageEncoder));
+        PN_TRY(launch_gemm(A, cv, weight_planes(pk, b.conv_p), c.channels, e, mode, stream, kStagePointwise));
       }
       dil *= c.dilation_base;
       if (dil > (1 << 24)) return fail("dilation overflow");
@@ -1064,7 +1109,7 @@ int pn_encoder_forward_train(const pn_encoder_cfg* cfg, const void* packed_raw, 
       e.scale = pk.at<float>(b.conv_p.scale); e.shift = pk.at<float>(b.conv_p.shift);
       e.resid = X; e.ld_resid = W.ldc;
       e.out_f32 = X; e.ld_out = W.ldc;
-      PN_TRY(launch_gemm(A, cv, weight_planes(pk, b.conv_p), c.channels, e, mode, stream, kStageEncoder));
+      PN_TRY(launch_gemm(A, cv, weight_planes(pk, b.conv_p), c.channels, e, mode, stream, kStagePointwise));
     }
     dil *= c.dilation_base;
     if (dil > (1 << 24)) return fail("dilation overflow");
@@ -1109,7 +1154,7 @@ int pn_scorer_pack(const pn_scorer_cfg* cfg, const float* const* params, int num
       if (!last) {
         g = *q++; bt = *q++; mu = *q++; var = *q++;
       }
-      PN_TRY(pack_linear(pk, H[i], w, H[i].cin, 1, 0, H[i].cin, nullptr, g, bt, mu, var, c.bn_eps, stream));
+      PN_TRY(pack_linear(pk, H[i], w, H[i].cin, 1, 0, H[i].cin, nullptr, g, bt, mu, var, c.bn_eps, stream, kStageHeads));
     }
   }
   if (c.fusion == PN_FUSION_SIMILARITY) return 0;
@@ -1142,10 +1187,11 @@ int pn_scorer_pack(const pn_scorer_cfg* cfg, const float* const* params, int num
       src_ld = d;
     }
     // scale = BN1 scale / wscale on every part; the shift (bias, mean, beta) goes to the protein side only
-    PN_TRY(pack_linear(pk, L.l1_p, wp_src, src_ld, 1, 0, d, bias, g, bt, mu, var, c.bn_eps, stream));
-    PN_TRY(pack_linear(pk, L.l1_l, wl_src, src_ld, 1, 0, d, nullptr, g, nullptr, nullptr, var, c.bn_eps, stream));
+    PN_TRY(pack_linear(pk, L.l1_p, wp_src, src_ld, 1, 0, d, bias, g, bt, mu, var, c.bn_eps, stream, kStageHeads));
+    PN_TRY(pack_linear(pk, L.l1_l, wl_src, src_ld, 1, 0, d, nullptr, g, nullptr, nullptr, var, c.bn_eps, stream, kStageHeads));
     if (c.fusion == PN_FUSION_CONCAT_PROD)
-      PN_TRY(pack_linear(pk, L.l1_x, w + 2 * d, src_ld, 1, 0, d, nullptr, g, nullptr, nullptr, var, c.bn_eps, stream));
+      PN_TRY(pack_linear(pk, L.l1_x, w + 2 * d, src_ld, 1, 0, d, nullptr, g, nullptr, nullptr, var, c.bn_eps, stream,
+                         kStageScorer));
     copy_floats_kernel<<<(c.out_hidden + 255) / 256, 256, 0, stream>>>(pk.at<float>(L.l1_p.shift), pk.at<float>(L.l1_shift),
                                                                        c.out_hidden);
     g_launches++;
@@ -1159,7 +1205,8 @@ int pn_scorer_pack(const pn_scorer_cfg* cfg, const float* const* params, int num
     } else {
       bias = *q++;
     }
-    PN_TRY(pack_linear(pk, L.hidden[j], w, c.out_hidden, 1, 0, c.out_hidden, bias, g, bt, mu, var, c.bn_eps, stream));
+    PN_TRY(pack_linear(pk, L.hidden[j], w, c.out_hidden, 1, 0, c.out_hidden, bias, g, bt, mu, var, c.bn_eps, stream,
+                       kStageScorer));
   }
   copy_floats_kernel<<<(c.out_hidden + 255) / 256, 256, 0, stream>>>(*q++, pk.at<float>(L.w_out), c.out_hidden);
   copy_floats_kernel<<<1, 32, 0, stream>>>(*q++, pk.at<float>(L.b_out), 1);
@@ -1403,7 +1450,7 @@ int pn_linear(const float* x, long long M, long long K, long long ldx, const flo
   split_rows_kernel<<<ew_grid(M * (ld / 8)), 256, 0, stream>>>(x, M, (int)K, ldx, a_hi, a_lo, ld);
   g_launches++;
   PN_CUDA(cudaGetLastError());
-  PN_TRY(pack_linear(ws, pl, w, K, 1, 0, K, bias, nullptr, nullptr, nullptr, nullptr, 0.f, stream));
+  PN_TRY(pack_linear(ws, pl, w, K, 1, 0, K, bias, nullptr, nullptr, nullptr, nullptr, 0.f, stream, kStageOther));
   Planes A;
   A.hi = a_hi; A.lo = a_lo; A.rows = M; A.cols = K; A.ld = ld;
   Epilogue e;
@@ -1436,7 +1483,7 @@ int pn_conv1d(const float* x, const int64_t* lengths, int batch, int cin, int T,
   g_launches++;
   PN_CUDA(cudaGetLastError());
   PN_TRY(pack_linear(ws, pl, w, (long long)cin * taps, taps, 1, (long long)cin * taps, bias, nullptr, nullptr, nullptr,
-                     nullptr, 0.f, stream));
+                     nullptr, 0.f, stream, kStageOther));
   Planes A;
   A.hi = a_hi; A.lo = a_lo; A.rows = pos; A.cols = cin; A.ld = cpad;
   ConvView cv;
@@ -1514,7 +1561,8 @@ int pn_t_pack_weight(const float* w, long long N, long long K, long long stride_
   g_launches++;
   PN_CUDA(cudaGetLastError());
   pack_weight_kernel<<<ew_grid(N * ld), 256, 0, stream>>>(w, (int)N, (int)K, 1, stride_n, stride_k, 0, (int)ld, (int)ld, am,
-                                                          ws, static_cast<__half*>(hi), static_cast<__half*>(lo));
+                                                          ws, static_cast<__half*>(hi), static_cast<__half*>(lo),
+                                                          TruncComp{16, 1, 1, 1, 0.f});
   g_launches++;
   PN_CUDA(cudaGetLastError());
   return 0;

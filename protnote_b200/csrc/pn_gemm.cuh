@@ -69,6 +69,11 @@ struct alignas(64) GemmParams {
   // overlaps the correction MMAs of the same chunk, so the tensor core never waits for a drain.  Needs
   // chunk_kblocks < pipeline stages (the chunk's operand stages stay resident until its corrections are issued).
   int split_corr;
+  // strict mode: the tcgen05 accumulator add rounds toward zero, so a chunk's sum comes out short by a factor that is
+  // proportional to the number of truncating adds of the chunk (measured: profiles/r02_trunc_comp_probe.txt).  The
+  // promoted total is multiplied by (1 + trunc_comp) before the epilogue, which removes the mean of that bias; what is
+  // left is zero-mean and uncorrelated between outputs, like round-to-nearest noise.  0 = off.
+  float trunc_comp;
   const long long* lengths;      // [B] valid positions per sequence (conv) or nullptr
   // pair-row addressing for the additive row terms: row r -> (r / pair_nl, r % pair_nl)
   int pair_nl;
@@ -734,6 +739,12 @@ __global__ void __launch_bounds__(GEN ? kGenThreads : kGemmThreads, 1) gemm_kern
             }
           }
         }
+      }
+      if (p.trunc_comp != 0.f) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sums[g][j] = fmaf(sums[g][j], p.trunc_comp, sums[g][j]);
       }
       float dot = 0.f;
 #pragma unroll

@@ -343,6 +343,12 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
           }
         }
       }
+      if (p.trunc_comp != 0.f) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sums[g][j] = fmaf(sums[g][j], p.trunc_comp, sums[g][j]);
+      }
       float dot = 0.f;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {

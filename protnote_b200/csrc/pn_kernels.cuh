@@ -34,22 +34,51 @@ __device__ __forceinline__ float weight_scale_from_absmax(unsigned bits) {
   return ldexpf(1.f, 8 - e);
 }
 
-// dst[n][tap*cpad + c] = split(w[n*sn + c*sc + tap*st] * s) ; zero elsewhere in [0, ld)
+// How the strict-mode engine will walk a packed weight row (the K loop of gemm_kernel): k-blocks of `bk` elements,
+// `cblocks` per tap, accumulator chunks of `chunk_kblocks` k-blocks.  beta == 0 -> no compensation.
+struct TruncComp {
+  int bk, cblocks, chunk_kblocks, num_kblocks;
+  float beta;
+};
+
+// dst[n][tap*cpad + c] = split(w[n*sn + c*sc + tap*st] * s * (1 + beta * r)) ; zero elsewhere in [0, ld)
 // Linear (out,in):         taps=1, sn=in, sc=1, st=0, cin=in, cpad=ld
 // Conv1d (out,in,k):       taps=k, sn=in*k, sc=k, st=1
+//
+// Truncation compensation.  Every tcgen05 accumulator add rounds the running sum toward zero, i.e. shrinks it by a factor
+// (1 - beta) on average (beta = 3.3e-8 measured on B200, tools/trunc_comp_probe.py).  A product that enters the
+// accumulator r adds before the chunk is promoted to fp32 registers therefore arrives scaled by (1 - beta)^r: the engine
+// computes, in expectation, the dot product with weights w[k] * (1 - beta * r(k)), a deterministic sawtooth along K that
+// is the same for every output row and does not average out downstream.  r(k) is known at pack time (strict-mode issue
+// order inside a k-block: all lo*hi / hi*lo products first, then the hi*hi products, one MMA per 16 K-elements), so the
+// weight is pre-multiplied by (1 + beta * r(k)).  What remains of the truncation is zero-mean noise of the size of
+// round-to-nearest noise.
 __global__ void pack_weight_kernel(const float* __restrict__ w, int N, int cin, int taps, long long sn, long long sc,
                                    long long st, int cpad, int ld, const unsigned* __restrict__ absmax,
-                                   float* __restrict__ scale_out, __half* __restrict__ hi, __half* __restrict__ lo) {
+                                   float* __restrict__ scale_out, __half* __restrict__ hi, __half* __restrict__ lo,
+                                   TruncComp tc) {
   const float s = weight_scale_from_absmax(*absmax);
   if (blockIdx.x == 0 && threadIdx.x == 0) *scale_out = s;
   const long long total = (long long)N * ld;
+  const int steps = tc.bk / 16;   // MMAs per pass per k-block
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int n = (int)(i / ld);
     const int k = (int)(i % ld);
     const int tap = k / cpad, c = k % cpad;
     float v = 0.f;
-    if (tap < taps && c < cin) v = w[n * sn + c * sc + tap * st] * s;
+    if (tap < taps && c < cin) {
+      v = w[n * sn + c * sc + tap * st] * s;
+      if (tc.beta != 0.f) {
+        const int kb = tap * tc.cblocks + c / tc.bk;
+        const int chunk0 = kb / tc.chunk_kblocks * tc.chunk_kblocks;
+        const int nc = min(tc.chunk_kblocks, tc.num_kblocks - chunk0);
+        const int q = kb - chunk0;
+        const int ks = (c % tc.bk) / 16;
+        const int r = 3 * steps * (nc - q) - 2 * steps - ks;   // adds from this product's own add to the end of the chunk
+        v = fmaf(v, tc.beta * (float)r, v);
+      }
+    }
     __half h, l;
     split_f16(v, h, l);
     hi[i] = h;

@@ -15,18 +15,22 @@ from ._lib import PN_FAST, PN_STRICT, EncoderCfg, ScorerCfg, check, pointer_arra
 
 MODES = {"strict": PN_STRICT, "fast": PN_FAST}
 
-# scratch memory is cached per (device, purpose) and only ever grows: the caching allocator would do the same,
-# but keeping one buffer makes the pointers stable for CUDA-graph capture.
+# Scratch memory is cached per (device, CUDA stream, purpose) and only ever grows.  A buffer is only ever handed to work
+# queued on the stream it is keyed by, so two streams (or two models driven from two threads on their own streams) never
+# share scratch, and a buffer that is replaced by a larger one is released on the stream that last used it (the caching
+# allocator's stream ordering then keeps it alive until the kernels already queued on that stream have run).  Pointers
+# stay stable per stream, which is what CUDA-graph capture needs.
 _scratch = {}
 
 
 def scratch(device: torch.device, key: str, nbytes: int) -> torch.Tensor:
-    k = (device.index, key)
+    k = (device.index, torch.cuda.current_stream(device).cuda_stream, key)
     buf = _scratch.get(k)
     if buf is None or buf.numel() < nbytes:
         buf = None
         _scratch.pop(k, None)
-        buf = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        with torch.cuda.device(device):
+            buf = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
         _scratch[k] = buf
     return buf
 
@@ -47,8 +51,20 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
     return t.contiguous()
 
 
+_options_epoch = 0
+
+
 def set_option(name: str, value: int):
+    """Engine options are process-global (include/protnote_b200.h).  Packed weights depend on some of them (the
+    truncation compensation follows the promotion period), so every change bumps an epoch that the modules fold into
+    their pack keys: the next forward re-packs."""
+    global _options_epoch
     check(_lib.load().pn_set_option(name.encode(), int(value)))
+    _options_epoch += 1
+
+
+def options_epoch() -> int:
+    return _options_epoch
 
 
 def _apply_env_options():

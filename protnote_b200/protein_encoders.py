@@ -88,7 +88,7 @@ class ProteInfer(torch.nn.Module):
 
     def _ensure_packed(self):
         srcs = self._pack_sources()
-        key = _versions(srcs)
+        key = _versions(srcs) + (native.options_epoch(),)
         if self._packed is not None and self._packed_key is None:      # invalidated by a training-mode forward
             self._packed.pack(srcs)
             self._packed_key = key
@@ -124,7 +124,8 @@ class ProteInfer(torch.nn.Module):
         convs = [self.conv1.weight, self.conv1.bias]
         for blk in self.resnet_blocks:
             convs += [blk.masked_conv1.weight, blk.masked_conv1.bias, blk.masked_conv2.weight, blk.masked_conv2.bias]
-        key = _versions(convs)      # the raw pack holds conv weights only: running-statistic updates do not invalidate it
+        # the raw pack holds conv weights only: running-statistic updates do not invalidate it
+        key = _versions(convs) + (native.options_epoch(),)
         if getattr(self, "_raw_key", None) != key or getattr(enc, "packed_raw", None) is None:
             enc.pack_raw(self._pack_sources())
             self._raw_key = key
@@ -152,7 +153,15 @@ class ProteInfer(torch.nn.Module):
         if self.training:
             raise ProtnoteB200Error("the sm_100a encoder implements eval-mode BatchNorm only; call .eval()")
         dev = self.conv1.weight.device
-        tokens = tokens.to(torch.uint8) if not tokens.is_cuda and tokens.dtype != torch.uint8 else tokens
+        if tokens.dtype != torch.uint8:
+            # range-check BEFORE narrowing (a -1 padding id or an id >= 256 must not wrap into a valid residue); CPU
+            # tensors are narrowed here so that one byte per residue crosses PCIe, CUDA tensors inside native
+            if tokens.is_floating_point() or tokens.dtype == torch.bool:
+                raise ValueError("token ids must be integers in [0, 255]")
+            if not tokens.is_cuda:
+                if tokens.numel() and (int(tokens.min()) < 0 or int(tokens.max()) > 255):
+                    raise ValueError("token ids must be integers in [0, 255]")
+                tokens = tokens.to(torch.uint8)
         return self._ensure_packed().forward_tokens(tokens.to(dev, non_blocking=True),
                                                     sequence_lengths.to(dev, non_blocking=True),
                                                     native.MODES[self.precision])

@@ -230,6 +230,12 @@ def forward_train(ops, comm, model, P_f, L_f, L_total: Optional[int] = None, upd
             for m in part.modules():
                 if isinstance(m, nn.BatchNorm1d) and m.num_batches_tracked is not None:
                     m.num_batches_tracked += 1
+        # the kernels updated the running statistics through raw pointers (torch's version counters did not move):
+        # the eval-mode weight pack, which folds them, and the cached label projection are stale from here on
+        if hasattr(model, "_packed_key"):
+            model._packed_key = None
+        if hasattr(model, "_label_cache"):
+            model._label_cache = None
     return logits.reshape(B, L_f.shape[0]), ctx
 
 

@@ -7,9 +7,20 @@ from oracle import protnote_oracle as O  # noqa: E402
 from tests.helpers import build_b200_model, load_case  # noqa: E402
 
 torch.set_num_threads(8)
-names = [a for a in sys.argv[1:] if not a.startswith("promote=")] or list(CASES)
+names = [a for a in sys.argv[1:] if "=" not in a] or list(CASES)
 promote = [tuple(int(v) for v in a.split("=")[1].split(",")) for a in sys.argv[1:] if a.startswith("promote=")] or [(32, 32, 64)]
 from protnote_b200 import native  # noqa: E402
+# beta=<ppt>: per-K-position truncation compensation folded into the packed weights (engine option trunc_beta_ppt)
+# comp=c1,c0 (ppt): uniform epilogue compensation (engine options trunc_comp_c1 / trunc_comp_c0)
+for a in sys.argv[1:]:
+    if a.startswith("beta="):
+        native.set_option("trunc_beta_ppt", int(a.split("=")[1]))
+        print(f"######## per-K-position truncation compensation beta = {a.split('=')[1]} ppt")
+    if a.startswith("comp="):
+        c1, c0 = (int(t) for t in a.split("=", 1)[1].split(","))
+        native.set_option("trunc_comp_c1", c1)
+        native.set_option("trunc_comp_c0", c0)
+        print(f"######## uniform truncation compensation ({c1} * K_chunk + {c0}) ppt")
 torch.backends.cuda.matmul.allow_tf32 = False
 torch.backends.cudnn.allow_tf32 = False
 for name in names:

@@ -8,8 +8,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_reference_arm_prints_one_json_line_with_the_contract_keys():
+    env = dict(os.environ, OMP_NUM_THREADS="1")
     res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
-                         capture_output=True, text=True, cwd=ROOT, timeout=600)
+                         capture_output=True, text=True, cwd=ROOT, timeout=600, env=env)
     assert res.returncode == 0, res.stderr[-2000:]
     lines = [ln for ln in res.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1, res.stdout
@@ -20,7 +21,10 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert d["impl"] == "reference" and d["unit"] == "pair-scores/s" and d["higher_is_better"] is True
     assert d["vs_baseline"] is None and d["data"] == "synthetic"
     assert "workload" in d["config"] and "BASELINE.json configs[1]" in d["config"]["workload"]
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["value"] == d["value"]
+    # every host core is used even when the launcher exports OMP_NUM_THREADS=1 (torch.distributed.run does)
+    assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0)) == d["cpu_baseline"]["threads"]
+    assert d["cpu_baseline"]["extrapolated"] is True and "extrapolated" in d["cpu_baseline"]["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["value"] > 0
 
