@@ -176,6 +176,57 @@ __device__ __forceinline__ void store_halves_coalesced(const uint32_t (&v)[16], 
   __syncwarp();
 }
 
+// A warp's 32 rows x 32 fp32 columns <-> global memory, 16 columns (64 bytes of every row) at a time through the same
+// staging block: four consecutive lanes move 64 contiguous bytes of one row, so one warp instruction touches 8 rows
+// instead of 32 (a row-per-thread float4 access is 32 separate 16-byte pieces: 4x the L1 tag cycles, and on the store
+// side 32 partial sectors).  `v` is this thread's row (lane = row); the load ADDS the block to it.
+__device__ __forceinline__ void add_f32_coalesced(float (&v)[32], uint8_t* stage, const float* row0_ptr, long long ld,
+                                                   uint32_t row_mask, int lane) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int rr = it * 8 + (lane >> 2);
+      const int ch = lane & 3;
+      uint4 val = make_uint4(0u, 0u, 0u, 0u);
+      if ((row_mask >> rr) & 1u) val = *reinterpret_cast<const uint4*>(row0_ptr + rr * ld + h * 16 + ch * 4);
+      *reinterpret_cast<uint4*>(stage + rr * kStageRowBytes + ch * 16) = val;
+    }
+    __syncwarp();
+    const uint4* mine = reinterpret_cast<const uint4*>(stage + lane * kStageRowBytes);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint4 q = mine[j];
+      v[h * 16 + 4 * j] += __uint_as_float(q.x);
+      v[h * 16 + 4 * j + 1] += __uint_as_float(q.y);
+      v[h * 16 + 4 * j + 2] += __uint_as_float(q.z);
+      v[h * 16 + 4 * j + 3] += __uint_as_float(q.w);
+    }
+    __syncwarp();
+  }
+}
+
+__device__ __forceinline__ void store_f32_coalesced(const float (&v)[32], uint8_t* stage, float* row0_ptr, long long ld,
+                                                    uint32_t row_mask, int lane) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    uint4* mine = reinterpret_cast<uint4*>(stage + lane * kStageRowBytes);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      mine[j] = make_uint4(__float_as_uint(v[h * 16 + 4 * j]), __float_as_uint(v[h * 16 + 4 * j + 1]),
+                           __float_as_uint(v[h * 16 + 4 * j + 2]), __float_as_uint(v[h * 16 + 4 * j + 3]));
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int rr = it * 8 + (lane >> 2);
+      const int ch = lane & 3;
+      const uint4 val = *reinterpret_cast<const uint4*>(stage + rr * kStageRowBytes + ch * 16);
+      if ((row_mask >> rr) & 1u) *reinterpret_cast<uint4*>(row0_ptr + rr * ld + h * 16 + ch * 4) = val;
+    }
+    __syncwarp();
+  }
+}
+
 // Epilogue math for one group of 32 consecutive columns of one row; `y` holds the raw accumulator sums on entry.
 // c0 = column offset of the group inside the tile (index into EpiConsts), n0 = global column.
 __device__ __forceinline__ void epilogue_group(const GemmParams& p, const EpiConsts& ec, uint8_t* stage, float (&y)[32],
@@ -199,15 +250,11 @@ __device__ __forceinline__ void epilogue_group(const GemmParams& p, const EpiCon
         if (addl) y[j] += __ldg(addl + n0 + j);
       }
   }
-  if (p.resid && valid) {
+  if (p.resid) {
     const float* rp = p.resid + row * p.ld_resid + n0;
-    if (full && p.vec_resid) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 r4 = *reinterpret_cast<const float4*>(rp + j);
-        y[j] += r4.x; y[j + 1] += r4.y; y[j + 2] += r4.z; y[j + 3] += r4.w;
-      }
-    } else {
+    if (full && p.vec_resid) {   // warp-uniform
+      add_f32_coalesced(y, stage, rp - lane * p.ld_resid, p.ld_resid, row_mask, lane);   // masked rows are zeroed below
+    } else if (valid) {
 #pragma unroll
       for (int j = 0; j < 32; ++j)
         if (n0 + j < p.N) y[j] += rp[j];
@@ -217,13 +264,11 @@ __device__ __forceinline__ void epilogue_group(const GemmParams& p, const EpiCon
 #pragma unroll
     for (int j = 0; j < 32; ++j) y[j] = 0.f;
   }
-  if (p.out_f32 && ((row_mask >> lane) & 1u)) {
+  if (p.out_f32) {
     float* op = p.out_f32 + row * p.ld_out + n0;
-    if (full && p.vec_out) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        *reinterpret_cast<float4*>(op + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
-    } else {
+    if (full && p.vec_out) {     // warp-uniform
+      store_f32_coalesced(y, stage, op - lane * p.ld_out, p.ld_out, row_mask, lane);
+    } else if ((row_mask >> lane) & 1u) {
 #pragma unroll
       for (int j = 0; j < 32; ++j)
         if (n0 + j < p.N) op[j] = y[j];
@@ -253,13 +298,11 @@ __device__ __forceinline__ void epilogue_group(const GemmParams& p, const EpiCon
         dot = fmaf(y[j + 3], w4.w, dot);
       }
     }
-    if (p.out_z && ((row_mask >> lane) & 1u)) {
+    if (p.out_z) {
       float* zp = p.out_z + row * p.ld_z + n0;
-      if (full && p.vec_z) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4*>(zp + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
-      } else {
+      if (full && p.vec_z) {     // warp-uniform
+        store_f32_coalesced(y, stage, zp - lane * p.ld_z, p.ld_z, row_mask, lane);
+      } else if ((row_mask >> lane) & 1u) {
 #pragma unroll
         for (int j = 0; j < 32; ++j)
           if (n0 + j < p.N) zp[j] = y[j];
@@ -357,7 +400,12 @@ __global__ void __launch_bounds__(GEN ? kGenThreads : kGemmThreads, 1) gemm_kern
 
   if (warp < 4) {
     reg_dealloc<kCtrlRegs>();
-    if (warp == 0 && lane == 0) {
+    // The two control roles are entered through elect.sync, not `lane == 0`: the compiler then knows that exactly one
+    // thread executes the warp-level (uniform datapath) UTMALDG / UTCHMMA / UTCBAR instructions and emits them back to
+    // back; behind a lane test it wraps every one of them in an ELECT ... BRA.U.ANY loop (5 extra instructions per MMA),
+    // and the single issuing thread - not the tensor core - becomes the limit for tiles narrower than 256 columns
+    // (profiles/r02_issue_thread_bound.txt).
+    if (warp == 0 && elect_one()) {
       // ---------------------------------------------------------------- TMA producer
       int stage = 0;
       uint32_t phase = 0;
@@ -374,6 +422,8 @@ __global__ void __launch_bounds__(GEN ? kGenThreads : kGemmThreads, 1) gemm_kern
           seq = m_tile / p.conv_tiles_per_seq;
           t0 = (m_tile % p.conv_tiles_per_seq) * kBM;
         }
+        // conv: (tap, channel block) walk without a division per k-block
+        int cb = 0, kc = 0, kbase = 0, t = t0 - (p.conv_taps / 2) * p.conv_dil;
         for (int kb = 0; kb < p.num_kblocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
@@ -381,12 +431,16 @@ __global__ void __launch_bounds__(GEN ? kGenThreads : kGemmThreads, 1) gemm_kern
           mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
           int kcol = kb * BK;   // K coordinate in the weight rows
           if (conv) {
-            const int tap = kb / p.conv_cblocks;
-            const int kc = (kb - tap * p.conv_cblocks) * BK;
-            const int t = t0 + (tap - p.conv_taps / 2) * p.conv_dil;
-            kcol = tap * p.conv_cpad + kc;
+            kcol = kbase + kc;
             tma_load_3d(sa, &p.tm_a_hi, full_bar(stage), kc, t, seq);
             if (NPASS == 3) tma_load_3d(sa + Cfg::kATile, &p.tm_a_lo, full_bar(stage), kc, t, seq);
+            kc += BK;
+            if (++cb == p.conv_cblocks) {   // next tap
+              cb = 0;
+              kc = 0;
+              kbase += p.conv_cpad;
+              t += p.conv_dil;
+            }
           } else if (!GEN) {
             if (p.a_kblk) {
               tma_load_3d(sa, &p.tm_a_hi, full_bar(stage), kcol & 63, m_tile * kBM, kcol >> 6);
@@ -429,7 +483,7 @@ __global__ void __launch_bounds__(GEN ? kGenThreads : kGemmThreads, 1) gemm_kern
           }
         }
       }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1 && elect_one()) {
       // ---------------------------------------------------------------- MMA issuer
       const uint32_t idesc = make_idesc_f16(kBM, p.bn, /*fp16*/ 0);
       int stage = 0;
@@ -512,25 +566,26 @@ __global__ void __launch_bounds__(GEN ? kGenThreads : kGemmThreads, 1) gemm_kern
             tc_fence_after();
             const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
             const uint32_t sb = sa + Cfg::kPlanes * Cfg::kATile;
+            // one descriptor per operand tile; the k-steps and the lo planes are reached by adding to its address field
+            // (16-byte units; the field cannot carry out: shared memory is < 256 KB)
+            const uint64_t a_hi0 = make_kmajor_desc<Cfg::kSwizzle>(sa);
+            const uint64_t b_hi0 = make_kmajor_desc<Cfg::kSwizzle>(sb);
             // Within a k-block the small hi*lo / lo*hi products go first: the accumulator add truncates relative
             // to the accumulator's magnitude, so every tiny term added before the hi*hi terms is added exactly.
             if (NPASS == 3) {
 #pragma unroll
               for (int ks = 0; ks < BK / 16; ++ks) {
-                const uint64_t a_hi = make_kmajor_desc<Cfg::kSwizzle>(sa + ks * 32);
-                const uint64_t b_hi = make_kmajor_desc<Cfg::kSwizzle>(sb + ks * 32);
-                const uint64_t a_lo = make_kmajor_desc<Cfg::kSwizzle>(sa + Cfg::kATile + ks * 32);
-                const uint64_t b_lo = make_kmajor_desc<Cfg::kSwizzle>(sb + Cfg::kBTile + ks * 32);
-                umma_f16(d_tmem, a_lo, b_hi, idesc, first ? 0u : 1u);
-                umma_f16(d_tmem, a_hi, b_lo, idesc, 1);
+                umma_f16(d_tmem, a_hi0 + (uint64_t)((Cfg::kATile + ks * 32) >> 4), b_hi0 + (uint64_t)((ks * 32) >> 4), idesc,
+                         first ? 0u : 1u);                                                    // A_lo * B_hi
+                umma_f16(d_tmem, a_hi0 + (uint64_t)((ks * 32) >> 4), b_hi0 + (uint64_t)((Cfg::kBTile + ks * 32) >> 4), idesc,
+                         1);                                                                  // A_hi * B_lo
                 first = false;
               }
             }
 #pragma unroll
             for (int ks = 0; ks < BK / 16; ++ks) {
-              const uint64_t a_hi = make_kmajor_desc<Cfg::kSwizzle>(sa + ks * 32);
-              const uint64_t b_hi = make_kmajor_desc<Cfg::kSwizzle>(sb + ks * 32);
-              umma_f16(d_tmem, a_hi, b_hi, idesc, first ? 0u : 1u);
+              umma_f16(d_tmem, a_hi0 + (uint64_t)((ks * 32) >> 4), b_hi0 + (uint64_t)((ks * 32) >> 4), idesc,
+                       first ? 0u : 1u);                                                      // A_hi * B_hi
               first = false;
             }
             umma_commit(empty_bar(stage));   // frees the smem slot once these MMAs have read it

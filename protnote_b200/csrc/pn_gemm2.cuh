@@ -150,7 +150,8 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
 
   if (warp < 4) {
     reg_dealloc<kCtrlRegs>();
-    if (warp == 0 && lane == 0) {
+    // control roles through elect.sync (see pn_gemm.cuh): no per-instruction election loops around UTMALDG / UTCHMMA
+    if (warp == 0 && elect_one()) {
       // ---------------------------------------------------------------- TMA producer (both CTAs)
       int stage = 0;
       uint32_t phase = 0;
@@ -165,6 +166,7 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
         }
         const int row0 = m_tile * (2 * kBM) + (int)rank * kBM;
         const int brow0 = n_tile * p.bn + (int)rank * half_bn;
+        int cb = 0, kc = 0, kbase = 0, t = t0 - (p.conv_taps / 2) * p.conv_dil;   // conv: (tap, channel block) walk
         for (int kb = 0; kb < p.num_kblocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
@@ -173,12 +175,16 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
           if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * my_bytes);
           int kcol = kb * BK;
           if (conv) {
-            const int tap = kb / p.conv_cblocks;
-            const int kc = (kb - tap * p.conv_cblocks) * BK;
-            const int t = t0 + (tap - p.conv_taps / 2) * p.conv_dil;
-            kcol = tap * p.conv_cpad + kc;
+            kcol = kbase + kc;
             tma2_load_3d(sa, &p.tm_a_hi, fb, kc, t, seq);
             if (NPASS == 3) tma2_load_3d(sa + Cfg::kATile, &p.tm_a_lo, fb, kc, t, seq);
+            kc += BK;
+            if (++cb == p.conv_cblocks) {   // next tap
+              cb = 0;
+              kc = 0;
+              kbase += p.conv_cpad;
+              t += p.conv_dil;
+            }
           } else {
             tma2_load_2d(sa, &p.tm_a_hi, fb, kcol, row0);
             if (NPASS == 3) tma2_load_2d(sa + Cfg::kATile, &p.tm_a_lo, fb, kcol, row0);
@@ -191,7 +197,7 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
           }
         }
       }
-    } else if (warp == 1 && lane == 0 && leader) {
+    } else if (warp == 1 && leader && elect_one()) {
       // ---------------------------------------------------------------- MMA issuer (leader CTA only)
       const uint32_t idesc = make_idesc_f16(2 * kBM, p.bn, /*fp16*/ 0);
       int stage = 0;
@@ -213,23 +219,20 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
             tc_fence_after();
             const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
             const uint32_t sb = sa + Cfg::kPlanes * Cfg::kATile;
+            const uint64_t a_hi0 = make_kmajor_desc<Cfg::kSwizzle>(sa);
+            const uint64_t b_hi0 = make_kmajor_desc<Cfg::kSwizzle>(sb);
             if (NPASS == 3) {
 #pragma unroll
               for (int ks = 0; ks < BK / 16; ++ks) {
-                const uint64_t a_hi = make_kmajor_desc<Cfg::kSwizzle>(sa + ks * 32);
-                const uint64_t b_hi = make_kmajor_desc<Cfg::kSwizzle>(sb + ks * 32);
-                const uint64_t a_lo = make_kmajor_desc<Cfg::kSwizzle>(sa + Cfg::kATile + ks * 32);
-                const uint64_t b_lo = make_kmajor_desc<Cfg::kSwizzle>(sb + Cfg::kBTile + ks * 32);
-                umma2_f16(d_tmem, a_lo, b_hi, idesc, first ? 0u : 1u);
-                umma2_f16(d_tmem, a_hi, b_lo, idesc, 1);
+                umma2_f16(d_tmem, a_hi0 + (uint64_t)((Cfg::kATile + ks * 32) >> 4), b_hi0 + (uint64_t)((ks * 32) >> 4), idesc,
+                          first ? 0u : 1u);
+                umma2_f16(d_tmem, a_hi0 + (uint64_t)((ks * 32) >> 4), b_hi0 + (uint64_t)((Cfg::kBTile + ks * 32) >> 4), idesc, 1);
                 first = false;
               }
             }
 #pragma unroll
             for (int ks = 0; ks < BK / 16; ++ks) {
-              const uint64_t a_hi = make_kmajor_desc<Cfg::kSwizzle>(sa + ks * 32);
-              const uint64_t b_hi = make_kmajor_desc<Cfg::kSwizzle>(sb + ks * 32);
-              umma2_f16(d_tmem, a_hi, b_hi, idesc, first ? 0u : 1u);
+              umma2_f16(d_tmem, a_hi0 + (uint64_t)((ks * 32) >> 4), b_hi0 + (uint64_t)((ks * 32) >> 4), idesc, first ? 0u : 1u);
               first = false;
             }
             umma2_commit_both(empty_bar(stage));
