@@ -106,7 +106,8 @@ def calibrate_model(model, dev, world=1, logit_std=2.0):
       1. one training-mode forward over a calibration batch with BatchNorm momentum 1 sets every running mean / variance
          (encoder, W_p, W_l, output MLP) to the statistics the layer actually sees, then they are jittered so the folded
          BatchNorm is not an exact normalisation;
-      2. the output neuron is rescaled (and its bias shifted) so the eval-mode logits of the calibration batch have
+      2. the output neuron is made orthogonal to the mean last-hidden activation (as oracle.synth_state_dict does for
+         the golden cases), then rescaled (and its bias shifted) so the eval-mode logits of the calibration batch have
          mean 0 and std `logit_std`.
     Rank 0's result is broadcast so every rank holds bit-identical weights."""
     import torch.distributed as dist
@@ -129,8 +130,15 @@ def calibrate_model(model, dev, world=1, logit_std=2.0):
         m.running_mean.add_((0.1 * sd * torch.randn(sd.shape, generator=g)).to(dev))
         m.running_var.mul_((0.7 + 0.6 * torch.rand(sd.shape, generator=g)).to(dev)).clamp_(min=1e-4)
     with torch.no_grad():
-        logits = model(sequence_onehots=x, sequence_lengths=lens, label_embeddings=lab)[0]
         final = list(model.output_layer)[-1]
+        # output neuron orthogonal to the mean last-hidden activation: without this the logit of a random network is a
+        # huge common term cancelled by the bias (|partial sums| ~ 500 for logits of +-2), a regime no trained model is in
+        # and in which fp32 rounding of the final dot product alone costs several 1e-5 - in the reference too
+        _, extra = model(sequence_onehots=x, sequence_lengths=lens, label_embeddings=lab, save_embeddings=True)
+        m = extra["output_layer_embeddings"].double().mean(0).to(dev)
+        w = final.weight.double()[0]
+        final.weight.copy_((w - (w @ m) / (m @ m) * m).float()[None, :])
+        logits = model(sequence_onehots=x, sequence_lengths=lens, label_embeddings=lab)[0]
         s = logit_std / float(logits.std().clamp_min(1e-20))
         final.bias.copy_((final.bias - logits.mean()) * s)
         final.weight.mul_(s)
@@ -143,7 +151,7 @@ def calibrate_model(model, dev, world=1, logit_std=2.0):
     model._label_cache = None
     return {"calibration_logit_std": float(logits.std()), "calibration_logit_mean": float(logits.mean()),
             "how": "product path only: train-mode forward with BatchNorm momentum 1 on 24 x 256 aa x 96 rows, jitter, "
-                   "output neuron rescaled"}
+                   "output neuron made orthogonal to the mean hidden activation and rescaled"}
 
 
 class ClockSampler:
@@ -676,11 +684,11 @@ class TrainStep:
         self.opt.zero_grad(set_to_none=True)
         with torch.no_grad():
             P_f = self.model.sequence_encoder.get_embeddings(x, lens)
-        logits = pn_train.train_logits(self.model, P_f, lab, comm=self.comm, L_total=self.L)
-        loss = torch.nn.functional.binary_cross_entropy_with_logits(logits, y, reduction="sum") / float(self.B * self.L)
+        # BCE evaluated inside the last forward kernel (loss + gradient seed: the [B, L] logits never round-trip through
+        # autograd); the parameter gradients are all-reduced inside the backward, overlapped with its GEMMs
+        loss, _ = pn_train.train_loss(self.model, P_f, lab, y, loss=self.loss_name, comm=self.comm, L_total=self.L,
+                                      reduce_gradients=True)
         loss.backward()
-        if self.comm is not None:
-            pn_train.allreduce_gradients(self.model, self.comm)
         self.opt.step()
         self.last_loss = loss.detach()
 
@@ -763,11 +771,10 @@ def train_parity_small(dev, rank, world):
     model = build_b200_model(ecfg, scfg, sd, device=dev).train()
     comm = pn_train.Comm() if world > 1 else None
     ls, le = label_row_bounds(L, 1, rank, world)
-    logits = pn_train.train_logits(model, P_f.to(dev), L_f[ls:le].to(dev).contiguous(), comm=comm, L_total=L)
-    loss = torch.nn.functional.binary_cross_entropy_with_logits(logits, y[:, ls:le].to(dev), reduction="sum") / float(B * L)
+    # the measured path: loss fused into the last forward kernel, gradients all-reduced inside the backward
+    loss, logits = pn_train.train_loss(model, P_f.to(dev), L_f[ls:le].to(dev).contiguous(), y[:, ls:le].to(dev).contiguous(),
+                                       loss="bce", comm=comm, L_total=L, reduce_gradients=True)
     loss.backward()
-    if comm is not None:
-        pn_train.allreduce_gradients(model, comm)
     full = all_gather_columns(logits.detach(), L) if world > 1 else logits.detach()
     tot = loss.detach().clone().reshape(1)
     if world > 1:

@@ -257,6 +257,21 @@ int pn_t_bn_relu(const void* z_hi, const void* z_lo, long long rows, int cols, l
 /* out[r] = relu(z[r] * scale + shift) . w + b  - the last hidden layer and Linear(H -> 1) (ProtNote.py:373-377) */
 int pn_t_bn_relu_dot(const void* z_hi, const void* z_lo, long long rows, int cols, long long ld_z, const float* state,
                      const float* w, const float* b, float* out, void* stream);
+/* The same pass with the loss fused in: additionally g_out[r] = grad_scale * d loss(x_r, targets[r]) / d x_r
+ * and *loss_sum += sum_r loss(x_r, targets[r]) (fp64, caller zeroes it), so the [B, L] logits need not round-trip through
+ * autograd and the loss module's elementwise passes disappear.  `out` (the logits) is optional.  Rows are pairs in
+ * (protein, label) order, L = label rows per protein on this rank; targets [rows] fp32.
+ *   PN_LOSS_BCE    torch.nn.BCEWithLogitsLoss(pos_weight) as built by protnote/utils/losses.py:270-272 ('BCE');
+ *                  pos_weight [L] or NULL.
+ *   PN_LOSS_FOCAL  protnote/utils/losses.py:171-213 FocalLoss(alpha, gamma, label_smoothing): BCE of the smoothed target,
+ *                  (1 - exp(-BCE))^gamma modulation, alpha_t weighting when alpha >= 0.  pos_weight must be NULL.
+ * For reduction 'mean' over a label-sharded batch pass grad_scale = 1 / (B * L_total) and divide loss_sum by B * L_total. */
+#define PN_LOSS_BCE 1
+#define PN_LOSS_FOCAL 2
+int pn_t_bn_relu_dot_loss(const void* z_hi, const void* z_lo, long long rows, int cols, long long ld_z, const float* state,
+                          const float* w, const float* b, float* out, const float* targets, long long L,
+                          const float* pos_weight, int loss_kind, float gamma, float alpha, float label_smoothing,
+                          float grad_scale, float* g_out, double* loss_sum, void* stream);
 /* layer 1 of the pair scorer: h[(b, l)] = relu((a[b] + c[l]) * scale + shift), rows b * L + l; a [B][H], c [L][H] dense */
 int pn_t_pair_hidden(const float* a, long long B, const float* c, long long L, int H, const float* state, void* hi,
                      void* lo, long long ld, void* hiT, void* loT, long long blocksT, void* stream);

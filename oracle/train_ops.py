@@ -143,6 +143,30 @@ class TorchOps:
         h = torch.relu(z.val * st.scale + st.shift)
         return h @ w.detach().to(self.dtype).reshape(-1) + b.detach().to(self.dtype).reshape(())
 
+    def bn_relu_dot_loss(self, z: TAct, st: TBN, w, b, targets, L, spec):
+        """Statement of pn_t_bn_relu_dot_loss: logits, grad_scale * d loss / d logit, sum of per-pair losses - with the
+        reference's own loss formulas (protnote/utils/losses.py:171-213 FocalLoss, :270-272 BCE) under autograd."""
+        with torch.enable_grad():       # (called from inside autograd.Function.forward, where grad mode is off)
+            return self._loss_and_seed(self.bn_relu_dot(z, st, w, b).detach().requires_grad_(True), targets, L, spec)
+
+    def _loss_and_seed(self, x, targets, L, spec):
+        t = targets.detach().to(self.dtype).reshape(-1)
+        if spec.kind_id == 1:
+            pw = None
+            if spec.pos_weight is not None:
+                pw = spec.pos_weight.detach().to(self.dtype).reshape(-1)
+                pw = (pw.expand(L) if pw.numel() == 1 else pw).repeat(x.numel() // L)
+            per = torch.nn.functional.binary_cross_entropy_with_logits(x, t, reduction="none", pos_weight=pw)
+        else:
+            ts = t * (1.0 - spec.label_smoothing) + (1 - t) * spec.label_smoothing if spec.label_smoothing > 0 else t
+            bce = torch.nn.functional.binary_cross_entropy_with_logits(x, ts, reduction="none")
+            per = ((1 - torch.exp(-bce)) ** spec.gamma) * bce
+            if spec.alpha >= 0:
+                per = (spec.alpha * ts + (1 - spec.alpha) * (1 - ts)) * per
+        total = per.sum()
+        (g,) = torch.autograd.grad(total, x)
+        return x.detach(), g * spec.grad_scale, total.detach().reshape(1)
+
     def pair_hidden(self, a, c, st: TBN, want_T=False):
         z = (a[:, None, :] + c[None, :, :]).reshape(-1, a.shape[1])
         return TAct(torch.relu(z * st.scale + st.shift), 1.0, want_T)

@@ -32,8 +32,33 @@ def _bn_train(x, sd, prefix, eps, new_stats, momentum=0.1):
     return y
 
 
-def train_step_oracle(sd: Dict[str, torch.Tensor], P_f, L_f, targets, cfg: ScorerCfg, dtype=torch.float64):
-    """Returns (logits [B, L], loss, {state_dict key: gradient}, {running-stat key: updated value})."""
+def focal_loss(logits, target, alpha: float, gamma: float, label_smoothing: float = 0.0, reduction: str = "mean"):
+    """FocalLoss.forward - protnote/utils/losses.py:193-213 (the default LOSS_FN, configs/base_config.yaml:61): optional label
+    smoothing of the targets, element-wise BCE-with-logits, modulation (1 - exp(-BCE))^gamma, alpha_t weighting when
+    alpha >= 0, mean / sum.  Pinned against the reference class by tests/test_train_cpu.py."""
+    if label_smoothing > 0:
+        target = target * (1.0 - label_smoothing) + (1 - target) * label_smoothing
+    bce = F.binary_cross_entropy_with_logits(logits, target, reduction="none")
+    pt = torch.exp(-bce)
+    loss = ((1 - pt) ** gamma) * bce
+    if alpha >= 0:
+        loss = (alpha * target + (1 - alpha) * (1 - target)) * loss
+    return loss.mean() if reduction == "mean" else loss.sum()
+
+
+def loss_oracle(logits, targets, loss="bce", pos_weight=None, gamma=2.0, alpha=-1.0, label_smoothing=0.0, reduction="mean"):
+    """The reference's get_loss choices that are per-element functions of (logit, target) - utils/losses.py:270-294:
+    'BCE' = torch.nn.BCEWithLogitsLoss(reduction='mean', pos_weight=...), 'FocalLoss' = focal_loss above."""
+    if loss in ("bce", "BCE"):
+        return F.binary_cross_entropy_with_logits(logits, targets, reduction=reduction, pos_weight=pos_weight)
+    if loss in ("focal", "FocalLoss"):
+        return focal_loss(logits, targets, alpha, gamma, label_smoothing, reduction)
+    raise NotImplementedError(loss)
+
+
+def train_step_oracle(sd: Dict[str, torch.Tensor], P_f, L_f, targets, cfg: ScorerCfg, dtype=torch.float64, **loss_kw):
+    """Returns (logits [B, L], loss, {state_dict key: gradient}, {running-stat key: updated value}).
+    loss_kw: arguments of loss_oracle (default: BCE-with-logits, mean)."""
     if cfg.feature_fusion != "concatenation":
         raise NotImplementedError(cfg.feature_fusion)
     p = {k: v.detach().clone().to(dtype).requires_grad_(True) for k, v in sd.items()
@@ -63,7 +88,9 @@ def train_step_oracle(sd: Dict[str, torch.Tensor], P_f, L_f, targets, cfg: Score
         x = torch.relu(x)
     logits = (x @ full[f"output_layer.{last}.weight"].T + full[f"output_layer.{last}.bias"]).reshape(
         P_e.shape[0], L_e.shape[0])
-    loss = F.binary_cross_entropy_with_logits(logits, targets.to(dtype))
+    if "pos_weight" in loss_kw and loss_kw["pos_weight"] is not None:
+        loss_kw = dict(loss_kw, pos_weight=loss_kw["pos_weight"].to(dtype))
+    loss = loss_oracle(logits, targets.to(dtype), **loss_kw)
     loss.backward()
     grads = {k: v.grad.detach() for k, v in p.items() if v.grad is not None}
     return logits.detach(), loss.detach(), grads, new_stats

@@ -99,6 +99,10 @@ class ProtNote(nn.Module):
         self.label_embedding_noising_alpha = label_embedding_noising_alpha
         self.residual_connection = residual_connection
         self.precision = precision
+        # The reference's last Linear runs under torch.autocast in ProtNoteTrainer.evaluation_step (:287-290), so ITS
+        # logits come back fp16 there; this module computes fp32-grade logits regardless of autocast and returns fp32.
+        # Set True to cast the returned logits to the active autocast dtype (dtype drop-in for callers that depend on it).
+        self.match_autocast_dtype = False
 
         hidden = [latent_dim * projection_head_hidden_dim_scale_factor] * (projection_head_num_layers - 1) + [latent_dim]
         self.W_p = _projection_mlp(protein_embedding_dim, hidden, dropout)
@@ -357,4 +361,6 @@ class ProtNote(nn.Module):
                 parts.append(p * t)
             embeddings["joint_embeddings"] = torch.cat(parts, dim=2).reshape(B * L, -1).detach().cpu()
             embeddings["output_layer_embeddings"] = hidden.cpu()
+        if self.match_autocast_dtype and torch.is_autocast_enabled():
+            logits = logits.to(torch.get_autocast_gpu_dtype())
         return logits, embeddings

@@ -28,10 +28,12 @@ long long g_chunk_rows = 0;      // 0 = auto
 // operand reads; it needs the 2-CTA operand sharing planned for the next round to pay off.  Off by default.
 int g_fuse_features = 0;
 // run the engine as CTA pairs (tcgen05 cta_group::2, 256-row tiles, each CTA loads half of the weight tile):
-// 1 always, 0 never, -1 (default) in fast mode only.  Measured on B200 (profiles/r01_cta_pair_probe.txt): fast mode is
-// bound by the L2 -> SM operand traffic, which the pair halves for B: encoder +10 %, scorer GEMM +1.6 %; strict mode
-// (three MMAs per operand byte) is tensor-bound and 2 % slower as pairs.
-int g_cta2 = -1;
+// 2 always (experiments), 1 (default) wherever the caller allows it and the problem has more than one 128-row tile,
+// 0 never, -1 in fast mode only.  Round 1 measured strict-mode pairs 2 % SLOWER (profiles/r01_cta_pair_probe.txt) - but
+// that engine was bound by its single MMA-issuing thread, not by the tensor core; with the issue loop fixed
+// (profiles/r02_issue_thread_bound.txt) the SM's 64 B/clk operand ingest is what binds the 1-CTA kernel at tile widths
+// below 256 and the pair, which halves the weight bytes per CTA, wins in strict mode too: encoder +8 %, scorer +2 %.
+int g_cta2 = 1;
 // threads along the columns of a reduction block (TX * TY == 256; TX * 8 consecutive columns per block row)
 int g_stats_tx = 32;
 // 1: strict-mode encoder convolutions keep the hi*hi products and the lo corrections in separate TMEM buffers
@@ -43,7 +45,7 @@ int g_split_corr = 0;
 // strict mode: K elements accumulated in TMEM between fp32 promotions, per stage of the path
 // (kStagePointwise: the 1x1 convolutions of the encoder's residual blocks, K = bottleneck width)
 enum { kStageEncoder = 0, kStageHeads = 1, kStageScorer = 2, kStageOther = 3, kStagePointwise = 4, kNumStages = 5 };
-int g_promote_k[kNumStages] = {32, 32, 256, 64, 32};
+int g_promote_k[kNumStages] = {64, 32, 256, 64, 64};
 // strict mode: compensation of the accumulator's round-toward-zero bias (GemmParams::trunc_comp).  The factor applied to a
 // launch is (c1 * K-elements per chunk + c0) * 1e-12; both coefficients are hardware properties measured with
 // tools/trunc_comp_probe.py.  c1 == 0 and c0 == 0 switch the compensation off.
@@ -262,7 +264,10 @@ int launch_gemm(const Planes& A, const ConvView& cv, const Planes& B, long long 
                 cudaStream_t stream, int stage_kind = kStageOther, int promote_override = -1, bool allow_pairs = true) {
   if (mode != PN_STRICT && mode != PN_FAST) return fail("mode must be PN_STRICT or PN_FAST");
   const bool gen = e.gen_a != nullptr;
-  const bool cta2 = (g_cta2 == 1 || (g_cta2 < 0 && mode == PN_FAST && allow_pairs)) && !gen && !A.kblocked && !B.kblocked;
+  // CTA pairs pay off from two 128-row tiles up (a lone tile would run half empty)
+  const long long rows_per_problem = cv.taps > 0 ? cv.T : A.rows;
+  const bool cta2 = (g_cta2 == 2 || ((g_cta2 == 1 || (g_cta2 < 0 && mode == PN_FAST)) && allow_pairs && rows_per_problem > kBM)) &&
+                    !gen && !A.kblocked && !B.kblocked;
   const int tile_rows = cta2 ? 2 * kBM : kBM;
   const int bk = gen ? 32 : pick_bk(mode);
   GemmParams p;
@@ -656,7 +661,7 @@ int run_projection(const pn_scorer_cfg& c, const ScorerLayout& L, const Arena& p
 
 size_t scorer_row_bytes(const pn_scorer_cfg& c) {
   const size_t ld_h = (size_t)round_up(c.out_hidden, 64);
-  return ld_h * 2 /*bytes*/ * 2 /*planes*/ * 2 /*ping-pong*/ + (size_t)tiles_n_for(c.out_hidden) * 2 * 4;
+  return ld_h * 2 /*bytes*/ * 2 /*planes*/ * 2 /*ping-pong*/ + (size_t)tiles_n_for(c.out_hidden) * 4 * 4;
 }
 
 }  // namespace
@@ -809,7 +814,7 @@ int pn_set_option(const char* name, long long value) {
     return 0;
   }
   if (strcmp(name, "cta2") == 0) {
-    g_cta2 = value < 0 ? -1 : (value != 0);
+    g_cta2 = value < 0 ? -1 : (value > 2 ? 2 : (int)value);
     return 0;
   }
   if (strcmp(name, "stats_tx") == 0) {
@@ -1288,7 +1293,7 @@ int pn_score_pairs_ex(const pn_scorer_cfg* cfg, const void* packed, const float*
   // the fused generator reads a / c with 16-byte loads over whole 32-wide k-blocks
   const bool fuse_ok = g_fuse_features && c.fusion != PN_FUSION_CONCAT_PROD && H % 32 == 0 &&
                        (reinterpret_cast<uintptr_t>(a) & 15) == 0 && (reinterpret_cast<uintptr_t>(c_in) & 15) == 0;
-  const int parts = 2 * tiles_n_for(H);   // one partial dot per (N tile, column half)
+  const int parts = 4 * tiles_n_for(H);   // one partial dot (two floats: hi, lo of an fp64 sum) per (N tile, column half)
   const size_t per_row = scorer_row_bytes(c);
   long long max_rows = (long long)((workspace_bytes > 8192 ? workspace_bytes - 8192 : 0) / per_row);
   if (g_chunk_rows > 0 && g_chunk_rows < max_rows) max_rows = g_chunk_rows;
@@ -1658,6 +1663,27 @@ int pn_t_bn_relu_dot(const void* z_hi, const void* z_lo, long long rows, int col
   bn_relu_dot_kernel<<<ew_grid(rows * 32), 256, 0, stream>>>(static_cast<const __half*>(z_hi),
                                                              static_cast<const __half*>(z_lo), rows, cols, ld_z, state, w,
                                                              b, out);
+  g_launches++;
+  PN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int pn_t_bn_relu_dot_loss(const void* z_hi, const void* z_lo, long long rows, int cols, long long ld_z, const float* state,
+                          const float* w, const float* b, float* out, const float* targets, long long L,
+                          const float* pos_weight, int loss_kind, float gamma, float alpha, float label_smoothing,
+                          float grad_scale, float* g_out, double* loss_sum, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (rows <= 0 || cols <= 0 || !z_hi || ld_z % 8 != 0) return fail("bad input to bn_relu_dot_loss");
+  if (loss_kind != PN_LOSS_BCE && loss_kind != PN_LOSS_FOCAL) return fail("loss_kind must be PN_LOSS_BCE or PN_LOSS_FOCAL");
+  if (!targets || !g_out || !loss_sum || L <= 0 || rows % L != 0) return fail("bn_relu_dot_loss: targets / g_out / loss_sum / L");
+  if (loss_kind == PN_LOSS_FOCAL && pos_weight) return fail("FocalLoss takes no pos_weight (protnote/utils/losses.py:171-213)");
+  if (loss_kind == PN_LOSS_FOCAL && !(gamma >= 0.f)) return fail("focal gamma must be >= 0");
+  LossSpec ls;
+  ls.kind = loss_kind; ls.gamma = gamma; ls.alpha = alpha; ls.label_smoothing = label_smoothing; ls.grad_scale = grad_scale;
+  ls.targets = targets; ls.pos_weight = pos_weight; ls.L = L; ls.g_out = g_out; ls.loss_sum = loss_sum;
+  bn_relu_dot_loss_kernel<<<ew_grid(rows * 32), 256, 0, stream>>>(static_cast<const __half*>(z_hi),
+                                                                  static_cast<const __half*>(z_lo), rows, cols, ld_z, state,
+                                                                  w, b, out, ls);
   g_launches++;
   PN_CUDA(cudaGetLastError());
   return 0;

@@ -88,7 +88,7 @@ struct alignas(64) GemmParams {
   const float* scale2; const float* shift2; // [N] (nullable)
   int relu;
   __half* out_hi; __half* out_lo; long long ld_split;   // z as fp16 planes (nullable; out_lo nullable)
-  const float* dot_w; float* dot_out;       // dot_out[(row*tiles_n + n_tile)*2 + half] = sum_n z*dot_w[n] (nullable)
+  const float* dot_w; float* dot_out;       // float2 (hi, lo) at [(row*tiles_n + n_tile)*2 + half] = sum_n z*dot_w[n] (nullable)
   int vec_z;
   int vec_out, vec_resid, vec_split;        // 16-byte vector access is legal for that tensor (host-checked)
   // GEN kernels only: A[r][k] = relu(gen_a[r / pair_nl][k] + gen_c[r % pair_nl][k]) is built in shared memory by the
@@ -801,15 +801,25 @@ __global__ void __launch_bounds__(GEN ? kGenThreads : kGemmThreads, 1) gemm_kern
 #pragma unroll
           for (int j = 0; j < 32; ++j) sums[g][j] = fmaf(sums[g][j], p.trunc_comp, sums[g][j]);
       }
-      float dot = 0.f;
+      // Linear(H -> 1): the dot with w_out is summed in fp32 over 32 columns at a time and across groups in fp64 (the
+      // partial sums of a calibrated / trained output neuron are far larger than the logit they cancel to); the fp64
+      // partial leaves as two floats (hi, lo) and finalize_logits_kernel adds all of them in fp64
+      double dot = 0.0;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         const int c0 = (g_lo + g) * 32;
         const int n0 = n_tile * p.bn + c0;
-        if (g_lo + g < g_hi && n0 < p.N)   // warp-uniform (rows out of range are masked inside)
-          epilogue_group(p, ec, stage, sums[g], c0, n0, row, valid, row_mask, lane, addp, addl, dot);
+        if (g_lo + g < g_hi && n0 < p.N) {   // warp-uniform (rows out of range are masked inside)
+          float dotg = 0.f;
+          epilogue_group(p, ec, stage, sums[g], c0, n0, row, valid, row_mask, lane, addp, addl, dotg);
+          dot += (double)dotg;
+        }
       }
-      if (p.dot_w && in_range) p.dot_out[(row * p.tiles_n + n_tile) * 2 + half] = dot;
+      if (p.dot_w && in_range) {
+        const float dhi = (float)dot;
+        float2* dst = reinterpret_cast<float2*>(p.dot_out) + (row * p.tiles_n + n_tile) * 2 + half;
+        *dst = make_float2(dhi, (float)(dot - (double)dhi));
+      }
     }
   }
 

@@ -352,15 +352,25 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) sums[g][j] = fmaf(sums[g][j], p.trunc_comp, sums[g][j]);
       }
-      float dot = 0.f;
+      // Linear(H -> 1): the dot with w_out is summed in fp32 over 32 columns at a time and across groups in fp64 (the
+      // partial sums of a calibrated / trained output neuron are far larger than the logit they cancel to); the fp64
+      // partial leaves as two floats (hi, lo) and finalize_logits_kernel adds all of them in fp64
+      double dot = 0.0;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         const int c0 = (g_lo + g) * 32;
         const int n0 = n_tile * p.bn + c0;
-        if (g_lo + g < g_hi && n0 < p.N)
-          epilogue_group(p, ec, stage, sums[g], c0, n0, row, valid, row_mask, lane, addp, addl, dot);
+        if (g_lo + g < g_hi && n0 < p.N) {   // warp-uniform (rows out of range are masked inside)
+          float dotg = 0.f;
+          epilogue_group(p, ec, stage, sums[g], c0, n0, row, valid, row_mask, lane, addp, addl, dotg);
+          dot += (double)dotg;
+        }
       }
-      if (p.dot_w && in_range) p.dot_out[(row * p.tiles_n + n_tile) * 2 + half] = dot;
+      if (p.dot_w && in_range) {
+        const float dhi = (float)dot;
+        float2* dst = reinterpret_cast<float2*>(p.dot_out) + (row * p.tiles_n + n_tile) * 2 + half;
+        *dst = make_float2(dhi, (float)(dot - (double)dhi));
+      }
     }
   }
 

@@ -96,12 +96,15 @@ __global__ void fold_affine_kernel(int n, const float* __restrict__ bias, const 
                                    float* __restrict__ scale, float* __restrict__ shift) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  float gs = 1.f;
-  if (var) gs = 1.f / sqrtf(var[i] + eps);
-  if (gamma) gs *= gamma[i];
-  const float inv_s = wscale ? 1.f / *wscale : 1.f;
-  scale[i] = gs * inv_s;
-  shift[i] = ((bias ? bias[i] : 0.f) - (mean ? mean[i] : 0.f)) * gs + (beta ? beta[i] : 0.f);
+  // evaluated in fp64 and rounded once: these two numbers multiply / offset every output of the column, so their rounding
+  // is a coherent error of the whole column (the reference's fp32 BatchNorm has several roundings here; fp64 is closer to
+  // the exact value than either association order of fp32)
+  double gs = 1.0;
+  if (var) gs = 1.0 / sqrt((double)var[i] + (double)eps);
+  if (gamma) gs *= (double)gamma[i];
+  const double inv_s = wscale ? 1.0 / (double)*wscale : 1.0;
+  scale[i] = (float)(gs * inv_s);
+  shift[i] = (float)(((bias ? (double)bias[i] : 0.0) - (mean ? (double)mean[i] : 0.0)) * gs + (beta ? (double)beta[i] : 0.0));
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -558,6 +558,85 @@ __global__ void __launch_bounds__(256) bn_relu_dot_kernel(const __half* __restri
   }
 }
 
+// Fused loss + backward seed: the same pass as bn_relu_dot_kernel; with the logit of pair r still in a
+// register it evaluates the per-element loss against targets[r] and d loss / d logit, so the [B, L] logits never round-trip
+// through autograd and the reference's 4 elementwise loss passes (protnote/utils/losses.py) disappear.
+//   kind 1  BCE-with-logits, optional pos_weight per label column   (losses.py:270-272, torch.nn.BCEWithLogitsLoss):
+//             l = (1 - t) x + (1 + (pw - 1) t) softplus(-x)
+//   kind 2  FocalLoss(alpha, gamma, label_smoothing)                (losses.py:171-213):
+//             t' = t (1 - s) + (1 - t) s;  b = BCE(x, t');  pt = exp(-b);  l = alpha_t (1 - pt)^gamma b,
+//             alpha_t = alpha t' + (1 - alpha)(1 - t')  when alpha >= 0
+// g[r] = grad_scale * dl/dx (grad_scale = 1 / (B * L_total) for reduction 'mean'), loss_sum += sum_r l  (fp64).
+struct LossSpec {
+  int kind;                  // 0 none, 1 BCE, 2 focal
+  float gamma, alpha, label_smoothing, grad_scale;
+  const float* targets;      // [rows], same order as the logits (row = b * L + l)
+  const float* pos_weight;   // [L] or nullptr (BCE only)
+  long long L;               // label rows per protein on this rank (indexes pos_weight)
+  float* g_out;              // [rows]
+  double* loss_sum;          // [1], accumulated
+};
+
+__device__ __forceinline__ void loss_and_seed(const LossSpec& ls, float x, long long r, float& loss, float& g) {
+  const float t = ls.targets[r];
+  const float sp = log1pf(expf(-fabsf(x))) + fmaxf(-x, 0.f);      // softplus(-x) = -log(sigmoid(x))
+  const float sig = 1.f / (1.f + expf(-x));
+  if (ls.kind == 1) {
+    const float pw = ls.pos_weight ? ls.pos_weight[r % ls.L] : 1.f;
+    const float cw = 1.f + (pw - 1.f) * t;
+    loss = (1.f - t) * x + cw * sp;
+    g = (1.f - t) - cw * (1.f - sig);
+  } else {
+    const float s = ls.label_smoothing;
+    const float ts = s > 0.f ? t * (1.f - s) + (1.f - t) * s : t;
+    const float b = (1.f - ts) * x + sp;
+    const float pt = expf(-b);
+    const float om = 1.f - pt;
+    const float mod = powf(om, ls.gamma);
+    const float at = ls.alpha >= 0.f ? ls.alpha * ts + (1.f - ls.alpha) * (1.f - ts) : 1.f;
+    loss = at * mod * b;
+    const float modm1 = ls.gamma == 1.f ? 1.f : (om > 0.f ? powf(om, ls.gamma - 1.f) : 0.f);
+    g = at * (sig - ts) * (ls.gamma * modm1 * pt * b + mod);
+  }
+}
+
+__global__ void __launch_bounds__(256) bn_relu_dot_loss_kernel(const __half* __restrict__ zh, const __half* __restrict__ zl,
+                                                               long long rows, int cols, long long ld,
+                                                               const float* __restrict__ state, const float* __restrict__ w,
+                                                               const float* __restrict__ b, float* __restrict__ out,
+                                                               const LossSpec ls) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int chunks = (cols + 7) / 8;
+  double local = 0.0;
+  for (long long r = warp0; r < rows; r += nwarps) {
+    float acc = 0.f;
+    for (int ch = lane; ch < chunks; ch += 32) {
+      const int c0 = ch * 8;
+      float v[8], sc[8], sf[8], wv[8];
+      load8(zh + r * ld + c0, zl ? zl + r * ld + c0 : nullptr, v);
+      load8_f32(state + c0, cols - c0, sc);
+      load8_f32(state + cols + c0, cols - c0, sf);
+      load8_f32(w + c0, cols - c0, wv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (c0 + j < cols) acc = fmaf(fmaxf(fmaf(v[j], sc[j], sf[j]), 0.f), wv[j], acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+      const float x = acc + (b ? __ldg(b) : 0.f);
+      if (out) out[r] = x;
+      float l, g;
+      loss_and_seed(ls, x, r, l, g);
+      ls.g_out[r] = g * ls.grad_scale;
+      local += (double)l;
+    }
+  }
+  if (lane == 0 && local != 0.0) atomicAdd(ls.loss_sum, local);
+}
+
 // ------------------------------------------------------------------------------------------------
 // BatchNorm + ReLU backward, pass 1: sums[0][c] = sum_r g_y, sums[1][c] = sum_r g_y * xhat (true scale, fp64),
 // maxes = (max |g_y|, max |xhat|); kind 1 also dw[c] = sum_r g_logit[r] * relu(pre)[r][c] and db = sum_r g_logit[r].

@@ -48,6 +48,14 @@ class Comm:
         return t
 
 
+    def sum_async(self, t: torch.Tensor):
+        """Starts the all-reduce of `t` on NCCL's own stream and returns the work handle (None at world 1): the caller keeps
+        computing and waits once, so a parameter gradient crosses NVLink while the backward of the next layer runs."""
+        if self.world > 1:
+            return self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group, async_op=True)
+        return None
+
+
 class _NoComm:
     world = 1
 
@@ -56,6 +64,29 @@ class _NoComm:
 
     def max_(self, t):
         return t
+
+    def sum_async(self, t):
+        return None
+
+
+class LossSpec:
+    """The loss the fused last-layer kernel evaluates (pn_t_bn_relu_dot_loss): the reference's `LOSS_FN` choices that are
+    plain per-element functions of (logit, target) - 'BCE' (torch.nn.BCEWithLogitsLoss with optional pos_weight,
+    protnote/utils/losses.py:270-272) and 'FocalLoss' (losses.py:171-213; the default of configs/base_config.yaml:61) -
+    with reduction 'mean' or 'sum' over the WHOLE batch (B x L_total pairs, all label shards)."""
+    KINDS = {"bce": 1, "BCE": 1, "focal": 2, "FocalLoss": 2}
+
+    def __init__(self, kind="bce", pos_weight=None, gamma=2.0, alpha=-1.0, label_smoothing=0.0, reduction="mean"):
+        if kind not in self.KINDS:
+            raise ValueError(f"fused loss '{kind}' is not implemented (BCE and FocalLoss are); compute it from the logits")
+        if reduction not in ("mean", "sum"):
+            raise ValueError("reduction must be 'mean' or 'sum'")
+        self.kind_id = self.KINDS[kind]
+        if self.kind_id == 2 and pos_weight is not None:
+            raise ValueError("FocalLoss takes no pos_weight")
+        self.pos_weight, self.gamma, self.alpha = pos_weight, float(gamma), float(alpha)
+        self.label_smoothing, self.reduction = float(label_smoothing), reduction
+        self.grad_scale = 1.0     # set per batch by forward_train
 
 
 def _split_sequential(seq: nn.Module) -> List[Tuple[nn.Linear, Optional[nn.BatchNorm1d]]]:
@@ -121,7 +152,8 @@ def head_backward(ops, comm, g_f32, saved, rows_total: int, sharded: bool, grads
 # --------------------------------------------------------------------------------------------------------------------
 # pair scorer (ProtNote.py:112-126,293,337-378)
 # --------------------------------------------------------------------------------------------------------------------
-def pairs_forward(ops, comm, P_e, L_e, hidden, final: nn.Linear, L_total: int, sharded: bool, update_running: bool):
+def pairs_forward(ops, comm, P_e, L_e, hidden, final: nn.Linear, L_total: int, sharded: bool, update_running: bool,
+                  loss: Optional[LossSpec] = None, targets=None):
     B, d = P_e.shape
     lin1, bn1 = hidden[0]
     if bn1 is None or any(bn is None for _, bn in hidden):
@@ -151,9 +183,35 @@ def pairs_forward(ops, comm, P_e, L_e, hidden, final: nn.Linear, L_total: int, s
         ctx["layers"].append((h, z, st, lin, bn))
         if j + 1 < len(hidden):
             h = ops.bn_relu(z, st, want_T=True)
-        else:                                                               # the last hidden layer is never stored:
+        elif loss is None:                                                  # the last hidden layer is never stored:
             logits = ops.bn_relu_dot(z, st, final.weight, final.bias)       # relu(BN(z)) . w_out + b_out per pair
+        else:                                                               # ... and the loss + its gradient seed are fused in
+            loss.grad_scale = 1.0 / float(B * L_total) if loss.reduction == "mean" else 1.0
+            logits, ctx["g_seed"], ctx["loss_sum"] = ops.bn_relu_dot_loss(z, st, final.weight, final.bias, targets,
+                                                                          L_e.shape[0], loss)
     return logits, ctx
+
+
+class _Grads(dict):
+    """{parameter: gradient}.  With `reduce_comm` set every gradient is all-reduced (sum over the label-sharded ranks) as
+    soon as it is stored, asynchronously: the 303 MB of parameter gradients cross NVLink behind the dgrad / wgrad GEMMs of
+    the layers still to come instead of after the backward as one blocking cat -> all_reduce -> copy."""
+
+    def __init__(self, reduce_comm=None):
+        super().__init__()
+        self.reduce_comm, self.pending = reduce_comm, []
+
+    def __setitem__(self, k, v):
+        super().__setitem__(k, v)
+        if self.reduce_comm is not None and v is not None:
+            w = self.reduce_comm.sum_async(v)
+            if w is not None:
+                self.pending.append(w)
+
+    def wait(self):
+        for w in self.pending:
+            w.wait()
+        self.pending = []
 
 
 def pairs_backward(ops, comm, ctx, g_logit, sharded: bool, grads: Dict):
@@ -212,8 +270,10 @@ def trainable_parameters(model) -> List[nn.Parameter]:
     return ps
 
 
-def forward_train(ops, comm, model, P_f, L_f, L_total: Optional[int] = None, update_running: bool = True):
-    """P_f [B, protein_dim] (all proteins), L_f [L_local, label_dim] (this rank's label rows) -> logits [B, L_local]."""
+def forward_train(ops, comm, model, P_f, L_f, L_total: Optional[int] = None, update_running: bool = True,
+                  loss: Optional[LossSpec] = None, targets=None):
+    """P_f [B, protein_dim] (all proteins), L_f [L_local, label_dim] (this rank's label rows) -> logits [B, L_local].
+    With `loss` (and targets [B, L_local]) the last kernel also leaves ctx['pairs']['loss_sum'] / ['g_seed']."""
     comm = comm or _NoComm()
     sharded = comm.world > 1
     L_total = int(L_total if L_total is not None else L_f.shape[0])
@@ -223,7 +283,7 @@ def forward_train(ops, comm, model, P_f, L_f, L_total: Optional[int] = None, upd
     hidden, final = mods[:-1], mods[-1][0]
     P_e, saved_p = head_forward(ops, comm, P_f, wp, B, False, update_running)
     L_e, saved_l = head_forward(ops, comm, L_f, wl, L_total, sharded, update_running)
-    logits, pctx = pairs_forward(ops, comm, P_e, L_e, hidden, final, L_total, sharded, update_running)
+    logits, pctx = pairs_forward(ops, comm, P_e, L_e, hidden, final, L_total, sharded, update_running, loss, targets)
     ctx = {"saved_p": saved_p, "saved_l": saved_l, "pairs": pctx, "B": B, "L_total": L_total, "sharded": sharded}
     if update_running:
         for part in (model.W_p, model.W_l, model.output_layer):
@@ -239,14 +299,17 @@ def forward_train(ops, comm, model, P_f, L_f, L_total: Optional[int] = None, upd
     return logits.reshape(B, L_f.shape[0]), ctx
 
 
-def backward_train(ops, comm, ctx, g_logits) -> Dict[nn.Parameter, torch.Tensor]:
-    """g_logits [B, L_local] -> {parameter: gradient} for this rank's label rows (sum over ranks = full gradient)."""
+def backward_train(ops, comm, ctx, g_logits, reduce_gradients: bool = False) -> Dict[nn.Parameter, torch.Tensor]:
+    """g_logits [B, L_local] -> {parameter: gradient} for this rank's label rows (sum over ranks = full gradient).
+    reduce_gradients: all-reduce every gradient over the ranks inside the backward, overlapped with it (see _Grads); the
+    returned gradients are then those of the whole batch and `allreduce_gradients` must not be called again."""
     comm = comm or _NoComm()
-    grads: Dict = {}
     sharded = ctx["sharded"]
+    grads = _Grads(comm if (reduce_gradients and sharded) else None)
     dPe, dLe = pairs_backward(ops, comm, ctx["pairs"], g_logits.reshape(-1), sharded, grads)
+    head_backward(ops, comm, dLe, ctx["saved_l"], ctx["L_total"], sharded, grads)      # the larger head first
     head_backward(ops, comm, dPe, ctx["saved_p"], ctx["B"], False, grads)
-    head_backward(ops, comm, dLe, ctx["saved_l"], ctx["L_total"], sharded, grads)
+    grads.wait()
     return grads
 
 
@@ -255,26 +318,68 @@ class _TrainFunction(torch.autograd.Function):
     (ProtNoteTrainer.py:738) delivers their gradients exactly as it does for the reference module."""
 
     @staticmethod
-    def forward(fctx, ops, comm, model, P_f, L_f, L_total, *params):
+    def forward(fctx, ops, comm, model, P_f, L_f, L_total, reduce_gradients, *params):
         logits, ctx = forward_train(ops, comm, model, P_f, L_f, L_total)
-        fctx.ops, fctx.comm, fctx.tctx, fctx.params = ops, comm, ctx, params
+        fctx.ops, fctx.comm, fctx.tctx, fctx.params, fctx.reduce = ops, comm, ctx, params, reduce_gradients
         return logits
 
     @staticmethod
     def backward(fctx, g_logits):
-        grads = backward_train(fctx.ops, fctx.comm, fctx.tctx, g_logits.contiguous())
+        grads = backward_train(fctx.ops, fctx.comm, fctx.tctx, g_logits.contiguous(), fctx.reduce)
         fctx.tctx = None
         out = tuple(grads.get(p) if p.requires_grad else None for p in fctx.params)
-        return (None, None, None, None, None, None) + out
+        return (None, None, None, None, None, None, None) + out
 
 
-def train_logits(model, P_f, L_f, ops=None, comm=None, L_total=None):
-    """Differentiable training-mode logits [B, L_local] of a protnote_b200.ProtNote module."""
+def train_logits(model, P_f, L_f, ops=None, comm=None, L_total=None, reduce_gradients=False):
+    """Differentiable training-mode logits [B, L_local] of a protnote_b200.ProtNote module.
+    reduce_gradients=True (label-sharded ranks): the backward all-reduces the parameter gradients itself, overlapped with
+    the remaining backward GEMMs; do not call `allreduce_gradients` afterwards."""
     if ops is None:
         from .train_native import NativeOps
         ops = NativeOps(model.precision)
     params = trainable_parameters(model)
-    return _TrainFunction.apply(ops, comm, model, P_f.detach(), L_f.detach(), L_total, *params)
+    return _TrainFunction.apply(ops, comm, model, P_f.detach(), L_f.detach(), L_total, bool(reduce_gradients), *params)
+
+
+class _TrainLossFunction(torch.autograd.Function):
+    """Loss fused into the last kernel of the forward: returns (loss, logits); the logits carry no graph
+    (they are for metrics), `loss.backward()` seeds the backward with the d loss / d logit the forward kernel left behind."""
+
+    @staticmethod
+    def forward(fctx, ops, comm, model, P_f, L_f, targets, spec, L_total, reduce_gradients, *params):
+        logits, ctx = forward_train(ops, comm, model, P_f, L_f, L_total, loss=spec, targets=targets)
+        pairs = ctx["pairs"]
+        total = float(ctx["B"] * ctx["L_total"]) if spec.reduction == "mean" else 1.0
+        loss = (pairs.pop("loss_sum") / total).to(torch.float32).reshape(())
+        fctx.ops, fctx.comm, fctx.tctx, fctx.params, fctx.reduce = ops, comm, ctx, params, reduce_gradients
+        fctx.mark_non_differentiable(logits)
+        return loss, logits
+
+    @staticmethod
+    def backward(fctx, g_loss, _g_logits):
+        pairs = fctx.tctx["pairs"]
+        g_logits = pairs.pop("g_seed") * g_loss.to(torch.float32)
+        grads = backward_train(fctx.ops, fctx.comm, fctx.tctx, g_logits, fctx.reduce)
+        fctx.tctx = None
+        out = tuple(grads.get(p) if p.requires_grad else None for p in fctx.params)
+        return (None,) * 9 + out
+
+
+def train_loss(model, P_f, L_f, targets, loss="bce", pos_weight=None, gamma=2.0, alpha=-1.0, label_smoothing=0.0,
+               reduction="mean", ops=None, comm=None, L_total=None, reduce_gradients=False):
+    """(loss, logits [B, L_local]) of one training-mode forward with the loss evaluated inside the last kernel.
+    `loss`: 'bce' (BCEWithLogitsLoss, optional pos_weight [L_local] or scalar) or 'focal' (FocalLoss(alpha, gamma,
+    label_smoothing), protnote/utils/losses.py:171-213).  On label-sharded ranks the returned loss is this rank's share
+    (sum of its pairs' losses / (B * L_total) for 'mean'): the sum over ranks is the loss of the whole batch, and
+    `loss.backward()` produces exactly the gradients the unsharded step would."""
+    if ops is None:
+        from .train_native import NativeOps
+        ops = NativeOps(model.precision)
+    spec = LossSpec(loss, pos_weight, gamma, alpha, label_smoothing, reduction)
+    params = trainable_parameters(model)
+    return _TrainLossFunction.apply(ops, comm, model, P_f.detach(), L_f.detach(), targets.detach(), spec, L_total,
+                                    bool(reduce_gradients), *params)
 
 
 def allreduce_gradients(model, comm: Comm):

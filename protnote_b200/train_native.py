@@ -208,6 +208,32 @@ class NativeOps:
                                             stream_ptr()))
         return out
 
+    def bn_relu_dot_loss(self, z: Act, st, w, b, targets, L, spec):
+        """bn_relu_dot with the loss of `spec` (train.LossSpec) fused in: returns (logits [rows], g_seed [rows] = grad_scale *
+        d loss / d logit, loss_sum fp64 [1] = sum of the per-pair losses of this rank's rows)."""
+        dev = z.hi.device
+        out = torch.empty(z.rows, dtype=torch.float32, device=dev)
+        g = torch.empty(z.rows, dtype=torch.float32, device=dev)
+        loss_sum = torch.zeros(1, dtype=torch.float64, device=dev)
+        w = self._f32(w, "output weight").reshape(-1)
+        b = self._f32(b, "output bias").reshape(-1)
+        t = self._f32(targets, "targets").reshape(-1)
+        if t.numel() != z.rows:
+            raise ValueError(f"targets hold {t.numel()} entries, the batch has {z.rows} (protein, label) pairs")
+        pw = None
+        if spec.pos_weight is not None:
+            pw = self._f32(spec.pos_weight, "pos_weight").reshape(-1)
+            if pw.numel() == 1:
+                pw = pw.expand(L).contiguous()
+            if pw.numel() != L:
+                raise ValueError(f"pos_weight has {pw.numel()} entries for {L} label rows")
+        with torch.cuda.device(dev):
+            check(self.lib.pn_t_bn_relu_dot_loss(ptr(z.hi), ptr(z.lo), z.rows, z.cols, z.ld, ptr(st), ptr(w), ptr(b), ptr(out),
+                                                 ptr(t), int(L), ptr(pw), spec.kind_id, C.c_float(spec.gamma),
+                                                 C.c_float(spec.alpha), C.c_float(spec.label_smoothing),
+                                                 C.c_float(spec.grad_scale), ptr(g), ptr(loss_sum), stream_ptr()))
+        return out, g, loss_sum
+
     def pair_hidden(self, a, c, st, want_T=False) -> Act:
         B, H = a.shape
         L = c.shape[0]

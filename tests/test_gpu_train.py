@@ -418,3 +418,31 @@ def test_training_step_degenerate_shapes(B, L):
     assert logits.shape == o_logits.shape and torch.isfinite(logits).all()
     assert all(torch.isfinite(p.grad).all() for p in model.parameters() if p.grad is not None)
     assert float((logits - o_logits).abs().max()) < 5e-2
+
+
+# ---------------------------------------------------------------------------------------------------- fused loss (N4)
+@pytest.mark.parametrize("kw", [dict(loss="bce"), dict(loss="bce", pos_weight="vector", reduction="sum"),
+                                dict(loss="focal", gamma=2.0, alpha=0.25),
+                                dict(loss="focal", gamma=1.0, alpha=-1.0, label_smoothing=0.1)],
+                         ids=lambda k: "-".join(f"{a}={b}" for a, b in k.items()))
+def test_fused_loss_and_seed_match_oracle(kw):
+    """pn_t_bn_relu_dot_loss through train.train_loss: the loss value, the logits and every parameter gradient of
+    `loss.backward()` against the training oracle with the reference's loss formulas (BCE / FocalLoss)."""
+    from oracle.make_golden_train import train_inputs
+    from protnote_b200 import train as pn_train
+    ecfg, scfg, sd, P_f, L_f, y = train_inputs("train_tiny")
+    kw = dict(kw)
+    if kw.get("pos_weight") == "vector":
+        kw["pos_weight"] = torch.rand(L_f.shape[0], generator=torch.Generator().manual_seed(2)) * 3 + 0.5
+    model = build_b200_model(ecfg, scfg, sd).train()
+    dkw = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in kw.items()}
+    loss, logits = pn_train.train_loss(model, P_f.cuda(), L_f.cuda(), y.cuda(), **dkw)
+    loss.backward()
+    torch.cuda.synchronize()
+    o_logits, o_loss, o_grads, _ = train_step_oracle(sd, P_f, L_f, y, scfg, **kw)
+    assert (logits.cpu().double() - o_logits).abs().max() <= 1e-4
+    assert abs(float(loss) - float(o_loss)) <= 1e-5 * max(1.0, abs(float(o_loss)))
+    named = dict(model.named_parameters())
+    for k, g in o_grads.items():
+        got = named[k].grad.cpu().double()
+        assert float((got - g).norm() / g.norm().clamp_min(1e-30)) <= 1e-3, k

@@ -183,3 +183,52 @@ def test_single_row_batchnorm_raises_like_torch():
         pn_train.forward_train(TorchOps(torch.float64), None, model, P_f[:1].double(), L_f.double())
     with pytest.raises(ValueError, match="Expected more than 1 value per channel"):
         pn_train.forward_train(TorchOps(torch.float64), None, model, P_f.double(), L_f[:1].double())
+
+
+# ---------------------------------------------------------------------------------------------------- fused loss (N4)
+LOSSES = [dict(loss="bce"), dict(loss="bce", reduction="sum"), dict(loss="bce", pos_weight="vector"),
+          dict(loss="focal", gamma=2.0, alpha=0.25), dict(loss="focal", gamma=1.0, alpha=-1.0, label_smoothing=0.1),
+          dict(loss="focal", gamma=3.0, alpha=0.6, reduction="sum")]
+
+
+def _loss_kw(kw, L, dtype=torch.float64):
+    kw = dict(kw)
+    if kw.get("pos_weight") == "vector":
+        kw["pos_weight"] = (torch.rand(L, generator=torch.Generator().manual_seed(2)) * 3 + 0.5).to(dtype)
+    return kw
+
+
+@pytest.mark.skipif(not reference_available(), reason="needs /root/reference (build container only)")
+def test_focal_loss_oracle_matches_reference_class(capsys):
+    """oracle.train_oracle.focal_loss == the reference's FocalLoss module (protnote/utils/losses.py:171-213), values and
+    gradients, over every option combination the fused kernel implements."""
+    import_reference()
+    from protnote.utils.losses import FocalLoss
+    from oracle.train_oracle import focal_loss
+    g = torch.Generator().manual_seed(0)
+    x = (torch.randn(7, 33, generator=g, dtype=torch.float64) * 4).requires_grad_(True)
+    t = (torch.rand(7, 33, generator=g) < 0.2).double()
+    for alpha, gamma, ls, red in ((0.25, 2.0, 0.0, "mean"), (-1.0, 1.0, 0.1, "mean"), (0.6, 3.0, 0.05, "sum"), (0.5, 0.5, 0.0, "mean")):
+        ref = FocalLoss(alpha=alpha, gamma=gamma, reduction=red, label_smoothing=ls)(x, t)
+        (gr,) = torch.autograd.grad(ref, x)
+        ours = focal_loss(x, t, alpha, gamma, ls, red)
+        (go,) = torch.autograd.grad(ours, x)
+        assert abs(float(ref) - float(ours)) < 1e-13 and (gr - go).abs().max() < 1e-13
+
+
+@pytest.mark.parametrize("kw", LOSSES, ids=lambda k: "-".join(f"{a}={b}" for a, b in k.items()))
+def test_fused_loss_sequencing_matches_oracle(kw):
+    """train.train_loss (loss + gradient seed produced by the last forward primitive) == loss(logits).backward() of the
+    oracle, run with the torch stand-in for the primitives."""
+    ecfg, scfg, sd, P_f, L_f, y = _problem(B=5, L=9, seed=21)
+    kw = _loss_kw(kw, L_f.shape[0])
+    model = build_b200_model(ecfg, scfg, sd, device="cpu").double().train()
+    loss, logits = pn_train.train_loss(model, P_f.double(), L_f.double(), y.double(), ops=TorchOps(torch.float64), **kw)
+    assert not logits.requires_grad
+    (loss * 1.0).backward()
+    o_logits, o_loss, o_grads, _ = train_step_oracle(sd, P_f, L_f, y, scfg, **kw)
+    assert (logits - o_logits).abs().max() < 1e-9
+    assert abs(float(loss) - float(o_loss)) <= 1e-6 * max(1.0, abs(float(o_loss)))      # the fused loss leaves as fp32
+    named = dict(model.named_parameters())
+    for k, g in o_grads.items():
+        assert (named[k].grad - g).abs().max() <= 1e-9 * max(1.0, float(g.abs().max())), k

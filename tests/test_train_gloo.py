@@ -32,7 +32,7 @@ def _problem():
     return ecfg, scfg, sd, torch.randn(B, 72, generator=g), torch.randn(L, 40, generator=g), synth_targets(B, L, 21)
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, fused=False):
     try:
         os.environ["MASTER_ADDR"] = "127.0.0.1"
         os.environ["MASTER_PORT"] = str(port)
@@ -42,12 +42,20 @@ def _worker(rank, world, port, q):
         model = build_b200_model(ecfg, scfg, sd, device="cpu").double().train()
         comm = pn_train.Comm()
         ls, le = label_row_bounds(L_f.shape[0], 1, rank, world)
-        logits = pn_train.train_logits(model, P_f.double(), L_f[ls:le].double(), ops=TorchOps(torch.float64), comm=comm,
-                                       L_total=L_f.shape[0])
-        # the loss of the whole batch is the mean over all B x L pairs: each rank contributes its slab's sum
-        loss = torch.nn.functional.binary_cross_entropy_with_logits(logits, y[:, ls:le].double(), reduction="sum") / y.numel()
-        loss.backward()
-        pn_train.allreduce_gradients(model, comm)
+        if fused:
+            # loss fused into the last forward primitive (focal, the reference's default LOSS_FN) and the parameter
+            # gradients all-reduced inside the backward, overlapped with it: no allreduce_gradients call
+            loss, logits = pn_train.train_loss(model, P_f.double(), L_f[ls:le].double(), y[:, ls:le].double(), loss="focal",
+                                               gamma=2.0, alpha=0.25, ops=TorchOps(torch.float64), comm=comm,
+                                               L_total=L_f.shape[0], reduce_gradients=True)
+            loss.backward()
+        else:
+            logits = pn_train.train_logits(model, P_f.double(), L_f[ls:le].double(), ops=TorchOps(torch.float64), comm=comm,
+                                           L_total=L_f.shape[0])
+            # the loss of the whole batch is the mean over all B x L pairs: each rank contributes its slab's sum
+            loss = torch.nn.functional.binary_cross_entropy_with_logits(logits, y[:, ls:le].double(), reduction="sum") / y.numel()
+            loss.backward()
+            pn_train.allreduce_gradients(model, comm)
         total = loss.detach().clone()
         dist.all_reduce(total)
         if rank == 0:
@@ -65,12 +73,16 @@ def _worker(rank, world, port, q):
         raise
 
 
-def test_label_sharded_training_step_equals_single_process():
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("fused", [False, True], ids=["bce_via_autograd", "fused_focal_overlapped_allreduce"])
+def test_label_sharded_training_step_equals_single_process(fused):
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, fused)) for r in range(world)]
     for p in procs:
         p.start()
     results = [q.get(timeout=300) for _ in range(world)]
@@ -84,10 +96,11 @@ def test_label_sharded_training_step_equals_single_process():
     bufs = {k: torch.from_numpy(v) for k, v in bufs.items()}
     logits0 = torch.from_numpy(logits0)
     ecfg, scfg, sd, P_f, L_f, y = _problem()
-    o_logits, o_loss, o_grads, o_stats = train_step_oracle(sd, P_f, L_f, y, scfg)
+    kw = dict(loss="focal", gamma=2.0, alpha=0.25) if fused else {}
+    o_logits, o_loss, o_grads, o_stats = train_step_oracle(sd, P_f, L_f, y, scfg, **kw)
     ls, le = label_row_bounds(L_f.shape[0], 1, 0, world)
     assert (logits0 - o_logits[:, ls:le]).abs().max() < 1e-9
-    assert abs(loss - float(o_loss)) < 1e-10
+    assert abs(loss - float(o_loss)) < (1e-7 if fused else 1e-10)      # the fused loss leaves each rank as fp32
     for k, g in o_grads.items():
         assert (grads[k] - g).abs().max() <= 1e-9 * max(1.0, float(g.abs().max())), k
     for k, v in o_stats.items():
