@@ -672,7 +672,11 @@ class TrainStep:
         onehots_h, lengths_h, labels_h = synthetic_inputs(B, T, L, pinned=False)
         ls, le = label_row_bounds(L, 1, rank, world)
         y_h = (torch.rand(B, L, generator=torch.Generator().manual_seed(5)) < 0.02).float()
-        self.x_h, self.len_h = onehots_h.pin_memory(), lengths_h.pin_memory()
+        from protnote_b200.sharded import shard_bounds
+        ps, pe = shard_bounds(B, rank, world)      # the frozen encoder runs on this rank's proteins only
+        self.x_h, self.len_h = onehots_h[ps:pe].contiguous().pin_memory(), lengths_h[ps:pe].contiguous().pin_memory()
+        if world > 1:
+            self.model.sequence_encoder.train_shard = (None, B)
         self.lab_h, self.yl_h = labels_h[ls:le].contiguous().pin_memory(), y_h[:, ls:le].contiguous().pin_memory()
         self.h2d = onehots_h.numel() * 4 + lengths_h.numel() * 8 + labels_h.numel() * 4 + y_h.numel() * 4
         self.x_d, self.len_d, self.lab_d, self.y_d = (t.to(dev) for t in (self.x_h, self.len_h, self.lab_h, self.yl_h))
@@ -684,6 +688,9 @@ class TrainStep:
         self.opt.zero_grad(set_to_none=True)
         with torch.no_grad():
             P_f = self.model.sequence_encoder.get_embeddings(x, lens)
+            if self.world > 1:      # [B / W, C] -> [B, C] on every rank (18 KB per protein)
+                from protnote_b200.sharded import all_gather_rows
+                P_f = all_gather_rows(P_f, self.B)
         # BCE evaluated inside the last forward kernel (loss + gradient seed: the [B, L] logits never round-trip through
         # autograd); the parameter gradients are all-reduced inside the backward, overlapped with its GEMMs
         loss, _ = pn_train.train_loss(self.model, P_f, lab, y, loss=self.loss_name, comm=self.comm, L_total=self.L,
@@ -780,9 +787,25 @@ def train_parity_small(dev, rank, world):
     if world > 1:
         import torch.distributed as dist
         dist.all_reduce(tot)
+    # the frozen encoder in train mode with the SEQUENCES sharded over the ranks (BatchNorm sums all-reduced)
+    from oracle.train_oracle import proteinfer_embeddings_train
+    from protnote_b200.sharded import all_gather_rows, shard_bounds
+    from tests.helpers import load_case
+    e_ecfg, e_scfg, e_sd, onehots, lengths, _, _ = load_case("tiny_concat")
+    enc = build_b200_model(e_ecfg, e_scfg, e_sd, device=dev).train().sequence_encoder
+    ps, pe = shard_bounds(onehots.shape[0], rank, world)
+    if world > 1:
+        enc.train_shard = (None, onehots.shape[0])
+    with torch.no_grad():
+        emb = enc.get_embeddings(onehots[ps:pe].to(dev), lengths[ps:pe].to(dev))
+        emb = all_gather_rows(emb, onehots.shape[0]) if world > 1 else emb
     if rank != 0:
         return None
     torch.set_num_threads(host_cores())
+    o_emb, o_stats = proteinfer_embeddings_train(e_sd, onehots, lengths, e_ecfg)
+    enc_err = float((emb.cpu().double() - o_emb).abs().max())
+    bufs = dict(enc.named_buffers())
+    stat_err = max(float((bufs[k[len("sequence_encoder."):]].cpu().double() - v).abs().max()) for k, v in o_stats.items())
     o_logits, o_loss, o_grads, _ = train_step_oracle(sd, P_f, L_f, y, scfg)
     named = dict(model.named_parameters())
     worst_rel, worst_max = 0.0, 0.0
@@ -796,7 +819,11 @@ def train_parity_small(dev, rank, world):
             "loss": float(tot), "oracle_loss": float(o_loss), "abs_loss_err": abs(float(tot) - float(o_loss)),
             "gradients_checked": len(o_grads), "worst_gradient_rel_l2_err": worst_rel,
             "worst_gradient_max_err_over_max_entry": worst_max,
-            "within_tol": bool((full.cpu().double() - o_logits).abs().max() <= TOL and worst_max <= 1e-3)}
+            "encoder_train_mode": {"what": "frozen encoder, BatchNorm batch statistics, sequences sharded over the ranks "
+                                           "(golden case tiny_concat) vs oracle.train_oracle.proteinfer_embeddings_train (fp64)",
+                                   "max_abs_embedding_err": enc_err, "max_abs_running_stat_err": stat_err},
+            "within_tol": bool((full.cpu().double() - o_logits).abs().max() <= TOL and worst_max <= 1e-3
+                               and enc_err <= 1e-5 and stat_err <= 1e-5)}
 
 
 def train_line(r, mode, world, B, T, L, steps, warmup):

@@ -38,13 +38,29 @@ int pn_version(void);
 const char* pn_last_error(void);
 /* 0 if `device` is a compute-capability 10.x GPU this library can run on. */
 int pn_device_check(int device);
-/* Engine knobs: "bk" = 32 | 64 (k-block / swizzle width, 0 = auto); "promote_k_encoder" | "promote_k_heads" |
- * "promote_k_scorer" | "promote_k" (all): strict mode, K elements summed in TMEM between fp32 promotions
- * (0 = never); "chunk_rows" (pairs per scorer chunk, 0 = auto); "cta2" (1: CTA-pair kernels, tcgen05 cta_group::2,
- * 256-row tiles; 0: single-CTA kernels; -1, the default: pairs in PN_FAST mode only, where they are faster); "split_corr" (1: strict-mode encoder convolutions accumulate the hi*hi
- * products and the lo corrections in separate TMEM buffers, 10 % faster encoder at a smaller parity margin; 0, the
- * default: one accumulator, promotion every 32 K); "fuse_features" (1: layer 1 of the pair scorer is built
- * inside the first GEMM's operand producer; 0, the default: separate kernel with an HBM round trip - faster today). */
+/* Engine knobs.  STATE IS PROCESS-GLOBAL (one process drives one GPU in the intended deployment, bin/main.py: mp.spawn, one
+ * rank per device): two models in one process cannot hold different options, and packed weights depend on some of them
+ * (the truncation compensation follows the promotion periods and "bk") - re-pack after changing those.  pn_last_error is
+ * thread-local; the optional timing list is mutex-guarded; everything else is plain state set before use.
+ *   "bk" = 32 | 64             k-block / swizzle width (0 = auto: 32 strict, 64 fast)
+ *   "promote_k_encoder" | "promote_k_pointwise" | "promote_k_heads" | "promote_k_scorer" | "promote_k_other" | "promote_k"
+ *                              strict mode: K elements summed in TMEM between fp32 promotions, per stage of the path
+ *                              (dilated convs + conv1 | 1x1 convs | W_p, W_l, layer-1 halves | output MLP | pn_linear,
+ *                              pn_conv1d | all); 0 = never promote.  Defaults 64 | 64 | 32 | 256 | 64.
+ *   "trunc_beta_ppt"           strict mode: expected shrink of the running sum per tensor-core accumulator add (the add
+ *                              rounds toward zero), in 1e-12 units; folded into the packed weights per K position so that
+ *                              the bias of every chunk cancels (csrc/pn_kernels.cuh, pack_weight_kernel).  Default 33000
+ *                              (measured on B200, tools/trunc_comp_probe.py); 0 = off (round-1 arithmetic).
+ *   "trunc_comp_c1" / "_c0"    uniform variant applied in the epilogue instead, (c1 * K_chunk + c0) * 1e-12; default off
+ *   "cta2"                     CTA-pair kernels (tcgen05 cta_group::2, 256-row tiles, each CTA loads half the weight tile):
+ *                              1 (default) wherever a problem has more than one 128-row tile, 0 never, -1 in PN_FAST mode
+ *                              only, 2 always
+ *   "chunk_rows"               pairs per scorer chunk (0 = auto)
+ *   "split_corr"               1: strict-mode encoder convolutions accumulate the hi*hi products and the lo corrections in
+ *                              separate TMEM buffers (round-1 experiment; default 0)
+ *   "fuse_features"            1: layer 1 of the pair scorer is built inside the first GEMM's operand producer (correct but
+ *                              slower than the separate kernel, profiles/r01_fused_generator_probe.txt; default 0)
+ *   "stats_tx"                 threads along the columns of a training-step reduction block */
 int pn_set_option(const char* name, long long value);
 /* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
 long long pn_launch_count(void);
@@ -101,6 +117,21 @@ int pn_encoder_forward_train(const pn_encoder_cfg* cfg, const void* packed_raw, 
                              int batch, int T, const float* const* bn_params, int num_bn_params, float momentum,
                              int update_running, float* out, void* workspace, size_t workspace_bytes, int mode,
                              void* stream);
+
+/* The same forward with the SEQUENCES sharded over ranks (one process per GPU): this rank passes its `batch` sequences;
+ * after the per-channel sums of every BatchNorm have been produced on `stream` the library calls
+ *     reduce(stats, count, user, stream)          (host callback; must ENQUEUE a sum over ranks of the `count` doubles at
+ *                                                   device pointer `stats` in stream order and return 0)
+ * and normalises with the all-rank statistics over `total_positions` = T * (sequences of all ranks) positions.  The result
+ * equals the unsharded pn_encoder_forward_train on the concatenated batch (running statistics included, on every rank).
+ * `stats_buffer`: device buffer of >= 2 * round_up(channels, 64) doubles owned by the caller (so that the callback can
+ * hand a tensor it already owns to its collective library); reduce == NULL -> plain single-rank behaviour. */
+typedef int (*pn_reduce_fn)(double* stats, int count, void* user, void* stream);
+int pn_encoder_forward_train_sharded(const pn_encoder_cfg* cfg, const void* packed_raw, const float* x,
+                                     const int64_t* lengths, int batch, int T, const float* const* bn_params,
+                                     int num_bn_params, float momentum, int update_running, float* out, void* workspace,
+                                     size_t workspace_bytes, int mode, double total_positions, double* stats_buffer,
+                                     pn_reduce_fn reduce, void* user, void* stream);
 
 /* Same from token ids: tokens [batch][T] uint8 (index into the sorted amino-acid vocabulary, i.e. the argmax of the one-hot
  * the reference's collator builds, protnote/data/collators.py:123-133; ids >= input_channels give an all-zero column).

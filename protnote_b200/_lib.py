@@ -42,6 +42,9 @@ _SZ = C.c_size_t
 _I = C.c_int
 
 # name -> (restype, argtypes); every symbol include/protnote_b200.h declares
+# host callback of pn_encoder_forward_train_sharded: (device pointer, count, user, stream) -> 0 on success
+REDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p)
+
 SIGNATURES = {
     "pn_version": (_I, []),
     "pn_last_error": (C.c_char_p, []),
@@ -58,6 +61,8 @@ SIGNATURES = {
     "pn_encoder_train_workspace_bytes": (_SZ, [C.POINTER(EncoderCfg), _I, _I]),
     "pn_encoder_forward_train": (_I, [C.POINTER(EncoderCfg), _P, _P, _P, _I, _I, C.POINTER(_P), _I, C.c_float, _I, _P, _P,
                                       _SZ, _I, _P]),
+    "pn_encoder_forward_train_sharded": (_I, [C.POINTER(EncoderCfg), _P, _P, _P, _I, _I, C.POINTER(_P), _I, C.c_float, _I, _P,
+                                              _P, _SZ, _I, C.c_double, _P, REDUCE_FN, _P, _P]),
     "pn_encoder_forward_tokens": (_I, [C.POINTER(EncoderCfg), _P, _P, _P, _I, _I, _P, _P, _SZ, _I, _P]),
     "pn_postprocess": (_I, [_P, _LL, _LL, _LL, _P, _I, _LL, C.c_float, _P, _LL, _P, _P, _P, _I, _P, _P, _P]),
     "pn_scorer_num_params": (_I, [C.POINTER(ScorerCfg)]),

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -191,24 +192,32 @@ int strict_chunk_kblocks(int stage_kind, int bk, int num_kblocks, int promote_ov
   return chunk;
 }
 
-int g_num_sms = 0;
-int num_sms() {
-  if (g_num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
-  }
-  return g_num_sms;
+// per-device caches (a process may drive more than one GPU: cuda:0 then cuda:1)
+constexpr int kMaxDevices = 64;
+int g_num_sms[kMaxDevices] = {0};
+int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev >= 0 && dev < kMaxDevices ? dev : 0;
 }
+int num_sms() {
+  const int dev = current_device();
+  if (g_num_sms[dev] == 0) {
+    cudaDeviceGetAttribute(&g_num_sms[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms[dev] <= 0) g_num_sms[dev] = 148;
+  }
+  return g_num_sms[dev];
+}
+std::mutex g_timed_mutex;   // guards g_timed (the optional per-launch event list)
 
 template <int BK, int NPASS, bool GEN = false>
 int launch_gemm_t(const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BK, NPASS, GEN>;
-  static bool configured = false;
-  if (!configured) {
+  // the attribute is per device: remember it per device, not per process
+  static bool configured[kMaxDevices] = {false};
+  if (!configured[current_device()]) {
     PN_CUDA(cudaFuncSetAttribute(gemm_kernel<BK, NPASS, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    configured = true;
+    configured[current_device()] = true;
   }
   const int total = p.tiles_m * p.tiles_n;
   const int grid = total < num_sms() ? total : num_sms();
@@ -224,6 +233,7 @@ int launch_gemm_t(const GemmParams& p, cudaStream_t stream) {
   PN_CUDA(cudaGetLastError());
   if (timed) {
     PN_CUDA(cudaEventRecord(tl.stop, stream));
+    std::lock_guard<std::mutex> lock(g_timed_mutex);
     g_timed.push_back(tl);
   }
   g_launches++;
@@ -233,10 +243,10 @@ int launch_gemm_t(const GemmParams& p, cudaStream_t stream) {
 template <int BK, int NPASS>
 int launch_gemm2_t(const GemmParams& p, cudaStream_t stream) {
   using Cfg = Gemm2Cfg<BK, NPASS>;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {false};
+  if (!configured[current_device()]) {
     PN_CUDA(cudaFuncSetAttribute(gemm2_kernel<BK, NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    configured = true;
+    configured[current_device()] = true;
   }
   const int total = p.tiles_m * p.tiles_n;
   int clusters = num_sms() / 2;
@@ -253,6 +263,7 @@ int launch_gemm2_t(const GemmParams& p, cudaStream_t stream) {
   PN_CUDA(cudaGetLastError());
   if (timed) {
     PN_CUDA(cudaEventRecord(tl.stop, stream));
+    std::lock_guard<std::mutex> lock(g_timed_mutex);
     g_timed.push_back(tl);
   }
   g_launches++;
@@ -749,6 +760,7 @@ int pn_device_check(int device) {
 }
 
 int pn_gemm_timing(int enable) {
+  std::lock_guard<std::mutex> lock(g_timed_mutex);
   for (TimedLaunch& t : g_timed) {
     cudaEventDestroy(t.start);
     cudaEventDestroy(t.stop);
@@ -760,6 +772,7 @@ int pn_gemm_timing(int enable) {
 
 int pn_gemm_timing_read(double* total_ms, long long* launches, double* algorithmic_flops) {
   double ms = 0.0, fl = 0.0;
+  std::lock_guard<std::mutex> lock(g_timed_mutex);
   for (TimedLaunch& t : g_timed) {
     PN_CUDA(cudaEventSynchronize(t.stop));
     float e = 0.f;
@@ -1046,7 +1059,19 @@ int pn_encoder_forward_train(const pn_encoder_cfg* cfg, const void* packed_raw, 
                              int batch, int T, const float* const* bn_params, int num_bn_params, float momentum,
                              int update_running, float* out, void* workspace, size_t workspace_bytes, int mode,
                              void* stream_) {
+  return pn_encoder_forward_train_sharded(cfg, packed_raw, x, lengths, batch, T, bn_params, num_bn_params, momentum,
+                                          update_running, out, workspace, workspace_bytes, mode, (double)batch * T, nullptr,
+                                          nullptr, nullptr, stream_);
+}
+
+int pn_encoder_forward_train_sharded(const pn_encoder_cfg* cfg, const void* packed_raw, const float* x,
+                                     const int64_t* lengths, int batch, int T, const float* const* bn_params,
+                                     int num_bn_params, float momentum, int update_running, float* out, void* workspace,
+                                     size_t workspace_bytes, int mode, double total_positions, double* stats_buffer,
+                                     pn_reduce_fn reduce, void* user, void* stream_) {
   PN_TRY(check_encoder_cfg(cfg));
+  if (reduce && !stats_buffer) return fail("sharded training-mode encoder needs a caller-owned stats_buffer");
+  if (!(total_positions >= (double)batch * T)) return fail("total_positions (%g) < this rank's positions", total_positions);
   const pn_encoder_cfg& c = *cfg;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (batch <= 0 || T <= 0 || !x) return fail("empty encoder input (batch %d, T %d)", batch, T);
@@ -1065,7 +1090,7 @@ int pn_encoder_forward_train(const pn_encoder_cfg* cfg, const void* packed_raw, 
   PN_CUDA(cudaGetLastError());
   float* X = ws.at<float>(W.x);
   float* Hraw = ws.at<float>(W.hraw);
-  double* stats = ws.at<double>(W.stats);
+  double* stats = stats_buffer ? stats_buffer : ws.at<double>(W.stats);
   float* state = ws.at<float>(W.state);
   ConvView cv;
   cv.batch = batch; cv.T = T; cv.lengths = len;
@@ -1083,7 +1108,8 @@ int pn_encoder_forward_train(const pn_encoder_cfg* cfg, const void* packed_raw, 
   auto bn_relu = [&](const float* src, int cols, long long ld_src, const float* const* q, __half* hi, __half* lo,
                      long long ld_dst) -> int {
     PN_TRY(pn_t_col_stats(nullptr, nullptr, src, pos, cols, ld_src, stats, stream));
-    PN_TRY(pn_t_bn_finalize(stats, (double)pos, nullptr, 0.0, q[0], q[1], c.bn_eps, momentum,
+    if (reduce && reduce(stats, 2 * cols, user, stream_) != 0) return fail("the BatchNorm-sum reduction callback failed");
+    PN_TRY(pn_t_bn_finalize(stats, total_positions, nullptr, 0.0, q[0], q[1], c.bn_eps, momentum,
                             update_running ? const_cast<float*>(q[2]) : nullptr,
                             update_running ? const_cast<float*>(q[3]) : nullptr, cols, state, stream));
     BnReluMaskF32Producer p{src, pos, cols, ld_src, state, len, T};
@@ -1342,7 +1368,7 @@ int pn_score_pairs_ex(const pn_scorer_cfg* cfg, const void* packed, const float*
       const bool fuse_features = fuse_ok && nl % kBM == 0;   // a tile = one protein x 128 consecutive label rows
       if (c.fusion != PN_FUSION_CONCAT_PROD && !fuse_features) {
         const int pf_threads = (int)(round_up(ld_h / 8, 32) < 1024 ? round_up(ld_h / 8, 32) : 1024);
-        pair_features_kernel<<<(unsigned)((rows + kPairRows - 1) / kPairRows), pf_threads, 0, stream>>>(a, H, c_in, H, (int)b0, (int)l0, (int)nl, rows,
+        pair_features_kernel<<<(unsigned)((nl + kPairRows - 1) / kPairRows), pf_threads, 0, stream>>>(a, H, c_in, H, (int)b0, (int)l0, (int)nl, (int)nb,
                                                                              H, buf_hi[0], mode == PN_STRICT ? buf_lo[0] : nullptr,
                                                                              ld_h);
         g_launches++;

@@ -187,43 +187,49 @@ __global__ void conv_input_tokens_kernel(const uint8_t* __restrict__ tokens, con
 // (reference protnote/models/ProtNote.py:112-126,293 materialises [B*L, 2d]; here it never exists):
 //   h1[(b,l)][k] = relu(a[b][k] + c[l][k])      a = BN1-folded protein half, c = BN1-scaled label half
 // rows of the chunk are pairs (b0 + r / nl, l0 + r % nl); output fp16 planes [nb*nl][ld].
-// One block = kPairRows consecutive pair rows; thread t = 8-column chunk t of every one of them (row and protein
-// indices are per-block scalars: the first version spent four 64-bit div/mod per 8 elements and was bound by
-// instruction issue at the power-capped clock, not by HBM).  grid (ceil(rows / kPairRows)), block = ld / 8 threads
-// rounded up to a warp (<= 1024).
+// One block = kPairRows consecutive LABEL rows x all nb proteins of the chunk; thread t = 8-column chunk t.  The label
+// half c[l] (12 KB per row, 400 MB at 32K rows - larger than the L2) is read ONCE per chunk and kept in registers while
+// the nb protein halves (nb * 12 KB, L1/L2 resident) stream past it; the first version walked pair rows protein-major and
+// re-read every c row once per protein (ncu: 4.0 GB read for 4.0 GB written per 2^19-pair chunk,
+// profiles/r02_scorer_launch_list.txt).  grid (ceil(nl / kPairRows)), block = ld / 8 threads rounded up to a warp.
 constexpr int kPairRows = 16;
 __global__ void pair_features_kernel(const float* __restrict__ a, long long lda, const float* __restrict__ c,
-                                     long long ldc, int b0, int l0, int nl, long long rows, int H,
+                                     long long ldc, int b0, int l0, int nl, int nb, int H,
                                      __half* __restrict__ hi, __half* __restrict__ lo, int ld) {
   const int chunks = ld / 8;
   const bool vec = ((lda | ldc) & 3) == 0;
-  const long long r_begin = (long long)blockIdx.x * kPairRows;
-  long long bb = r_begin / nl;                 // one division per block
-  int l = (int)(r_begin - bb * nl);
-  for (int rr = 0; rr < kPairRows; ++rr) {
-    const long long r = r_begin + rr;
-    if (r >= rows) break;
-    const float* arow = a + (b0 + bb) * lda;
-    const float* crow = c + (long long)(l0 + l) * ldc;
-    for (int ch = threadIdx.x; ch < chunks; ch += blockDim.x) {
-      const int k0 = ch * 8;
-      float v[8];
-      if (k0 + 8 <= H && vec) {
-        const float4 a0 = __ldg(reinterpret_cast<const float4*>(arow + k0)), a1 = __ldg(reinterpret_cast<const float4*>(arow + k0 + 4));
+  const int l_begin = blockIdx.x * kPairRows;
+  for (int ch = threadIdx.x; ch < chunks; ch += blockDim.x) {
+    const int k0 = ch * 8;
+    const bool fast = k0 + 8 <= H && vec;
+    for (int rr = 0; rr < kPairRows; ++rr) {
+      const int l = l_begin + rr;
+      if (l >= nl) break;
+      const float* crow = c + (long long)(l0 + l) * ldc;
+      float cv[8];
+      if (fast) {
         const float4 c0 = __ldg(reinterpret_cast<const float4*>(crow + k0)), c1 = __ldg(reinterpret_cast<const float4*>(crow + k0 + 4));
-        v[0] = a0.x + c0.x; v[1] = a0.y + c0.y; v[2] = a0.z + c0.z; v[3] = a0.w + c0.w;
-        v[4] = a1.x + c1.x; v[5] = a1.y + c1.y; v[6] = a1.z + c1.z; v[7] = a1.w + c1.w;
+        cv[0] = c0.x; cv[1] = c0.y; cv[2] = c0.z; cv[3] = c0.w; cv[4] = c1.x; cv[5] = c1.y; cv[6] = c1.z; cv[7] = c1.w;
       } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = (k0 + j < H) ? arow[k0 + j] + crow[k0 + j] : 0.f;
+        for (int j = 0; j < 8; ++j) cv[j] = (k0 + j < H) ? crow[k0 + j] : 0.f;
       }
+      for (int bb = 0; bb < nb; ++bb) {
+        const float* arow = a + (long long)(b0 + bb) * lda;
+        float v[8];
+        if (fast) {
+          const float4 a0 = __ldg(reinterpret_cast<const float4*>(arow + k0)), a1 = __ldg(reinterpret_cast<const float4*>(arow + k0 + 4));
+          v[0] = a0.x + cv[0]; v[1] = a0.y + cv[1]; v[2] = a0.z + cv[2]; v[3] = a0.w + cv[3];
+          v[4] = a1.x + cv[4]; v[5] = a1.y + cv[5]; v[6] = a1.z + cv[6]; v[7] = a1.w + cv[7];
+        } else {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
-      split8_store(v, hi + r * ld + k0, lo ? lo + r * ld + k0 : nullptr);
-    }
-    if (++l == nl) {
-      l = 0;
-      ++bb;
+          for (int j = 0; j < 8; ++j) v[j] = (k0 + j < H) ? arow[k0 + j] + cv[j] : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+        const long long r = (long long)bb * nl + l;
+        split8_store(v, hi + r * ld + k0, lo ? lo + r * ld + k0 : nullptr);
+      }
     }
   }
 }

@@ -184,9 +184,13 @@ def _encoder_pack_raw(self, params: Sequence[torch.Tensor]):
 
 
 def _encoder_forward_train(self, x: torch.Tensor, lengths: torch.Tensor, bn_params: Sequence[torch.Tensor],
-                           momentum: float, update_running: bool = True, mode: int = PN_STRICT) -> torch.Tensor:
+                           momentum: float, update_running: bool = True, mode: int = PN_STRICT, group=None,
+                           total_sequences: Optional[int] = None) -> torch.Tensor:
     """Batch-statistic BatchNorm forward of the encoder (pn_encoder_forward_train); bn_params: per block
-    bn1.{weight, bias, running_mean, running_var}, bn2.{...} - the running statistics are updated in place."""
+    bn1.{weight, bias, running_mean, running_var}, bn2.{...} - the running statistics are updated in place.
+    With `total_sequences` (and an initialised torch.distributed group) `x` holds THIS RANK's sequences of a batch of
+    `total_sequences`: the per-channel sums of every BatchNorm are all-reduced between the statistics pass and the
+    normalisation pass (pn_encoder_forward_train_sharded), so the result is the unsharded batch's."""
     _require_cuda(x, "sequence_onehots")
     dev = self.packed_raw.device
     x = _f32c(x)
@@ -201,10 +205,34 @@ def _encoder_forward_train(self, x: torch.Tensor, lengths: torch.Tensor, bn_para
     if B == 0:
         return out
     ws = scratch(dev, "encoder_train", self.lib.pn_encoder_train_workspace_bytes(C.byref(self.cfg), B, T))
+    if total_sequences is None or int(total_sequences) == B:
+        with torch.cuda.device(dev):
+            check(self.lib.pn_encoder_forward_train(C.byref(self.cfg), ptr(self.packed_raw), ptr(x), ptr(lengths), B, T,
+                                                    pointer_array(bn_params), len(bn_params), C.c_float(momentum),
+                                                    int(update_running), ptr(out), ptr(ws), ws.numel(), mode, stream_ptr()))
+        return out
+    import torch.distributed as dist
+    stats = torch.empty(2 * ((self.cfg.channels + 63) // 64 * 64), dtype=torch.float64, device=dev)
+    failure = []
+
+    def reduce(_ptr, count, _user, _stream):
+        try:
+            dist.all_reduce(stats[:count], group=group)      # stream-ordered after the sums, before the normalisation
+            return 0
+        except Exception as exc:  # noqa: BLE001 - reported through the C return code
+            failure.append(exc)
+            return 1
+
+    cb = _lib.REDUCE_FN(reduce)
     with torch.cuda.device(dev):
-        check(self.lib.pn_encoder_forward_train(C.byref(self.cfg), ptr(self.packed_raw), ptr(x), ptr(lengths), B, T,
-                                                pointer_array(bn_params), len(bn_params), C.c_float(momentum),
-                                                int(update_running), ptr(out), ptr(ws), ws.numel(), mode, stream_ptr()))
+        rc = self.lib.pn_encoder_forward_train_sharded(C.byref(self.cfg), ptr(self.packed_raw), ptr(x), ptr(lengths), B, T,
+                                                       pointer_array(bn_params), len(bn_params), C.c_float(momentum),
+                                                       int(update_running), ptr(out), ptr(ws), ws.numel(), mode,
+                                                       C.c_double(float(total_sequences) * T), ptr(stats), cb, None,
+                                                       stream_ptr())
+    if failure:
+        raise failure[0]
+    check(rc)
     return out
 
 

@@ -74,6 +74,10 @@ class ProteInfer(torch.nn.Module):
         self._dilation_base = dilation_base
         self._packed = None
         self._packed_key = None
+        # training mode, sequences sharded over ranks: (process group or None for the default group, sequences of the whole
+        # batch).  When set, get_embeddings() is handed THIS rank's sequences and the BatchNorm batch statistics are
+        # all-reduced so that the embeddings (and the updated running statistics) are those of the unsharded batch.
+        self.train_shard = None
 
     # ------------------------------------------------------------------ packed-weight cache
     def _pack_sources(self):
@@ -138,7 +142,9 @@ class ProteInfer(torch.nn.Module):
                 if bn.momentum != momentum:
                     raise ProtnoteB200Error("one momentum for all encoder BatchNorm layers is assumed")
                 bns += [bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var]
-        out = enc.forward_train(x, sequence_lengths, bns, momentum, True, native.MODES[self.precision])
+        group, total = self.train_shard if self.train_shard is not None else (None, None)
+        out = enc.forward_train(x, sequence_lengths, bns, momentum, True, native.MODES[self.precision], group=group,
+                                total_sequences=total)
         # the kernels updated the running statistics through raw pointers (torch's version counters did not move):
         # the eval-mode pack, which folds those statistics, is stale from here on
         self._packed_key = None

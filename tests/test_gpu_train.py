@@ -446,3 +446,35 @@ def test_fused_loss_and_seed_match_oracle(kw):
     for k, g in o_grads.items():
         got = named[k].grad.cpu().double()
         assert float((got - g).norm() / g.norm().clamp_min(1e-30)) <= 1e-3, k
+
+
+def test_sharded_train_mode_encoder_callback_path(monkeypatch):
+    """pn_encoder_forward_train_sharded on one GPU: the batch [x; x] 'sharded' over two ranks that both hold x.  The
+    all-reduce of the BatchNorm sums (a host callback between the statistics pass and the normalisation pass) is stood in
+    for by doubling them; mean and biased variance of [x; x] equal those of x, so embeddings must match the plain forward
+    of x (the running variance differs: its unbiased correction uses n = 2 B T)."""
+    import torch.distributed as dist
+    from oracle.protnote_oracle import synth_inputs
+    ecfg, scfg, *_ = CASES["tiny_concat"]
+    sd = synth_state_dict(ecfg, scfg, seed=CASES["tiny_concat"][6], calib_T=64)
+    onehots, lengths, _ = synth_inputs(3, 96, 4, ecfg, scfg, ragged=True, seed=5)
+    plain = build_b200_model(ecfg, scfg, sd, device="cuda").train()
+    with torch.no_grad():
+        want = plain.sequence_encoder.get_embeddings(onehots.cuda(), lengths.cuda())
+    calls = []
+
+    def fake_all_reduce(t, group=None, **kw):
+        calls.append(t.numel())
+        t.mul_(2.0)
+
+    monkeypatch.setattr(dist, "all_reduce", fake_all_reduce)
+    sharded = build_b200_model(ecfg, scfg, sd, device="cuda").train()
+    sharded.sequence_encoder.train_shard = (None, 2 * onehots.shape[0])
+    with torch.no_grad():
+        got = sharded.sequence_encoder.get_embeddings(onehots.cuda(), lengths.cuda())
+    torch.cuda.synchronize()
+    assert len(calls) == 2 * ecfg.num_resnet_blocks          # one reduction per BatchNorm layer
+    assert float((got - want).abs().max()) <= 1e-6 * max(1.0, float(want.abs().max()))
+    rm_p = dict(plain.named_buffers())["sequence_encoder.resnet_blocks.0.bn_activation_1.0.running_mean"]
+    rm_s = dict(sharded.named_buffers())["sequence_encoder.resnet_blocks.0.bn_activation_1.0.running_mean"]
+    assert float((rm_p - rm_s).abs().max()) <= 1e-7

@@ -17,4 +17,4 @@ for path in sys.argv[1:]:
         pipe = v.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", 0)
         ghz = v.get("sm__cycles_elapsed.max", 0) / (us * 1e3) if us else 0
         print(f"{i:3d} {name[:44]:44s} {us:9.1f} us {100 * us * 1e3 / tot:5.1f}%  tensor pipe {pipe:5.1f}%  DRAM rd {rd:8.1f} MB wr {wr:8.1f} MB "
-              f"= {(rd + wr) / us / 1e3 if us else 0:5.2f} TB/s  SM clock {ghz:.2f} GHz")
+              f"= {(rd + wr) / us if us else 0:5.2f} TB/s  SM clock {ghz:.2f} GHz")
