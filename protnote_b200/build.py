@@ -38,6 +38,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(LIB_DIR, exist_ok=True)
     cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
            "-shared", "-Xcompiler", "-fPIC", "-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd[1:1] = os.environ.get("PN_NVCC_FLAGS", "").split()     # experiments: e.g. PN_NVCC_FLAGS="-DPN_NO_RESID_PREFETCH"
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

@@ -54,6 +54,9 @@ long long g_trunc_c1 = 0, g_trunc_c0 = 0;
 // strict mode: per-K-position compensation folded into the packed weights (pack_weight_kernel, TruncComp), in units of
 // 1e-12 per truncating add.  Weights must be re-packed after this or a promote_k / bk option changes.
 long long g_trunc_beta_ppt = 33000;
+// strict mode: W_p and the protein half of output layer 1 in fp64 on the CUDA cores (linear_f64_kernel); 0 = tensor-core
+// path like every other layer.
+int g_f64_protein_head = 1;
 
 // optional per-launch CUDA-event timing of the pair scorer's GEMM launches (bench.py's roofline numbers)
 struct TimedLaunch {
@@ -552,6 +555,10 @@ struct ScorerLayout {
   std::vector<PackedLinear> hidden;      // output hidden layers 2..n
   size_t w_out = 0, b_out = 0;           // final Linear(H -> 1)
   size_t tmp = 0;                        // scratch for the concatenation_diff weight fold [H][latent]
+  // fp64 protein-side head (strict mode): original fp32 weights of W_p and of the protein half of output layer 1, and
+  // their BatchNorm folds in fp64 (linear_f64_kernel)
+  std::vector<size_t> wp_raw, wp_scale64, wp_shift64;
+  size_t l1p_raw = 0, l1p_scale64 = 0, l1p_shift64 = 0;
   size_t bytes = 0;
 };
 
@@ -566,10 +573,23 @@ ScorerLayout scorer_layout(const pn_scorer_cfg& c) {
       in_dim = out_dim;
     }
   }
+  {
+    int in_dim = c.protein_dim;
+    for (int i = 0; i < c.proj_layers; ++i) {
+      const int out_dim = i == c.proj_layers - 1 ? c.latent_dim : c.proj_hidden;
+      L.wp_raw.push_back(ar.take((size_t)out_dim * in_dim * 4));
+      L.wp_scale64.push_back(ar.take((size_t)out_dim * 8));
+      L.wp_shift64.push_back(ar.take((size_t)out_dim * 8));
+      in_dim = out_dim;
+    }
+  }
   if (c.fusion == PN_FUSION_SIMILARITY) {
     L.bytes = ar.off;
     return L;
   }
+  L.l1p_raw = ar.take((size_t)c.out_hidden * c.latent_dim * 4);
+  L.l1p_scale64 = ar.take((size_t)c.out_hidden * 8);
+  L.l1p_shift64 = ar.take((size_t)c.out_hidden * 8);
   L.l1_p = carve_linear(ar, c.out_hidden, c.latent_dim, 1);
   L.l1_l = carve_linear(ar, c.out_hidden, c.latent_dim, 1);
   if (c.fusion == PN_FUSION_CONCAT_PROD) L.l1_x = carve_linear(ar, c.out_hidden, c.latent_dim, 1);
@@ -616,6 +636,51 @@ int run_projection(const pn_scorer_cfg& c, const ScorerLayout& L, const Arena& p
                    cudaStream_t stream) {
   const std::vector<PackedLinear>& head = protein ? L.wp : L.wl;
   const int in_dim = protein ? c.protein_dim : c.label_dim;
+  if (protein && mode == PN_STRICT && g_f64_protein_head) {
+    // fp64 path (see linear_f64_kernel): two ping-pong fp64 activation buffers per row chunk
+    const long long ld64 = round_up(c.proj_hidden > c.latent_dim ? c.proj_hidden : c.latent_dim, 64);
+    const long long ldi = round_up(in_dim, 64);
+    const size_t per_row64 = (size_t)(ldi + 2 * ld64) * 8;
+    long long chunk = (long long)(workspace_bytes / per_row64);
+    if (chunk <= 0) return fail("projection workspace too small (%zu bytes)", workspace_bytes);
+    for (long long r0 = 0; r0 < n; r0 += chunk) {
+      const long long rows = (n - r0) < chunk ? (n - r0) : chunk;
+      Arena ws(workspace, workspace_bytes);
+      double* x64 = ws.at<double>(ws.take((size_t)rows * ldi * 8));
+      double* buf[2] = {ws.at<double>(ws.take((size_t)rows * ld64 * 8)), ws.at<double>(ws.take((size_t)rows * ld64 * 8))};
+      if (!ws.ok()) return fail("projection workspace accounting error");
+      f32_to_f64_rows_kernel<<<ew_grid(rows * ldi), 256, 0, stream>>>(in + r0 * in_dim, rows, in_dim, in_dim, x64, ldi);
+      g_launches++;
+      PN_CUDA(cudaGetLastError());
+      const double* cur = x64;
+      long long ldc = ldi;
+      int K = in_dim, q = 0;
+      for (size_t i = 0; i < head.size(); ++i) {
+        const bool last = i + 1 == head.size();
+        const int N = head[i].N;
+        const dim3 grid((unsigned)((N + 63) / 64), (unsigned)((rows + 63) / 64));
+        linear_f64_kernel<<<grid, 256, 0, stream>>>(cur, rows, K, ldc, pk.at<float>(L.wp_raw[i]), N, K,
+                                                    last ? nullptr : pk.at<double>(L.wp_scale64[i]),
+                                                    last ? nullptr : pk.at<double>(L.wp_shift64[i]), last ? 0 : 1, buf[q], ld64,
+                                                    (last && emb_out) ? emb_out + r0 * c.latent_dim : nullptr, c.latent_dim);
+        g_launches++;
+        PN_CUDA(cudaGetLastError());
+        cur = buf[q];
+        ldc = ld64;
+        K = N;
+        q ^= 1;
+      }
+      if (half_out) {
+        const dim3 grid((unsigned)((c.out_hidden + 63) / 64), (unsigned)((rows + 63) / 64));
+        linear_f64_kernel<<<grid, 256, 0, stream>>>(cur, rows, K, ldc, pk.at<float>(L.l1p_raw), c.out_hidden, K,
+                                                    pk.at<double>(L.l1p_scale64), pk.at<double>(L.l1p_shift64), 0, nullptr, 0,
+                                                    half_out + r0 * c.out_hidden, c.out_hidden);
+        g_launches++;
+        PN_CUDA(cudaGetLastError());
+      }
+    }
+    return 0;
+  }
   const int ld_in = (int)round_up(in_dim, 64);
   const int ld_h = (int)round_up(c.proj_hidden > c.latent_dim ? c.proj_hidden : c.latent_dim, 64);
   const size_t per_row = (size_t)ld_in * 4 + (size_t)ld_h * 4 * 2 + 1024;
@@ -811,6 +876,10 @@ int pn_set_option(const char* name, long long value) {
     } else {
       return fail("unknown option '%s'", name);
     }
+    return 0;
+  }
+  if (strcmp(name, "f64_protein_head") == 0) {
+    g_f64_protein_head = value != 0;
     return 0;
   }
   if (strcmp(name, "trunc_beta_ppt") == 0) {
@@ -1186,6 +1255,14 @@ int pn_scorer_pack(const pn_scorer_cfg* cfg, const float* const* params, int num
         g = *q++; bt = *q++; mu = *q++; var = *q++;
       }
       PN_TRY(pack_linear(pk, H[i], w, H[i].cin, 1, 0, H[i].cin, nullptr, g, bt, mu, var, c.bn_eps, stream, kStageHeads));
+      if (head == 0) {   // fp64 protein-side head: the weights as they are + the BatchNorm fold in fp64
+        PN_CUDA(cudaMemcpyAsync(pk.at<float>(L.wp_raw[i]), w, (size_t)H[i].N * H[i].cin * 4, cudaMemcpyDeviceToDevice, stream));
+        fold_affine_f64_kernel<<<(H[i].N + 255) / 256, 256, 0, stream>>>(H[i].N, nullptr, g, bt, mu, var, (double)c.bn_eps,
+                                                                         true, pk.at<double>(L.wp_scale64[i]),
+                                                                         pk.at<double>(L.wp_shift64[i]));
+        g_launches++;
+        PN_CUDA(cudaGetLastError());
+      }
     }
   }
   if (c.fusion == PN_FUSION_SIMILARITY) return 0;
@@ -1217,6 +1294,14 @@ int pn_scorer_pack(const pn_scorer_cfg* cfg, const float* const* params, int num
       wl_src = tl;
       src_ld = d;
     }
+    // fp64 protein-side head: W1p as it is (row pitch d) + BN1 folded in fp64
+    PN_CUDA(cudaMemcpy2DAsync(pk.at<float>(L.l1p_raw), (size_t)d * 4, wp_src, (size_t)src_ld * 4, (size_t)d * 4, c.out_hidden,
+                              cudaMemcpyDeviceToDevice, stream));
+    fold_affine_f64_kernel<<<(c.out_hidden + 255) / 256, 256, 0, stream>>>(c.out_hidden, bias, g, bt, mu, var, (double)c.bn_eps,
+                                                                           true, pk.at<double>(L.l1p_scale64),
+                                                                           pk.at<double>(L.l1p_shift64));
+    g_launches++;
+    PN_CUDA(cudaGetLastError());
     // scale = BN1 scale / wscale on every part; the shift (bias, mean, beta) goes to the protein side only
     PN_TRY(pack_linear(pk, L.l1_p, wp_src, src_ld, 1, 0, d, bias, g, bt, mu, var, c.bn_eps, stream, kStageHeads));
     PN_TRY(pack_linear(pk, L.l1_l, wl_src, src_ld, 1, 0, d, nullptr, g, nullptr, nullptr, var, c.bn_eps, stream, kStageHeads));
@@ -1252,7 +1337,9 @@ size_t pn_project_workspace_bytes(const pn_scorer_cfg* cfg, long long rows) {
   const long long ld_in = round_up(in_dim, 64);
   const long long ld_h = round_up(cfg->proj_hidden > cfg->latent_dim ? cfg->proj_hidden : cfg->latent_dim, 64);
   const long long r = round_up(rows < 1 ? 1 : rows, kBM);
-  return (size_t)(r * (ld_in * 4 + ld_h * 4 * 2 + 1024) + 8192);
+  // the larger of the tensor-core path (fp16 planes) and the fp64 protein-side path (three fp64 row buffers)
+  const long long planes = ld_in * 4 + ld_h * 4 * 2 + 1024, f64 = (ld_in + 2 * ld_h) * 8;
+  return (size_t)(r * (planes > f64 ? planes : f64) + 8192);
 }
 
 int pn_project_sequences(const pn_scorer_cfg* cfg, const void* packed, const float* P_f, long long n, float* P_e,
@@ -1368,7 +1455,7 @@ int pn_score_pairs_ex(const pn_scorer_cfg* cfg, const void* packed, const float*
       const bool fuse_features = fuse_ok && nl % kBM == 0;   // a tile = one protein x 128 consecutive label rows
       if (c.fusion != PN_FUSION_CONCAT_PROD && !fuse_features) {
         const int pf_threads = (int)(round_up(ld_h / 8, 32) < 1024 ? round_up(ld_h / 8, 32) : 1024);
-        pair_features_kernel<<<(unsigned)((nl + kPairRows - 1) / kPairRows), pf_threads, 0, stream>>>(a, H, c_in, H, (int)b0, (int)l0, (int)nl, (int)nb,
+        pair_features_kernel<<<(unsigned)((rows + kPairRows - 1) / kPairRows), pf_threads, 0, stream>>>(a, H, c_in, H, (int)b0, (int)l0, (int)nl, rows,
                                                                              H, buf_hi[0], mode == PN_STRICT ? buf_lo[0] : nullptr,
                                                                              ld_h);
         g_launches++;

@@ -206,47 +206,6 @@ __device__ __forceinline__ void add_f32_coalesced(float (&v)[32], uint8_t* stage
   }
 }
 
-// The residual block of a group, fetched ahead of its use in the coalesced layout of add_f32_coalesced (v[h * 4 + it] =
-// 16 bytes of row it * 8 + lane / 4, columns h * 16 + (lane % 4) * 4 ..): the loads of group g + 1 are issued before the
-// arithmetic of group g, and those of the tile's first group before the accumulator is even complete, so the DRAM
-// latency of the residual stream (the 1x1 convolutions of the encoder read 4.6 KB per position) hides behind the main
-// loop instead of stalling the eight epilogue warps four times per tile.
-__device__ __forceinline__ void resid_prefetch(uint4 (&v)[8], const float* row0_ptr, long long ld, uint32_t row_mask,
-                                               int lane) {
-#pragma unroll
-  for (int h = 0; h < 2; ++h)
-#pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      const int rr = it * 8 + (lane >> 2);
-      const int ch = lane & 3;
-      v[h * 4 + it] = ((row_mask >> rr) & 1u) ? __ldg(reinterpret_cast<const uint4*>(row0_ptr + rr * ld + h * 16 + ch * 4))
-                                             : make_uint4(0u, 0u, 0u, 0u);
-    }
-}
-
-__device__ __forceinline__ void add_prefetched(float (&y)[32], uint8_t* stage, const uint4 (&v)[8], int lane) {
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-#pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      const int rr = it * 8 + (lane >> 2);
-      const int ch = lane & 3;
-      *reinterpret_cast<uint4*>(stage + rr * kStageRowBytes + ch * 16) = v[h * 4 + it];
-    }
-    __syncwarp();
-    const uint4* mine = reinterpret_cast<const uint4*>(stage + lane * kStageRowBytes);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const uint4 q = mine[j];
-      y[h * 16 + 4 * j] += __uint_as_float(q.x);
-      y[h * 16 + 4 * j + 1] += __uint_as_float(q.y);
-      y[h * 16 + 4 * j + 2] += __uint_as_float(q.z);
-      y[h * 16 + 4 * j + 3] += __uint_as_float(q.w);
-    }
-    __syncwarp();
-  }
-}
-
 __device__ __forceinline__ void store_f32_coalesced(const float (&v)[32], uint8_t* stage, float* row0_ptr, long long ld,
                                                     uint32_t row_mask, int lane) {
 #pragma unroll
@@ -272,8 +231,7 @@ __device__ __forceinline__ void store_f32_coalesced(const float (&v)[32], uint8_
 // c0 = column offset of the group inside the tile (index into EpiConsts), n0 = global column.
 __device__ __forceinline__ void epilogue_group(const GemmParams& p, const EpiConsts& ec, uint8_t* stage, float (&y)[32],
                                                int c0, int n0, long long row, bool valid, uint32_t row_mask, int lane,
-                                               const float* addp, const float* addl, float& dot,
-                                               const uint4 (*resid_pre)[8] = nullptr) {
+                                               const float* addp, const float* addl, float& dot) {
   const bool full = (n0 + 32 <= p.N);
 #pragma unroll
   for (int j = 0; j < 32; j += 4) {
@@ -295,8 +253,9 @@ __device__ __forceinline__ void epilogue_group(const GemmParams& p, const EpiCon
   if (p.resid) {
     const float* rp = p.resid + row * p.ld_resid + n0;
     if (full && p.vec_resid) {   // warp-uniform; masked rows are zeroed below
-      if (resid_pre) add_prefetched(y, stage, *resid_pre, lane);
-      else add_f32_coalesced(y, stage, rp - lane * p.ld_resid, p.ld_resid, row_mask, lane);
+      // (issuing these loads a group ahead - even before the accumulator is complete - was tried and LOST 2 % on the
+      //  encoder and 7 % on the scorer to register spills: profiles/r02_ab_prefetch_pairfeatures.txt)
+      add_f32_coalesced(y, stage, rp - lane * p.ld_resid, p.ld_resid, row_mask, lane);
     } else if (valid) {
 #pragma unroll
       for (int j = 0; j < 32; ++j)
@@ -769,12 +728,6 @@ __global__ void __launch_bounds__(GEN ? kGenThreads : kGemmThreads, 1) gemm_kern
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       const uint32_t row_mask = __ballot_sync(0xffffffffu, in_range);
-      // residual stream: group g's block is in flight while group g - 1 is being finished (see resid_prefetch)
-      const bool pre_ok = p.resid != nullptr && p.vec_resid;
-      auto pre_group = [&](int g) { return pre_ok && g < 4 && g_lo + g < g_hi && n_tile * p.bn + (g_lo + g + 1) * 32 <= p.N; };
-      auto pre_ptr = [&](int g) { return p.resid + (row - lane) * p.ld_resid + n_tile * p.bn + (g_lo + g) * 32; };
-      uint4 rpre[8];
-      if (pre_group(0)) resid_prefetch(rpre, pre_ptr(0), p.ld_resid, row_mask, lane);
       float sums[4][32];
 #pragma unroll
       for (int g = 0; g < 4; ++g)
@@ -860,15 +813,7 @@ __global__ void __launch_bounds__(GEN ? kGenThreads : kGemmThreads, 1) gemm_kern
         const int n0 = n_tile * p.bn + c0;
         if (g_lo + g < g_hi && n0 < p.N) {   // warp-uniform (rows out of range are masked inside)
           float dotg = 0.f;
-          if (pre_group(g)) {
-            uint4 cur[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) cur[e] = rpre[e];
-            if (pre_group(g + 1)) resid_prefetch(rpre, pre_ptr(g + 1), p.ld_resid, row_mask, lane);
-            epilogue_group(p, ec, stage, sums[g], c0, n0, row, valid, row_mask, lane, addp, addl, dotg, &cur);
-          } else {
-            epilogue_group(p, ec, stage, sums[g], c0, n0, row, valid, row_mask, lane, addp, addl, dotg);
-          }
+          epilogue_group(p, ec, stage, sums[g], c0, n0, row, valid, row_mask, lane, addp, addl, dotg);
           dot += (double)dotg;
         }
       }

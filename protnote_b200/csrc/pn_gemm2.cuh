@@ -297,12 +297,6 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       const uint32_t row_mask = __ballot_sync(0xffffffffu, in_range);
-      // residual stream: group g's block is in flight while group g - 1 is being finished (see resid_prefetch)
-      const bool pre_ok = p.resid != nullptr && p.vec_resid;
-      auto pre_group = [&](int g) { return pre_ok && g < 4 && g_lo + g < g_hi && n_tile * p.bn + (g_lo + g + 1) * 32 <= p.N; };
-      auto pre_ptr = [&](int g) { return p.resid + (row - lane) * p.ld_resid + n_tile * p.bn + (g_lo + g) * 32; };
-      uint4 rpre[8];
-      if (pre_group(0)) resid_prefetch(rpre, pre_ptr(0), p.ld_resid, row_mask, lane);
       float sums[4][32];
 #pragma unroll
       for (int g = 0; g < 4; ++g)
@@ -368,15 +362,7 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
         const int n0 = n_tile * p.bn + c0;
         if (g_lo + g < g_hi && n0 < p.N) {   // warp-uniform (rows out of range are masked inside)
           float dotg = 0.f;
-          if (pre_group(g)) {
-            uint4 cur[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) cur[e] = rpre[e];
-            if (pre_group(g + 1)) resid_prefetch(rpre, pre_ptr(g + 1), p.ld_resid, row_mask, lane);
-            epilogue_group(p, ec, stage, sums[g], c0, n0, row, valid, row_mask, lane, addp, addl, dotg, &cur);
-          } else {
-            epilogue_group(p, ec, stage, sums[g], c0, n0, row, valid, row_mask, lane, addp, addl, dotg);
-          }
+          epilogue_group(p, ec, stage, sums[g], c0, n0, row, valid, row_mask, lane, addp, addl, dotg);
           dot += (double)dotg;
         }
       }

@@ -108,6 +108,91 @@ __global__ void fold_affine_kernel(int n, const float* __restrict__ bias, const 
 }
 
 // ------------------------------------------------------------------------------------------------
+// fp64 protein-side head (strict mode).  Everything a protein contributes to its 32K logits goes through one vector,
+// a[b] = BN1-folded protein half of output layer 1: an error in a[b] shifts ALL logits of protein b
+// coherently, and fp32-grade arithmetic leaves ~7e-7 |a|max there (2e-5 at |a| = 30) - the largest single term of the
+// logit error, in the reference's fp32 path as well (profiles/r02_scorer_error_by_stage.txt).  The work is negligible
+// (57 MFLOP per protein against 38 MFLOP per PAIR), so strict mode evaluates W_p and that half in fp64 on the CUDA cores:
+//   y[m][n] = act((sum_k x[m][k] * w[n][k]) * scale[n] + shift[n]),  x fp64, w fp32 (the original weights), scale/shift fp64.
+// 64 x 64 output tile per block of 256 threads (4 x 4 outputs per thread), K in steps of 16 through shared memory.
+// ------------------------------------------------------------------------------------------------
+__global__ void fold_affine_f64_kernel(int n, const float* __restrict__ bias, const float* __restrict__ gamma,
+                                       const float* __restrict__ beta, const float* __restrict__ mean,
+                                       const float* __restrict__ var, double eps, bool with_shift,
+                                       double* __restrict__ scale, double* __restrict__ shift) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double gs = 1.0;
+  if (var) gs = 1.0 / sqrt((double)var[i] + eps);
+  if (gamma) gs *= (double)gamma[i];
+  scale[i] = gs;
+  shift[i] = with_shift ? ((bias ? (double)bias[i] : 0.0) - (mean ? (double)mean[i] : 0.0)) * gs + (beta ? (double)beta[i] : 0.0) : 0.0;
+}
+
+__global__ void f32_to_f64_rows_kernel(const float* __restrict__ x, long long rows, int cols, long long ldx,
+                                       double* __restrict__ y, long long ldy) {
+  const long long total = rows * ldy;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / ldy;
+    const int c = (int)(i % ldy);
+    y[i] = c < cols ? (double)x[r * ldx + c] : 0.0;
+  }
+}
+
+__global__ void __launch_bounds__(256) linear_f64_kernel(const double* __restrict__ x, long long M, int K, long long ldx,
+                                                         const float* __restrict__ w, int N, long long ldw,
+                                                         const double* __restrict__ scale, const double* __restrict__ shift,
+                                                         int relu, double* __restrict__ y64, long long ldy64,
+                                                         float* __restrict__ y32, long long ldy32) {
+  __shared__ double xs[16][64 + 1];
+  __shared__ double ws[16][64 + 1];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;     // tx -> n, ty -> m
+  const long long m0 = (long long)blockIdx.y * 64;
+  const int n0 = blockIdx.x * 64;
+  double acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    // 64 rows x 16 k of each operand: 1024 elements, 4 per thread
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int idx = threadIdx.x + e * 256;
+      const int r = idx >> 4, kk = idx & 15;
+      const long long m = m0 + r;
+      const int n = n0 + r;
+      xs[kk][r] = (m < M && k0 + kk < K) ? x[m * ldx + k0 + kk] : 0.0;
+      ws[kk][r] = (n < N && k0 + kk < K) ? (double)w[(long long)n * ldw + k0 + kk] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      double xv[4], wv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) xv[i] = xs[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) wv[j] = ws[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(xv[i], wv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      double v = acc[i][j] * (scale ? scale[n] : 1.0) + (shift ? shift[n] : 0.0);
+      if (relu) v = v > 0.0 ? v : 0.0;
+      if (y64) y64[m * ldy64 + n] = v;
+      if (y32) y32[m * ldy32 + n] = (float)v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // activations: fp32 -> fp16 hi/lo planes
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void split8_store(const float (&v)[8], __half* hi, __half* lo) {
@@ -187,49 +272,46 @@ __global__ void conv_input_tokens_kernel(const uint8_t* __restrict__ tokens, con
 // (reference protnote/models/ProtNote.py:112-126,293 materialises [B*L, 2d]; here it never exists):
 //   h1[(b,l)][k] = relu(a[b][k] + c[l][k])      a = BN1-folded protein half, c = BN1-scaled label half
 // rows of the chunk are pairs (b0 + r / nl, l0 + r % nl); output fp16 planes [nb*nl][ld].
-// One block = kPairRows consecutive LABEL rows x all nb proteins of the chunk; thread t = 8-column chunk t.  The label
-// half c[l] (12 KB per row, 400 MB at 32K rows - larger than the L2) is read ONCE per chunk and kept in registers while
-// the nb protein halves (nb * 12 KB, L1/L2 resident) stream past it; the first version walked pair rows protein-major and
-// re-read every c row once per protein (ncu: 4.0 GB read for 4.0 GB written per 2^19-pair chunk,
-// profiles/r02_scorer_launch_list.txt).  grid (ceil(nl / kPairRows)), block = ld / 8 threads rounded up to a warp.
+// One block = kPairRows consecutive pair rows; thread t = 8-column chunk t of every one of them (row and protein
+// indices are per-block scalars: the first version spent four 64-bit div/mod per 8 elements and was bound by
+// instruction issue at the power-capped clock, not by HBM).  grid (ceil(rows / kPairRows)), block = ld / 8 threads
+// rounded up to a warp (<= 1024).
+// (A label-major walk that keeps c[l] in registers while the chunk's proteins stream past it reads 10x less - the c rows are
+// re-read once per protein here, 4.0 GB per 2^19-pair chunk - but writes 16 rows that lie 200 MB apart per thread and ran
+// 5.6 % SLOWER on B200: profiles/r02_ab_prefetch_pairfeatures.txt.  The kernel runs at the HBM peak as it is, 6.5 TB/s.)
 constexpr int kPairRows = 16;
 __global__ void pair_features_kernel(const float* __restrict__ a, long long lda, const float* __restrict__ c,
-                                     long long ldc, int b0, int l0, int nl, int nb, int H,
+                                     long long ldc, int b0, int l0, int nl, long long rows, int H,
                                      __half* __restrict__ hi, __half* __restrict__ lo, int ld) {
   const int chunks = ld / 8;
   const bool vec = ((lda | ldc) & 3) == 0;
-  const int l_begin = blockIdx.x * kPairRows;
-  for (int ch = threadIdx.x; ch < chunks; ch += blockDim.x) {
-    const int k0 = ch * 8;
-    const bool fast = k0 + 8 <= H && vec;
-    for (int rr = 0; rr < kPairRows; ++rr) {
-      const int l = l_begin + rr;
-      if (l >= nl) break;
-      const float* crow = c + (long long)(l0 + l) * ldc;
-      float cv[8];
-      if (fast) {
+  const long long r_begin = (long long)blockIdx.x * kPairRows;
+  long long bb = r_begin / nl;                 // one division per block
+  int l = (int)(r_begin - bb * nl);
+  for (int rr = 0; rr < kPairRows; ++rr) {
+    const long long r = r_begin + rr;
+    if (r >= rows) break;
+    const float* arow = a + (b0 + bb) * lda;
+    const float* crow = c + (long long)(l0 + l) * ldc;
+    for (int ch = threadIdx.x; ch < chunks; ch += blockDim.x) {
+      const int k0 = ch * 8;
+      float v[8];
+      if (k0 + 8 <= H && vec) {
+        const float4 a0 = __ldg(reinterpret_cast<const float4*>(arow + k0)), a1 = __ldg(reinterpret_cast<const float4*>(arow + k0 + 4));
         const float4 c0 = __ldg(reinterpret_cast<const float4*>(crow + k0)), c1 = __ldg(reinterpret_cast<const float4*>(crow + k0 + 4));
-        cv[0] = c0.x; cv[1] = c0.y; cv[2] = c0.z; cv[3] = c0.w; cv[4] = c1.x; cv[5] = c1.y; cv[6] = c1.z; cv[7] = c1.w;
+        v[0] = a0.x + c0.x; v[1] = a0.y + c0.y; v[2] = a0.z + c0.z; v[3] = a0.w + c0.w;
+        v[4] = a1.x + c1.x; v[5] = a1.y + c1.y; v[6] = a1.z + c1.z; v[7] = a1.w + c1.w;
       } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) cv[j] = (k0 + j < H) ? crow[k0 + j] : 0.f;
+        for (int j = 0; j < 8; ++j) v[j] = (k0 + j < H) ? arow[k0 + j] + crow[k0 + j] : 0.f;
       }
-      for (int bb = 0; bb < nb; ++bb) {
-        const float* arow = a + (long long)(b0 + bb) * lda;
-        float v[8];
-        if (fast) {
-          const float4 a0 = __ldg(reinterpret_cast<const float4*>(arow + k0)), a1 = __ldg(reinterpret_cast<const float4*>(arow + k0 + 4));
-          v[0] = a0.x + cv[0]; v[1] = a0.y + cv[1]; v[2] = a0.z + cv[2]; v[3] = a0.w + cv[3];
-          v[4] = a1.x + cv[4]; v[5] = a1.y + cv[5]; v[6] = a1.z + cv[6]; v[7] = a1.w + cv[7];
-        } else {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = (k0 + j < H) ? arow[k0 + j] + cv[j] : 0.f;
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
-        const long long r = (long long)bb * nl + l;
-        split8_store(v, hi + r * ld + k0, lo ? lo + r * ld + k0 : nullptr);
-      }
+      for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+      split8_store(v, hi + r * ld + k0, lo ? lo + r * ld + k0 : nullptr);
+    }
+    if (++l == nl) {
+      l = 0;
+      ++bb;
     }
   }
 }
