@@ -112,7 +112,7 @@ def calibrate_model(model, dev, world=1, logit_std=2.0):
     Rank 0's result is broadcast so every rank holds bit-identical weights."""
     import torch.distributed as dist
     bns = [m for m in model.modules() if isinstance(m, torch.nn.BatchNorm1d)]
-    x, lens, lab = synthetic_inputs(24, 256, 96, pinned=False, ragged=True)
+    x, lens, lab = synthetic_inputs(24, 256, 1024, pinned=False, ragged=True)
     x, lens, lab = x.to(dev), lens.to(dev), lab.to(dev)
     precision = model.precision
     model.precision = model.sequence_encoder.precision = "strict"
@@ -150,7 +150,7 @@ def calibrate_model(model, dev, world=1, logit_std=2.0):
         logits = model(sequence_onehots=x, sequence_lengths=lens, label_embeddings=lab)[0]
     model._label_cache = None
     return {"calibration_logit_std": float(logits.std()), "calibration_logit_mean": float(logits.mean()),
-            "how": "product path only: train-mode forward with BatchNorm momentum 1 on 24 x 256 aa x 96 rows, jitter, "
+            "how": "product path only: train-mode forward with BatchNorm momentum 1 on 24 x 256 aa x 1024 rows, jitter, "
                    "output neuron made orthogonal to the mean hidden activation and rescaled"}
 
 
