@@ -206,6 +206,43 @@ __device__ __forceinline__ void add_f32_coalesced(float (&v)[32], uint8_t* stage
   }
 }
 
+// Residual blocks fetched ahead with cp.async (pair kernel): the 32 x 32 fp32 block of the NEXT group goes straight from
+// global to a per-warp shared-memory buffer (rows of 128 + 16 pad bytes, so row-per-thread LDS.128 is conflict-free)
+// while the current group is being finished; the first group's block is requested before the accumulator is even
+// complete.  No registers are held across the wait (a register prefetch spilled: profiles/r02_ab_prefetch_pairfeatures.txt),
+// and the DRAM latency of the fp32 residual stream - eight exposed round trips per tile for the encoder's 1x1
+// convolutions - disappears behind the main loop.
+constexpr int kResidRowBytes = 144;
+constexpr int kResidBlockBytes = 32 * kResidRowBytes;     // per epilogue warp
+
+__device__ __forceinline__ void resid_cp_async(uint8_t* buf, const float* row0_ptr, long long ld, uint32_t row_mask, int lane) {
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int rr = it * 4 + (lane >> 3);
+    const int ch = lane & 7;
+    if ((row_mask >> rr) & 1u)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(buf + rr * kResidRowBytes + ch * 16)),
+                   "l"(row0_ptr + rr * ld + ch * 4)
+                   : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+__device__ __forceinline__ void add_resid_from_smem(float (&y)[32], const uint8_t* buf, int lane) {
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncwarp();                      // every lane's copies have landed and are visible to the warp
+  const uint4* mine = reinterpret_cast<const uint4*>(buf + lane * kResidRowBytes);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint4 q = mine[j];
+    y[4 * j] += __uint_as_float(q.x);
+    y[4 * j + 1] += __uint_as_float(q.y);
+    y[4 * j + 2] += __uint_as_float(q.z);
+    y[4 * j + 3] += __uint_as_float(q.w);
+  }
+  __syncwarp();                      // the buffer may be refilled
+}
+
 __device__ __forceinline__ void store_f32_coalesced(const float (&v)[32], uint8_t* stage, float* row0_ptr, long long ld,
                                                     uint32_t row_mask, int lane) {
 #pragma unroll
@@ -231,7 +268,8 @@ __device__ __forceinline__ void store_f32_coalesced(const float (&v)[32], uint8_
 // c0 = column offset of the group inside the tile (index into EpiConsts), n0 = global column.
 __device__ __forceinline__ void epilogue_group(const GemmParams& p, const EpiConsts& ec, uint8_t* stage, float (&y)[32],
                                                int c0, int n0, long long row, bool valid, uint32_t row_mask, int lane,
-                                               const float* addp, const float* addl, float& dot) {
+                                               const float* addp, const float* addl, float& dot,
+                                               uint8_t* resid_smem = nullptr, const float* resid_next = nullptr) {
   const bool full = (n0 + 32 <= p.N);
 #pragma unroll
   for (int j = 0; j < 32; j += 4) {
@@ -255,7 +293,12 @@ __device__ __forceinline__ void epilogue_group(const GemmParams& p, const EpiCon
     if (full && p.vec_resid) {   // warp-uniform; masked rows are zeroed below
       // (issuing these loads a group ahead - even before the accumulator is complete - was tried and LOST 2 % on the
       //  encoder and 7 % on the scorer to register spills: profiles/r02_ab_prefetch_pairfeatures.txt)
-      add_f32_coalesced(y, stage, rp - lane * p.ld_resid, p.ld_resid, row_mask, lane);
+      if (resid_smem) {          // block already in shared memory (cp.async, requested a group ago)
+        add_resid_from_smem(y, resid_smem, lane);
+        if (resid_next) resid_cp_async(resid_smem, resid_next, p.ld_resid, row_mask, lane);   // ... and the next one leaves now
+      } else {
+        add_f32_coalesced(y, stage, rp - lane * p.ld_resid, p.ld_resid, row_mask, lane);
+      }
     } else if (valid) {
 #pragma unroll
       for (int j = 0; j < 32; ++j)

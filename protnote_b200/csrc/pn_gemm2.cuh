@@ -80,9 +80,10 @@ struct Gemm2Cfg {
   static constexpr int kATile = kBM * BK * 2;              // this CTA's 128 rows
   static constexpr int kBTile = (kMaxBN / 2) * BK * 2;     // this CTA's half of the weight rows
   static constexpr int kStageBytes = kPlanes * (kATile + kBTile);
-  static constexpr int kStagesRaw = kSmemBudget / kStageBytes;
+  static constexpr int kResidBytes = 8 * kResidBlockBytes;      // cp.async residual blocks, one per epilogue warp
+  static constexpr int kStagesRaw = (kSmemBudget - kResidBytes) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + kEpiSmemBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + kEpiSmemBytes + kResidBytes;
 };
 
 template <int BK, int NPASS>
@@ -297,6 +298,13 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       const uint32_t row_mask = __ballot_sync(0xffffffffu, in_range);
+      // residual stream: the block of group g + 1 is copied global -> shared (cp.async) while group g is finished, the
+      // first block while the accumulator is still being produced
+      uint8_t* rbuf = epi_smem + kEpiSmemBytes + (warp - 4) * kResidBlockBytes;
+      const bool pre_ok = p.resid != nullptr && p.vec_resid;
+      auto pre_group = [&](int g) { return pre_ok && g < 4 && g_lo + g < g_hi && n_tile * p.bn + (g_lo + g + 1) * 32 <= p.N; };
+      auto pre_ptr = [&](int g) { return p.resid + (row - lane) * p.ld_resid + n_tile * p.bn + (g_lo + g) * 32; };
+      if (pre_group(0)) resid_cp_async(rbuf, pre_ptr(0), p.ld_resid, row_mask, lane);
       float sums[4][32];
 #pragma unroll
       for (int g = 0; g < 4; ++g)
@@ -362,7 +370,11 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
         const int n0 = n_tile * p.bn + c0;
         if (g_lo + g < g_hi && n0 < p.N) {   // warp-uniform (rows out of range are masked inside)
           float dotg = 0.f;
-          epilogue_group(p, ec, stage, sums[g], c0, n0, row, valid, row_mask, lane, addp, addl, dotg);
+          if (pre_group(g))
+            epilogue_group(p, ec, stage, sums[g], c0, n0, row, valid, row_mask, lane, addp, addl, dotg, rbuf,
+                           pre_group(g + 1) ? pre_ptr(g + 1) : nullptr);
+          else
+            epilogue_group(p, ec, stage, sums[g], c0, n0, row, valid, row_mask, lane, addp, addl, dotg);
           dot += (double)dotg;
         }
       }
