@@ -535,7 +535,7 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- the other BASELINE.json configurations at this N
     configs = None
-    if not args.no_configs and args.mode == "strict" and (B, T, L, kdesc) == (B_TOTAL, T_LEN, L_ROWS, 1):
+    if not args.no_configs and args.mode == "strict" and ((B, T, L, kdesc) == (B_TOTAL, T_LEN, L_ROWS, 1) or args.force_configs):
         configs = run_other_configs(args, model, dev, rank, world)
     if rank != 0:
         return
@@ -607,6 +607,7 @@ def run_other_configs(args, model, dev, rank, world):
     out = {"note": "measured after the headline in the same process, device-resident inputs, CUDA events, max over ranks; "
                    "fewer steps than the headline (stated per entry)"}
     t0 = time.perf_counter()
+    out["memory_allocated_gib_after_headline"] = torch.cuda.memory_allocated(dev) / 2 ** 30
     try:
         B, T, L, k = EC_SHAPE
         out["ec"] = run_small_config(model, dev, rank, world, B, T, L, k, steps=2, warmup=1, with_parity=True)
@@ -615,6 +616,7 @@ def run_other_configs(args, model, dev, rank, world):
     except Exception as exc:  # noqa: BLE001 - an auxiliary configuration must not lose the headline line
         out["ec"] = {"error": f"{type(exc).__name__}: {exc}"}
     release_memory()
+    out["memory_allocated_gib_after_ec"] = torch.cuda.memory_allocated(dev) / 2 ** 30
     sweep = []
     try:
         for T in SWEEP_T:
@@ -630,8 +632,12 @@ def run_other_configs(args, model, dev, rank, world):
     except Exception as exc:  # noqa: BLE001
         out["sweep"] = {"error": f"{type(exc).__name__}: {exc}", "points": sweep}
     model.inference_descriptions_per_label = 1
-    release_memory()
+    # the inference model's packs, label cache and every cached workspace go before the training step needs ~100 GB
+    model._packed = model._packed_key = model._label_cache = None
+    model.sequence_encoder._packed = model.sequence_encoder._packed_key = None
     del model
+    release_memory()
+    out["memory_allocated_gib_before_train"] = torch.cuda.memory_allocated(dev) / 2 ** 30
     try:
         out["train"] = train_configs(args, dev, rank, world)
     except Exception as exc:  # noqa: BLE001
@@ -649,7 +655,8 @@ TRAIN_B = 64
 TRAIN_FLOP_PER_PAIR = 3 * 2 * (2 * 3072 * 3072) + 2 * 3072
 TRAIN_FLOP_PER_LABEL_ROW = 3 * 50_331_648 + 3 * 2 * 1024 * 3072     # W_l forward + backward, label half of layer 1
 TRAIN_FLOP_PER_PROTEIN = 3 * 50_798_592 + 3 * 2 * 1024 * 3072 + 1024 * 60_896_000   # W_p, protein half, frozen encoder
-TRAIN_STRICT_BYTES_PER_LABEL_ROW = 155e9 / 32768    # activation memory of a strict step at batch 64
+# activation memory of a strict step at batch 64: measured 101.6 GiB at 16 384 rows per rank (2 GPUs) incl. ~12 GiB fixed
+TRAIN_STRICT_BYTES_PER_LABEL_ROW = 180 * 2 ** 30 / 32768
 
 
 class TrainStep:
@@ -741,6 +748,7 @@ class TrainStep:
 
 def train_measure(dev, rank, world, mode, B, T, L, steps, warmup, e2e=True):
     from protnote_b200 import native
+    torch.cuda.reset_peak_memory_stats(dev)
     ts = TrainStep(dev, rank, world, mode, B, T, L)
     losses = []
     for _ in range(warmup):
@@ -848,15 +856,20 @@ def train_configs(args, dev, rank, world):
     release_memory()
     for mode in ("fast", "strict"):
         if mode == "strict":
-            need = TRAIN_STRICT_BYTES_PER_LABEL_ROW * (L / world) + 12e9
+            need = TRAIN_STRICT_BYTES_PER_LABEL_ROW * (L / world) + 12 * 2 ** 30
             free = torch.cuda.mem_get_info(dev)[0]
-            if need > 0.9 * free:
-                out[mode] = {"skipped": f"strict activations of {L // world} label rows per rank need ~{need / 1e9:.0f} GB "
-                                        f"(> 90% of the {free / 1e9:.0f} GB free); runs label-sharded on more GPUs"}
+            if need > 0.85 * free:
+                out[mode] = {"skipped": f"strict activations of {L // world} label rows per rank need ~{need / 2 ** 30:.0f} GiB "
+                                        f"(> 85% of the {free / 2 ** 30:.0f} GiB free); runs label-sharded on 2 or more GPUs"}
                 continue
-        r = train_measure(dev, rank, world, mode, B, T, L, steps=3, warmup=2, e2e=False)
-        if rank == 0:
-            out[mode] = train_line(r, mode, world, B, T, L, 3, 2)
+        try:
+            r = train_measure(dev, rank, world, mode, B, T, L, steps=3, warmup=2, e2e=False)
+            if rank == 0:
+                out[mode] = train_line(r, mode, world, B, T, L, 3, 2)
+        except Exception as exc:  # noqa: BLE001 - keep what was measured
+            out[mode] = {"error": f"{type(exc).__name__}: {str(exc)[:300]}",
+                         "memory_allocated_gib": torch.cuda.memory_allocated(dev) / 2 ** 30}
+            release_memory()
     return out if rank == 0 else None
 
 
@@ -914,6 +927,7 @@ def main():
     ap.add_argument("--no-parity", action="store_true", help="skip the in-run check of the logits against the CPU oracle")
     ap.add_argument("--no-configs", action="store_true",
                     help="skip the other BASELINE.json configurations (EC shape, sweep, training step) after the headline")
+    ap.add_argument("--force-configs", action="store_true", help="run the `configs` block after a non-headline shape too (debugging)")
     ap.add_argument("--descriptions-per-label", type=int, default=1,
                     help="k consecutive label rows ensembled per label (INFERENCE_GO_DESCRIPTIONS name+label -> 2)")
     ap.add_argument("--workload", default="inference", choices=["inference", "train", "ec"],

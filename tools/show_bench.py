@@ -21,7 +21,8 @@ for path in sys.argv[1:]:
         print(f"   train parity: {json.dumps(t.get('parity'))[:400]}")
         for m in ("fast", "strict"):
             print(f"   train {m}: {json.dumps(t.get(m))[:500]}")
-        print(f"   configs seconds {c.get('seconds')}  train error {t.get('error')}")
+        print(f"   configs seconds {c.get('seconds')}  train error {t.get('error')}  memory GiB after headline/ec/before train: "
+              f"{c.get('memory_allocated_gib_after_headline')} {c.get('memory_allocated_gib_after_ec')} {c.get('memory_allocated_gib_before_train')}")
     if "fast_mode" in d:
         print(f"   fast_mode: {d['fast_mode']['value']:.4g} pairs/s, scorer GEMM {d['fast_mode']['scorer_gemm_tflops']}")
     if "cpu_baseline" in d:
