@@ -948,7 +948,9 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+        # a rank-order bug must fail in minutes, not sit in a collective until the default 10-minute watchdog fires
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=300))
     try:
         if args.workload == "train":
             run_train(args, rank, world, local_rank)

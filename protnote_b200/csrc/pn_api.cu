@@ -57,6 +57,8 @@ long long g_trunc_beta_ppt = 33000;
 // strict mode: W_p and the protein half of output layer 1 in fp64 on the CUDA cores (linear_f64_kernel); 0 = tensor-core
 // path like every other layer.
 int g_f64_protein_head = 1;
+// pair kernel: L2 eviction-priority hints on the TMA loads (GemmParams::l2_hints)
+int g_l2_hints = 2;
 
 // optional per-launch CUDA-event timing of the pair scorer's GEMM launches (bench.py's roofline numbers)
 struct TimedLaunch {
@@ -361,6 +363,7 @@ int launch_gemm(const Planes& A, const ConvView& cv, const Planes& B, long long 
     PN_TRY(make_map(&p.tm_b_hi, B.hi, 2, dims, strides, box, bk * 2));
     if (need_lo) PN_TRY(make_map(&p.tm_b_lo, B.lo, 2, dims, strides, box, bk * 2));
   }
+  p.l2_hints = g_l2_hints;
   p.scale = e.scale; p.shift = e.shift;
   p.resid = e.resid; p.ld_resid = e.ld_resid;
   p.out_f32 = e.out_f32; p.ld_out = e.ld_out;
@@ -876,6 +879,11 @@ int pn_set_option(const char* name, long long value) {
     } else {
       return fail("unknown option '%s'", name);
     }
+    return 0;
+  }
+  if (strcmp(name, "l2_hints") == 0) {
+    if (value < 0 || value > 2) return fail("l2_hints must be 0, 1 or 2");
+    g_l2_hints = (int)value;
     return 0;
   }
   if (strcmp(name, "f64_protein_head") == 0) {

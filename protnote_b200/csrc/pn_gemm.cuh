@@ -74,6 +74,7 @@ struct alignas(64) GemmParams {
   // promoted total is multiplied by (1 + trunc_comp) before the epilogue, which removes the mean of that bias; what is
   // left is zero-mean and uncorrelated between outputs, like round-to-nearest noise.  0 = off.
   float trunc_comp;
+  int l2_hints;                  // pair kernel: 0 none, 1 weights evict_last, 2 weights evict_last + activations evict_first
   const long long* lengths;      // [B] valid positions per sequence (conv) or nullptr
   // pair-row addressing for the additive row terms: row r -> (r / pair_nl, r % pair_nl)
   int pair_nl;

@@ -42,6 +42,26 @@ __device__ __forceinline__ void tma2_load_3d(uint32_t dst, const CUtensorMap* m,
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// The same loads with an L2 eviction-priority hint (createpolicy-encoded 64-bit operand).  The weights (B) are re-read by
+// every wave of M tiles and must stay L2-resident while 12 KB of activations per row stream past them; without a hint
+// ncu showed the 38 MB of W being re-fetched from HBM on ~80 % of the waves (16.8 GB read per 2^19-row launch where the
+// A planes are 6.4 GB): B is loaded evict_last, A evict_first.
+constexpr uint64_t kL2EvictFirst = 0x12F0000000000000ull;
+constexpr uint64_t kL2EvictLast = 0x14F0000000000000ull;
+__device__ __forceinline__ void tma2_load_2d_hint(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1,
+                                                  uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_3d_hint(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2,
+                                                  uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
+      : "memory");
+}
 __device__ __forceinline__ void tmem2_alloc(uint32_t smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
 }
@@ -157,6 +177,7 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t my_bytes = Cfg::kPlanes * (Cfg::kATile + (uint32_t)half_bn * BK * 2);
+      const uint64_t pol_a = p.l2_hints == 2 ? kL2EvictFirst : 0x1000000000000000ull;   // 1: A evict_normal
       for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
         const int m_tile = tile / p.tiles_n, n_tile = tile % p.tiles_n;
         if (tile_is_padding(m_tile)) continue;
@@ -177,8 +198,13 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
           int kcol = kb * BK;
           if (conv) {
             kcol = kbase + kc;
-            tma2_load_3d(sa, &p.tm_a_hi, fb, kc, t, seq);
-            if (NPASS == 3) tma2_load_3d(sa + Cfg::kATile, &p.tm_a_lo, fb, kc, t, seq);
+            if (p.l2_hints) {
+              tma2_load_3d_hint(sa, &p.tm_a_hi, fb, kc, t, seq, pol_a);
+              if (NPASS == 3) tma2_load_3d_hint(sa + Cfg::kATile, &p.tm_a_lo, fb, kc, t, seq, pol_a);
+            } else {
+              tma2_load_3d(sa, &p.tm_a_hi, fb, kc, t, seq);
+              if (NPASS == 3) tma2_load_3d(sa + Cfg::kATile, &p.tm_a_lo, fb, kc, t, seq);
+            }
             kc += BK;
             if (++cb == p.conv_cblocks) {   // next tap
               cb = 0;
@@ -187,11 +213,21 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
               t += p.conv_dil;
             }
           } else {
-            tma2_load_2d(sa, &p.tm_a_hi, fb, kcol, row0);
-            if (NPASS == 3) tma2_load_2d(sa + Cfg::kATile, &p.tm_a_lo, fb, kcol, row0);
+            if (p.l2_hints) {
+              tma2_load_2d_hint(sa, &p.tm_a_hi, fb, kcol, row0, pol_a);
+              if (NPASS == 3) tma2_load_2d_hint(sa + Cfg::kATile, &p.tm_a_lo, fb, kcol, row0, pol_a);
+            } else {
+              tma2_load_2d(sa, &p.tm_a_hi, fb, kcol, row0);
+              if (NPASS == 3) tma2_load_2d(sa + Cfg::kATile, &p.tm_a_lo, fb, kcol, row0);
+            }
           }
-          tma2_load_2d(sb, &p.tm_b_hi, fb, kcol, brow0);
-          if (NPASS == 3) tma2_load_2d(sb + Cfg::kBTile, &p.tm_b_lo, fb, kcol, brow0);
+          if (p.l2_hints) {
+            tma2_load_2d_hint(sb, &p.tm_b_hi, fb, kcol, brow0, kL2EvictLast);
+            if (NPASS == 3) tma2_load_2d_hint(sb + Cfg::kBTile, &p.tm_b_lo, fb, kcol, brow0, kL2EvictLast);
+          } else {
+            tma2_load_2d(sb, &p.tm_b_hi, fb, kcol, brow0);
+            if (NPASS == 3) tma2_load_2d(sb + Cfg::kBTile, &p.tm_b_lo, fb, kcol, brow0);
+          }
           if (++stage == Cfg::kStages) {
             stage = 0;
             phase ^= 1;

@@ -203,6 +203,23 @@ def _encoder_forward_train(self, x: torch.Tensor, lengths: torch.Tensor, bn_para
             raise _lib.ProtnoteB200Error("BatchNorm parameters / buffers must be contiguous fp32 CUDA tensors")
     out = torch.empty(B, self.cfg.channels, dtype=torch.float32, device=dev)
     if B == 0:
+        if total_sequences is not None and int(total_sequences) > 0:
+            # a rank without sequences (more ranks than sequences) still owes the other ranks its share - zero - of every
+            # BatchNorm-sum all-reduce, in the order pn_encoder_forward_train_sharded issues them
+            # (and it applies the same running-statistic update: pn_t_bn_finalize on the reduced sums)
+            import torch.distributed as dist
+            count = float(total_sequences) * T
+            state = torch.empty(4 * self.cfg.channels, dtype=torch.float32, device=dev)
+            with torch.cuda.device(dev):
+                for i in range(self.cfg.num_blocks):
+                    for j, cols in enumerate((self.cfg.channels, self.cfg.bottleneck)):
+                        g, b, rm, rv = bn_params[8 * i + 4 * j: 8 * i + 4 * j + 4]
+                        stats = torch.zeros(2 * cols, dtype=torch.float64, device=dev)
+                        dist.all_reduce(stats, group=group)
+                        check(self.lib.pn_t_bn_finalize(ptr(stats), C.c_double(count), None, C.c_double(0.0), ptr(g), ptr(b),
+                                                        C.c_float(self.cfg.bn_eps), C.c_float(momentum),
+                                                        ptr(rm) if update_running else None,
+                                                        ptr(rv) if update_running else None, cols, ptr(state), stream_ptr()))
         return out
     ws = scratch(dev, "encoder_train", self.lib.pn_encoder_train_workspace_bytes(C.byref(self.cfg), B, T))
     if total_sequences is None or int(total_sequences) == B:

@@ -81,10 +81,21 @@ def test_label_sharded_training_step_on_two_nccl_ranks():
             "dist.init_process_group('nccl', device_id=torch.device('cuda', lr))\n"
             "out = bench.train_parity_small(torch.device('cuda', lr), r, w)\n"
             "if r == 0: print('PARITY ' + json.dumps(out), flush=True)\n"
+            # more ranks than sequences: rank 1 owns none and must still take part in every BatchNorm-sum all-reduce
+            "from tests.helpers import build_b200_model, load_case\n"
+            "from protnote_b200.sharded import all_gather_rows, shard_bounds\n"
+            "ecfg, scfg, sd, onehots, lengths, _, _ = load_case('tiny_concat')\n"
+            "enc = build_b200_model(ecfg, scfg, sd, device=torch.device('cuda', lr)).train().sequence_encoder\n"
+            "enc.train_shard = (None, 1)\n"
+            "ps, pe = shard_bounds(1, r, w)\n"
+            "with torch.no_grad():\n"
+            "    e = all_gather_rows(enc.get_embeddings(onehots[:1][ps:pe].cuda(), lengths[:1][ps:pe].cuda()), 1)\n"
+            "torch.cuda.synchronize()\n"
+            "if r == 0: print('ZERO_RANK_OK ' + str(tuple(e.shape)), flush=True)\n"
             "dist.destroy_process_group()\n")
     res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), "--no-python",
-                          sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT, timeout=900)
+                          sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT, timeout=600)
     assert res.returncode == 0, res.stderr[-3000:]
     import json
     line = [ln for ln in res.stdout.splitlines() if ln.startswith("PARITY ")][-1]
@@ -92,3 +103,4 @@ def test_label_sharded_training_step_on_two_nccl_ranks():
     assert out["ranks"] == 2 and out["within_tol"], out
     assert out["max_abs_logit_err"] <= 1e-4 and out["abs_loss_err"] <= 1e-5
     assert out["worst_gradient_max_err_over_max_entry"] <= 1e-3
+    assert "ZERO_RANK_OK (1, 72)" in res.stdout

@@ -478,3 +478,43 @@ def test_sharded_train_mode_encoder_callback_path(monkeypatch):
     rm_p = dict(plain.named_buffers())["sequence_encoder.resnet_blocks.0.bn_activation_1.0.running_mean"]
     rm_s = dict(sharded.named_buffers())["sequence_encoder.resnet_blocks.0.bn_activation_1.0.running_mean"]
     assert float((rm_p - rm_s).abs().max()) <= 1e-7
+
+
+def test_sharded_train_mode_encoder_rank_without_sequences(monkeypatch):
+    """More ranks than sequences: a rank that owns no sequence still takes part in every BatchNorm-sum all-reduce (zeros)
+    and applies the same running-statistic update (pn_t_bn_finalize on the reduced sums) - otherwise the other ranks hang.
+    One GPU: the all-reduce is stood in for by adding the sums a data-holding rank produced."""
+    import torch.distributed as dist
+    from oracle.protnote_oracle import synth_inputs
+    ecfg, scfg, *_ = CASES["tiny_concat"]
+    sd = synth_state_dict(ecfg, scfg, seed=CASES["tiny_concat"][6], calib_T=64)
+    onehots, lengths, _ = synth_inputs(2, 80, 4, ecfg, scfg, ragged=True, seed=9)
+    # rank A holds both sequences; record the sums it hands to each all-reduce
+    recorded = []
+    monkeypatch.setattr(dist, "all_reduce", lambda t, group=None, **kw: recorded.append(t.clone()))
+    a = build_b200_model(ecfg, scfg, sd, device="cuda").train()
+    a.sequence_encoder.train_shard = (None, 3)           # pretend a third sequence lives elsewhere: takes the sharded path
+    with torch.no_grad():
+        a.sequence_encoder.get_embeddings(onehots.cuda(), lengths.cuda())
+    torch.cuda.synchronize()
+    assert len(recorded) == 2 * ecfg.num_resnet_blocks
+    # rank B holds nothing: it must issue the same number of all-reduces with the same sizes, in the same order
+    sizes, it = [], iter(recorded)
+
+    def fake(t, group=None, **kw):
+        sizes.append(t.numel())
+        t.add_(next(it))
+
+    monkeypatch.setattr(dist, "all_reduce", fake)
+    b = build_b200_model(ecfg, scfg, sd, device="cuda").train()
+    b.sequence_encoder.train_shard = (None, 3)
+    with torch.no_grad():
+        out = b.sequence_encoder.get_embeddings(onehots[:0].cuda(), lengths[:0].cuda())
+    torch.cuda.synchronize()
+    assert out.shape == (0, ecfg.output_channels)
+    assert sizes == [t.numel() for t in recorded]
+    # first BatchNorm layer: both "ranks" saw the same reduced sums -> the same running statistics
+    for key in ("running_mean", "running_var"):
+        ka = dict(a.named_buffers())[f"sequence_encoder.resnet_blocks.0.bn_activation_1.0.{key}"]
+        kb = dict(b.named_buffers())[f"sequence_encoder.resnet_blocks.0.bn_activation_1.0.{key}"]
+        assert torch.allclose(ka, kb, rtol=1e-6, atol=1e-7), key
