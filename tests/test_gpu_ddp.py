@@ -78,7 +78,8 @@ def test_label_sharded_training_step_on_two_nccl_ranks():
     code = ("import json, os, torch, torch.distributed as dist, bench\n"
             "r, w, lr = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['LOCAL_RANK'])\n"
             "torch.cuda.set_device(lr)\n"
-            "dist.init_process_group('nccl', device_id=torch.device('cuda', lr))\n"
+            "import datetime\n"
+            "dist.init_process_group('nccl', device_id=torch.device('cuda', lr), timeout=datetime.timedelta(seconds=90))\n"
             "out = bench.train_parity_small(torch.device('cuda', lr), r, w)\n"
             "if r == 0: print('PARITY ' + json.dumps(out), flush=True)\n"
             # more ranks than sequences: rank 1 owns none and must still take part in every BatchNorm-sum all-reduce
@@ -95,7 +96,7 @@ def test_label_sharded_training_step_on_two_nccl_ranks():
             "dist.destroy_process_group()\n")
     res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), "--no-python",
-                          sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT, timeout=600)
+                          sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT, timeout=300)
     assert res.returncode == 0, res.stderr[-3000:]
     import json
     line = [ln for ln in res.stdout.splitlines() if ln.startswith("PARITY ")][-1]
