@@ -564,12 +564,13 @@ def run_ours(args, rank, world, local_rank):
                      else "pn::gemm_kernel<64,1>", "bound": "tensor", "achieved": achieved, "peak": peak,
                      "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
                      # NOT measured in this run: dram__bytes_read.sum + dram__bytes_write.sum per launch of the committed
-                     # `ncu --set full` capture, scaled by the rows of the timed launches (31.5 KB/row for the layer that
-                     # stores its activations, 13.2 KB/row for the dot-epilogue layer -> 22.4 KB per row per launch;
-                     # algorithmic: 12 KB/row of A planes read, +12 KB/row written by the storing layer = 18 KB/row)
-                     "traffic": (22.4e3 * gemm_flops / (2.0 * 3072 * 3072) / gemm_launches) if gemm_launches else None,
-                     "traffic_source": "profiles/r01_ncu_full_gemm_scorer_encoder.txt (constant from that ncu capture, "
-                                       "scaled by rows; not re-measured per run)",
+                     # `ncu --set full` capture of round 2 (2^19-row launches: layer 2 reads 16.78 GB + writes 4.63 GB =
+                     # 40.8 KB/row, the dot-epilogue layer 14.35 + 0.69 GB = 28.7 KB/row -> 34.8 KB per row per launch),
+                     # scaled by the rows of the timed launches; algorithmic: 12 KB/row of A planes read, +12 KB/row written
+                     # by the storing layer = 18 KB/row.  The excess is the 38 MB of weights not staying L2-resident.
+                     "traffic": (34.8e3 * gemm_flops / (2.0 * 3072 * 3072) / gemm_launches) if gemm_launches else None,
+                     "traffic_source": "profiles/r02_ncu_full_after.txt (constant from that ncu capture, scaled by rows; "
+                                       "not re-measured per run)",
                      "traffic_unit": "bytes per launch",
                      "algorithmic_bytes_per_launch": (18.0e3 * gemm_flops / (2.0 * 3072 * 3072) / gemm_launches)
                      if gemm_launches else None,

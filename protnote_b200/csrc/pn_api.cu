@@ -57,8 +57,10 @@ long long g_trunc_beta_ppt = 33000;
 // strict mode: W_p and the protein half of output layer 1 in fp64 on the CUDA cores (linear_f64_kernel); 0 = tensor-core
 // path like every other layer.
 int g_f64_protein_head = 1;
-// pair kernel: L2 eviction-priority hints on the TMA loads (GemmParams::l2_hints)
-int g_l2_hints = 2;
+// pair kernel: L2 eviction-priority hints on the TMA loads (GemmParams::l2_hints).  Measured on B200 (16 x 32768 pairs,
+// strict): no hints 43.4-45.2 ms, weights evict_last 45.0 ms, + activations evict_first 50.0-50.2 ms: the A tile that twelve
+// clusters share is dropped before the last of them has read it.  Off by default (profiles/r02_ab_prefetch_pairfeatures.txt).
+int g_l2_hints = 0;
 
 // optional per-launch CUDA-event timing of the pair scorer's GEMM launches (bench.py's roofline numbers)
 struct TimedLaunch {

@@ -42,10 +42,11 @@ __device__ __forceinline__ void tma2_load_3d(uint32_t dst, const CUtensorMap* m,
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
-// The same loads with an L2 eviction-priority hint (createpolicy-encoded 64-bit operand).  The weights (B) are re-read by
-// every wave of M tiles and must stay L2-resident while 12 KB of activations per row stream past them; without a hint
-// ncu showed the 38 MB of W being re-fetched from HBM on ~80 % of the waves (16.8 GB read per 2^19-row launch where the
-// A planes are 6.4 GB): B is loaded evict_last, A evict_first.
+// The same loads with an L2 eviction-priority hint (createpolicy-encoded 64-bit operand).  Motivation: ncu shows the
+// scorer's layer-2 launch reading 16.8 GB from HBM where its A planes are 6.4 GB - the 38 MB of weights do not stay
+// L2-resident while 12 KB of activations per row stream past them.  Experiment (option l2_hints): B evict_last made no
+// difference, A evict_first cost 11-15 % (the A tile that twelve clusters share is dropped before the last one has read
+// it).  DRAM runs at 21 % and is not the limiter; the hints stay off.
 constexpr uint64_t kL2EvictFirst = 0x12F0000000000000ull;
 constexpr uint64_t kL2EvictLast = 0x14F0000000000000ull;
 __device__ __forceinline__ void tma2_load_2d_hint(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1,
