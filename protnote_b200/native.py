@@ -222,7 +222,10 @@ def _encoder_forward_train(self, x: torch.Tensor, lengths: torch.Tensor, bn_para
                                                         ptr(rv) if update_running else None, cols, ptr(state), stream_ptr()))
         return out
     ws = scratch(dev, "encoder_train", self.lib.pn_encoder_train_workspace_bytes(C.byref(self.cfg), B, T))
-    if total_sequences is None or int(total_sequences) == B:
+    # sharded whenever other ranks exist (one of them may hold nothing, so `total == B` on this rank proves nothing)
+    import torch.distributed as _dist
+    multi = _dist.is_available() and _dist.is_initialized() and _dist.get_world_size(group) > 1
+    if total_sequences is None or (int(total_sequences) == B and not multi):
         with torch.cuda.device(dev):
             check(self.lib.pn_encoder_forward_train(C.byref(self.cfg), ptr(self.packed_raw), ptr(x), ptr(lengths), B, T,
                                                     pointer_array(bn_params), len(bn_params), C.c_float(momentum),
