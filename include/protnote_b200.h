@@ -55,6 +55,8 @@ int pn_device_check(int device);
  *   "cta2"                     CTA-pair kernels (tcgen05 cta_group::2, 256-row tiles, each CTA loads half the weight tile):
  *                              1 (default) wherever a problem has more than one 128-row tile, 0 never, -1 in PN_FAST mode
  *                              only, 2 always
+ *   "f64_protein_head"         1 (default): PN_STRICT computes W_p and the protein half of output layer 1 in fp64
+ *   "l2_hints"                 pair kernel: L2 eviction hints on the TMA loads (0 off - default, measured slower; 1; 2)
  *   "chunk_rows"               pairs per scorer chunk (0 = auto)
  *   "split_corr"               1: strict-mode encoder convolutions accumulate the hi*hi products and the lo corrections in
  *                              separate TMEM buffers (round-1 experiment; default 0)
@@ -172,7 +174,10 @@ int pn_scorer_pack(const pn_scorer_cfg* cfg, const float* const* params, int num
                    size_t packed_bytes, void* stream);
 
 /* W_p then the protein half of output layer 1:  P_f [n][protein_dim] -> P_e [n][latent_dim] (nullable) and
- * a [n][out_hidden] (BatchNorm-1 scale AND shift folded in).  workspace: pn_project_workspace_bytes(cfg, n). */
+ * a [n][out_hidden] (BatchNorm-1 scale AND shift folded in).  workspace: pn_project_workspace_bytes(cfg, n).
+ * PN_STRICT evaluates this head in fp64 on the CUDA cores (option "f64_protein_head", default 1): a[b] carries everything
+ * protein b contributes to ALL of its logits, so its fp32-grade rounding error was the largest term of the logit error
+ * (profiles/r02_scorer_error_by_stage.txt), and it costs 57 MFLOP per protein against 38 MFLOP per pair. */
 size_t pn_project_workspace_bytes(const pn_scorer_cfg* cfg, long long rows);
 int pn_project_sequences(const pn_scorer_cfg* cfg, const void* packed, const float* P_f, long long n, float* P_e,
                          float* a, void* workspace, size_t workspace_bytes, int mode, void* stream);

@@ -36,3 +36,34 @@ def test_product_arm_refuses_to_run_without_a_gpu():
     res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1"],
                          capture_output=True, text=True, cwd=ROOT, timeout=600)
     assert res.returncode != 0 and "no CPU path" in (res.stderr + res.stdout)
+
+
+def test_parity_block_and_topk_rule_on_cpu():
+    """bench.parity_block is the in-run checker of every bench line: on CPU, fed with the oracle's own logits (plus a
+    perturbation) it must report zero (resp. the perturbation), all documented keys, and its top-k rule must agree with
+    tests/helpers.topk_agree."""
+    import torch
+    import bench
+    from oracle.protnote_oracle import EncoderCfg, ScorerCfg, protnote_forward
+    from tests.helpers import topk_agree
+    torch.manual_seed(0)
+    model = bench.base_config_model("strict")
+    onehots, lengths, labels = bench.synthetic_inputs(3, 48, 40, pinned=False)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    ref = protnote_forward(sd, onehots, lengths, labels, EncoderCfg(), ScorerCfg())
+    blk = bench.parity_block(model, ref.clone(), onehots, lengths, labels, 1, world=2, proteins=(0, 1, 2))
+    for key in ("checker", "proteins", "pairs_checked", "max_abs_err", "tol", "within_tol", "logit_std",
+                "top10_identical_where_decided", "shard_boundary_columns", "shard_boundary_max_abs_err"):
+        assert key in blk, key
+    assert blk["max_abs_err"] == 0.0 and blk["within_tol"] and blk["top10_identical_where_decided"]
+    assert blk["pairs_checked"] == 3 * 40 and blk["shard_boundary_columns"] == [0, 19, 20, 39]
+    off = ref.clone()
+    off[1, 20] += 3e-4
+    blk = bench.parity_block(model, off, onehots, lengths, labels, 1, world=2, proteins=(0, 1, 2))
+    assert not blk["within_tol"] and abs(blk["max_abs_err"] - 3e-4) < 1e-6 and abs(blk["shard_boundary_max_abs_err"] - 3e-4) < 1e-6
+    # the top-k rule of the bench and of the tests is the same function of (reference, candidate)
+    g = torch.Generator().manual_seed(1)
+    for _ in range(20):
+        r = torch.randn(4, 30, generator=g)
+        c = r + torch.randn(4, 30, generator=g) * 2e-4
+        assert bench.topk_decided_agree(r, c, 10, 1e-4)[0] == topk_agree(r, c, 10, 1e-4)
