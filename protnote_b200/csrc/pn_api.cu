@@ -635,6 +635,19 @@ __global__ void copy_floats_kernel(const float* __restrict__ src, float* __restr
   if (i < n) dst[i] = src[i];
 }
 
+// fp64 layer of the protein-side head: the skinny kernel up to 64 rows, the tiled one above
+void launch_linear_f64(const double* x, long long M, int K, long long ldx, const float* w, int N, long long ldw,
+                       const double* scale, const double* shift, int relu, double* y64, long long ldy64, float* y32,
+                       long long ldy32, cudaStream_t stream) {
+  if (M <= 64) {
+    const dim3 grid((unsigned)((N + 7) / 8), (unsigned)((M + 7) / 8));
+    linear_f64_skinny_kernel<<<grid, 256, 0, stream>>>(x, M, K, ldx, w, N, ldw, scale, shift, relu, y64, ldy64, y32, ldy32);
+  } else {
+    const dim3 grid((unsigned)((N + 63) / 64), (unsigned)((M + 63) / 64));
+    linear_f64_kernel<<<grid, 256, 0, stream>>>(x, M, K, ldx, w, N, ldw, scale, shift, relu, y64, ldy64, y32, ldy32);
+  }
+}
+
 // One projection head (W_p or W_l) followed by its half of output layer 1.
 int run_projection(const pn_scorer_cfg& c, const ScorerLayout& L, const Arena& pk, bool protein, const float* in,
                    long long n, float* emb_out, float* half_out, void* workspace, size_t workspace_bytes, int mode,
@@ -663,11 +676,9 @@ int run_projection(const pn_scorer_cfg& c, const ScorerLayout& L, const Arena& p
       for (size_t i = 0; i < head.size(); ++i) {
         const bool last = i + 1 == head.size();
         const int N = head[i].N;
-        const dim3 grid((unsigned)((N + 63) / 64), (unsigned)((rows + 63) / 64));
-        linear_f64_kernel<<<grid, 256, 0, stream>>>(cur, rows, K, ldc, pk.at<float>(L.wp_raw[i]), N, K,
-                                                    last ? nullptr : pk.at<double>(L.wp_scale64[i]),
-                                                    last ? nullptr : pk.at<double>(L.wp_shift64[i]), last ? 0 : 1, buf[q], ld64,
-                                                    (last && emb_out) ? emb_out + r0 * c.latent_dim : nullptr, c.latent_dim);
+        launch_linear_f64(cur, rows, K, ldc, pk.at<float>(L.wp_raw[i]), N, K, last ? nullptr : pk.at<double>(L.wp_scale64[i]),
+                          last ? nullptr : pk.at<double>(L.wp_shift64[i]), last ? 0 : 1, buf[q], ld64,
+                          (last && emb_out) ? emb_out + r0 * c.latent_dim : nullptr, c.latent_dim, stream);
         g_launches++;
         PN_CUDA(cudaGetLastError());
         cur = buf[q];
@@ -676,10 +687,8 @@ int run_projection(const pn_scorer_cfg& c, const ScorerLayout& L, const Arena& p
         q ^= 1;
       }
       if (half_out) {
-        const dim3 grid((unsigned)((c.out_hidden + 63) / 64), (unsigned)((rows + 63) / 64));
-        linear_f64_kernel<<<grid, 256, 0, stream>>>(cur, rows, K, ldc, pk.at<float>(L.l1p_raw), c.out_hidden, K,
-                                                    pk.at<double>(L.l1p_scale64), pk.at<double>(L.l1p_shift64), 0, nullptr, 0,
-                                                    half_out + r0 * c.out_hidden, c.out_hidden);
+        launch_linear_f64(cur, rows, K, ldc, pk.at<float>(L.l1p_raw), c.out_hidden, K, pk.at<double>(L.l1p_scale64),
+                          pk.at<double>(L.l1p_shift64), 0, nullptr, 0, half_out + r0 * c.out_hidden, c.out_hidden, stream);
         g_launches++;
         PN_CUDA(cudaGetLastError());
       }

@@ -192,6 +192,47 @@ __global__ void __launch_bounds__(256) linear_f64_kernel(const double* __restric
   }
 }
 
+// The same layer for SKINNY batches (M <= 64 rows: the reference's evaluation batch is 8 proteins): the tiled kernel above
+// would run 48 blocks for N = 3072 and take 0.45 ms per layer (5 % of a 32-protein step, ncu profiles/r02_launch_shares.txt).
+// Here one warp owns one output column and 8 rows: the lanes stride over K (w[n][k] coalesced, x rows L1-resident), a fixed
+// shuffle tree reduces them - deterministic - and lane 0 finishes the column.  grid (ceil(N / 8), ceil(M / 8)), 256 threads.
+__global__ void __launch_bounds__(256) linear_f64_skinny_kernel(const double* __restrict__ x, long long M, int K, long long ldx,
+                                                                const float* __restrict__ w, int N, long long ldw,
+                                                                const double* __restrict__ scale, const double* __restrict__ shift,
+                                                                int relu, double* __restrict__ y64, long long ldy64,
+                                                                float* __restrict__ y32, long long ldy32) {
+  const int lane = threadIdx.x & 31;
+  const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const long long m0 = (long long)blockIdx.y * 8;
+  if (n >= N) return;
+  double acc[8] = {};
+  const float* wrow = w + (long long)n * ldw;
+  for (int k = lane; k < K; k += 32) {
+    const double wv = (double)__ldg(wrow + k);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const long long m = m0 + r;
+      acc[r] = fma(m < M ? x[m * ldx + k] : 0.0, wv, acc[r]);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const long long m = m0 + r;
+      if (m >= M) break;
+      double v = acc[r] * (scale ? scale[n] : 1.0) + (shift ? shift[n] : 0.0);
+      if (relu) v = v > 0.0 ? v : 0.0;
+      if (y64) y64[m * ldy64 + n] = v;
+      if (y32) y32[m * ldy32 + n] = (float)v;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // activations: fp32 -> fp16 hi/lo planes
 // ------------------------------------------------------------------------------------------------

@@ -45,12 +45,13 @@ def test_truncation_compensation_removes_the_accumulator_bias(native):
     assert rms1 < 0.6 * rms0 and rms1 < rms_torch
 
 
-def test_fp64_protein_side_head(native):
+@pytest.mark.parametrize("rows", [5, 70], ids=["skinny_kernel", "tiled_kernel"])
+def test_fp64_protein_side_head(native, rows):
     """a[b] (W_p + protein half of output layer 1) carries every protein's contribution to all of its logits: strict mode
     evaluates it in fp64 and only rounds the result to fp32."""
     ecfg, scfg, sd, onehots, lengths, labels, g = load_case("base_small")
     model = build_b200_model(ecfg, scfg, sd)
-    P_f = torch.randn(5, scfg.protein_embedding_dim, generator=torch.Generator().manual_seed(3))
+    P_f = torch.randn(rows, scfg.protein_embedding_dim, generator=torch.Generator().manual_seed(3))
     f64 = torch.float64
     P_e64 = projection_head(sd, "W_p", P_f.double(), scfg, f64)
     W1 = sd["output_layer.0.weight"].double()
