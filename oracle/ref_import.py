@@ -1,16 +1,24 @@
 """TEST INFRASTRUCTURE ONLY - not part of the product path.
 
-Import shim for the *unmodified* reference classes living in /root/reference.
+Import shim for the *unmodified* reference classes.
 
 The reference's hot-path modules (`protnote/models/ProtNote.py`,
 `protnote/models/protein_encoders.py`, `protnote/data/datasets.py:535-569`)
 import cleanly once a handful of third-party modules that the hot path never
 touches (`loralib`, `blosum`, `wget`, `Bio.*`) are stubbed in `sys.modules`
-(SURVEY.md section 8c).  This file is used ONLY in the build container, by
-`oracle/make_golden.py` and by the CPU tests that pin the travelling oracle
-(`oracle/protnote_oracle.py`) against the real reference.  `/root/reference`
-does not exist on the GPU box; nothing under `-m gpu`, `smoke()` or `bench.py`
-imports this file.
+(SURVEY.md section 8c).  Where they are imported from:
+
+  * `/root/reference` in the build container - used by `oracle/make_golden*.py`
+    and by the CPU tests that pin the travelling oracle
+    (`oracle/protnote_oracle.py`) against the real reference;
+  * `oracle/_ref/` on the GPU box - a byte-for-byte copy of the reference's own
+    `protnote/` package staged by `oracle/build_ref.py` (git-ignored: the
+    reference's sources never enter this repository; shipped with the snapshot
+    like a built .so).  Only `bench.py`'s CPU arm (`--impl reference`,
+    `cpu_baseline`) uses it there, to time the reference's own classes.
+
+Nothing under `-m gpu` or `smoke()` imports this file, and the product package
+`protnote_b200` never does.
 """
 from __future__ import annotations
 

@@ -1,4 +1,5 @@
-# A/B of build-time variants on the GPU box: rebuild with the given nvcc flags, then run the sustained sweep
+# A/B of build-time variants on the GPU box: rebuild the library with extra nvcc flags (PN_NVCC_FLAGS, read by
+# protnote_b200/build.py), then run the sustained sweep.   bash tools/ab_build.sh "" "-DSOME_EXPERIMENT"
 for flags in "$@"; do
   echo "=== PN_NVCC_FLAGS=$flags"
   PN_NVCC_FLAGS="$flags" python -m protnote_b200.build --force > /dev/null
