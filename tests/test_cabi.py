@@ -109,3 +109,32 @@ def test_header_is_plain_c(tmp_path):
     assert run.returncode == 0, run.stderr           # sizes are host arithmetic; the empty call returns an error status
     version, scorer_bytes, encoder_bytes, nparams = run.stdout.split()
     assert int(version) >= 1 and int(scorer_bytes) > 100e6 and int(encoder_bytes) > 50e6 and int(nparams) == 49
+
+
+def test_label_fingerprint_digest_is_order_sensitive():
+    """The on-disk label-projection cache is keyed by a digest of the label embeddings and weights: permuting rows (a
+    re-sorted vocabulary) or columns must change it, an identical copy must not."""
+    import torch
+    from protnote_b200.ProtNote import ProtNote
+    g = torch.Generator().manual_seed(0)
+    t = torch.randn(37, 16, generator=g)
+    base = ProtNote._digest(t)
+    assert ProtNote._digest(t.clone()) == base
+    perm = torch.randperm(37, generator=g)
+    assert ProtNote._digest(t[perm])[:2] == pytest.approx(base[:2], rel=1e-12)      # plain sums cannot see a permutation
+    assert abs(ProtNote._digest(t[perm])[2] - base[2]) > 1e-6 * abs(base[2])        # the position-weighted sum does
+    assert abs(ProtNote._digest(t[:, torch.randperm(16, generator=g)])[2] - base[2]) > 1e-6 * abs(base[2])
+
+
+def test_token_ids_are_range_checked_before_narrowing():
+    """CPU token tensors are narrowed to uint8 for the PCIe copy: ids outside [0, 255] (a -1 padding id, 256+) must raise
+    instead of wrapping into a valid residue - before any device work."""
+    import torch
+    from protnote_b200.protein_encoders import ProteInfer
+    enc = ProteInfer(num_labels=4, input_channels=20, output_channels=16, kernel_size=9, activation=torch.nn.ReLU,
+                     dilation_base=3, num_resnet_blocks=1, bottleneck_factor=0.5).eval()
+    lengths = torch.tensor([5, 5])
+    for bad in (torch.tensor([[0, 1, -1, 3, 4], [0, 1, 2, 3, 4]]), torch.tensor([[0, 1, 256, 3, 4], [0, 1, 2, 3, 4]]),
+                torch.rand(2, 5)):
+        with pytest.raises(ValueError):
+            enc.get_embeddings_from_tokens(bad, lengths)
