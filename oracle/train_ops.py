@@ -136,6 +136,13 @@ class TorchOps:
         vc = (sc[1] / L - mc * mc).clamp_min(0)
         return self._finalize(ma + mc, va + vc, float(B) * float(L), bn, update_running)
 
+    def affine_state(self, bias, cols, device=None):
+        """State of a layer without BatchNorm: relu(z * 1 + bias); mean 0 / invstd 1 make xhat = z, which the backward
+        only ever multiplies with a cleared sum."""
+        t = self.dtype
+        b = torch.zeros(cols, dtype=t) if bias is None else bias.detach().to(t).reshape(-1)
+        return TBN(torch.ones(cols, dtype=t), b, torch.zeros(cols, dtype=t), torch.ones(cols, dtype=t))
+
     def bn_relu(self, z: TAct, st: TBN, want_T=False):
         return TAct(torch.relu(z.val * st.scale + st.shift), 1.0, want_T)
 

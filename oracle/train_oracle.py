@@ -59,7 +59,7 @@ def loss_oracle(logits, targets, loss="bce", pos_weight=None, gamma=2.0, alpha=-
 def train_step_oracle(sd: Dict[str, torch.Tensor], P_f, L_f, targets, cfg: ScorerCfg, dtype=torch.float64, **loss_kw):
     """Returns (logits [B, L], loss, {state_dict key: gradient}, {running-stat key: updated value}).
     loss_kw: arguments of loss_oracle (default: BCE-with-logits, mean)."""
-    if cfg.feature_fusion != "concatenation":
+    if not cfg.feature_fusion.startswith("concatenation"):
         raise NotImplementedError(cfg.feature_fusion)
     p = {k: v.detach().clone().to(dtype).requires_grad_(True) for k, v in sd.items()
          if v.is_floating_point() and not k.startswith("sequence_encoder.") and "running_" not in k}
@@ -75,8 +75,10 @@ def train_step_oracle(sd: Dict[str, torch.Tensor], P_f, L_f, targets, cfg: Score
                 x = torch.relu(_bn_train(x, full, f"{prefix}.{4 * i + 1}", cfg.bn_eps, new_stats))
         return x
 
-    P_e = head("W_p", P_f.to(dtype))
-    L_e = head("W_l", L_f.to(dtype))
+    # ProtNote.py:83-86: with embedding dropouts the heads are Sequential(Dropout, MLP) and their keys move to W_p.1.* /
+    # W_l.1.*.  The dropout itself is a random draw: this oracle takes P_f / L_f AFTER it (the caller replays the masks).
+    P_e = head("W_p.1" if cfg.sequence_embedding_dropout > 0 else "W_p", P_f.to(dtype))
+    L_e = head("W_l.1" if cfg.label_embedding_dropout > 0 else "W_l", L_f.to(dtype))
     x = joint_features(P_e, L_e, cfg.feature_fusion)
     hidden, last = output_mlp_layout(cfg)
     for lin, bn in hidden:

@@ -156,8 +156,6 @@ class ProteInfer(torch.nn.Module):
     def get_embeddings_from_tokens(self, tokens, sequence_lengths):
         """[B, T] integer residue ids (the argmax of the collator's one-hot, collators.py:123-133) -> [B, C]; the result is
         bit-identical to get_embeddings() on the one-hot, with 1 byte instead of 80 per residue crossing PCIe."""
-        if self.training:
-            raise ProtnoteB200Error("the sm_100a encoder implements eval-mode BatchNorm only; call .eval()")
         dev = self.conv1.weight.device
         if tokens.dtype != torch.uint8:
             # range-check BEFORE narrowing (a -1 padding id or an id >= 256 must not wrap into a valid residue); CPU
@@ -168,6 +166,16 @@ class ProteInfer(torch.nn.Module):
                 if tokens.numel() and (int(tokens.min()) < 0 or int(tokens.max()) > 255):
                     raise ValueError("token ids must be integers in [0, 255]")
                 tokens = tokens.to(torch.uint8)
+        if self.training:
+            # .train() mode (batch-statistic BatchNorm, _get_embeddings_train): that kernel chain takes the one-hot layout,
+            # which is expanded here ON the device - still one byte per residue over PCIe.  A pure layout expansion: ids
+            # >= input_channels give an all-zero column, as in the eval-mode token kernel; padding is masked downstream.
+            tokens = tokens.to(dev, non_blocking=True)
+            if tokens.dtype != torch.uint8 and tokens.numel() and (int(tokens.min()) < 0 or int(tokens.max()) > 255):
+                raise ValueError("token ids must be integers in [0, 255]")
+            ids = torch.arange(self.conv1.in_channels, device=dev, dtype=tokens.dtype)
+            onehots = (tokens[:, None, :] == ids[None, :, None]).to(torch.float32)
+            return self._get_embeddings_train(onehots, sequence_lengths.to(dev, non_blocking=True))
         return self._ensure_packed().forward_tokens(tokens.to(dev, non_blocking=True),
                                                     sequence_lengths.to(dev, non_blocking=True),
                                                     native.MODES[self.precision])

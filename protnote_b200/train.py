@@ -47,6 +47,12 @@ class Comm:
             self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
         return t
 
+    def bcast_(self, t: torch.Tensor):
+        """The first rank's value on every rank (for quantities that are replicated over the ranks but random)."""
+        if self.world > 1:
+            src = self.dist.get_global_rank(self.group, 0) if self.group is not None else 0
+            self.dist.broadcast(t, src=src, group=self.group)
+        return t
 
     def sum_async(self, t: torch.Tensor):
         """Starts the all-reduce of `t` on NCCL's own stream and returns the work handle (None at world 1): the caller keeps
@@ -63,6 +69,9 @@ class _NoComm:
         return t
 
     def max_(self, t):
+        return t
+
+    def bcast_(self, t):
         return t
 
     def sum_async(self, t):
@@ -89,18 +98,29 @@ class LossSpec:
         self.grad_scale = 1.0     # set per batch by forward_train
 
 
-def _split_sequential(seq: nn.Module) -> List[Tuple[nn.Linear, Optional[nn.BatchNorm1d]]]:
-    """[(Linear, BatchNorm1d or None)] of a torchvision-MLP-shaped Sequential (ProtNote.py:63-81,337-378).
-    Dropout layers must be inactive (p == 0): the reference's defaults (base_config.yaml:39-41)."""
+def _unwrap(seq: nn.Module):
+    """(modules, p) of a head: ProtNote.py:83-86 wraps W_p / W_l in Sequential(Dropout(p), MLP) when
+    SEQUENCE_EMBEDDING_DROPOUT / LABEL_EMBEDDING_DROPOUT > 0 - p is that input dropout, 0 without the wrapper."""
     mods = list(seq)
     if len(mods) == 2 and isinstance(mods[0], nn.Dropout) and isinstance(mods[1], nn.Sequential):
-        if mods[0].p > 0:
-            raise NotImplementedError("dropout > 0 is not implemented on the sm_100a training path")
-        mods = list(mods[1])
+        return list(mods[1]), float(mods[0].p)
+    return mods, 0.0
+
+
+def input_dropout(seq: nn.Module) -> float:
+    return _unwrap(seq)[1]
+
+
+def _split_sequential(seq: nn.Module) -> List[Tuple[nn.Linear, Optional[nn.BatchNorm1d]]]:
+    """[(Linear, BatchNorm1d or None)] of a torchvision-MLP-shaped Sequential (ProtNote.py:63-81,337-378).
+    Dropout layers INSIDE the MLP (OUTPUT_MLP_DROPOUT) must be inactive (p == 0): the reference's default
+    (base_config.yaml:39).  The input dropout of a Sequential(Dropout, MLP) wrapper is applied by forward_train."""
+    mods, _ = _unwrap(seq)
     out = []
     for i, m in enumerate(mods):
         if isinstance(m, nn.Dropout) and m.p > 0:
-            raise NotImplementedError("dropout > 0 is not implemented on the sm_100a training path")
+            raise NotImplementedError("OUTPUT_MLP_DROPOUT > 0 (dropout inside W_p / W_l / output_layer) is not implemented "
+                                      "on the sm_100a training path")
         if isinstance(m, nn.Linear):
             bn = mods[i + 1] if i + 1 < len(mods) and isinstance(mods[i + 1], nn.BatchNorm1d) else None
             out.append((m, bn))
@@ -152,34 +172,59 @@ def head_backward(ops, comm, g_f32, saved, rows_total: int, sharded: bool, grads
 # --------------------------------------------------------------------------------------------------------------------
 # pair scorer (ProtNote.py:112-126,293,337-378)
 # --------------------------------------------------------------------------------------------------------------------
+def layer1_factors(lin1: nn.Linear, d: int, fusion: str):
+    """The two [H, d] matrices that make layer 1 of the output MLP a sum of a protein term and a label term
+    (ProtNote.py:112-152): z1[b,l] = P_e[b] Wp^T + L_e[l] Wl^T.
+      'concatenation'       [p; t]        Wp = W[:, :d],               Wl = W[:, d:2d]
+      'concatenation_diff'  [p; t; p - t] Wp = W[:, :d] + W[:, 2d:],   Wl = W[:, d:2d] - W[:, 2d:]
+    ([H, d] parameter arithmetic, once per step; 'concatenation_prod' is not a sum of two such terms.)"""
+    W = lin1.weight.detach()
+    if fusion == "concatenation" and W.shape[1] == 2 * d:
+        return W[:, :d], W[:, d:]
+    if fusion == "concatenation_diff" and W.shape[1] == 3 * d:
+        return W[:, :d] + W[:, 2 * d:], W[:, d:2 * d] - W[:, 2 * d:]
+    raise NotImplementedError(f"the training path implements FEATURE_FUSION 'concatenation' (base_config.yaml:44) and "
+                              f"'concatenation_diff'; got '{fusion}' with {W.shape[1]} input features for latent_dim {d}")
+
+
+def _layer_state(ops, comm, z, lin, bn, count, sharded, update_running):
+    """BatchNorm state of one hidden layer from its batch statistics - or, without BatchNorm (OUTPUT_MLP_BATCHNORM False:
+    get_mlp then gives the Linear a bias, ProtNote.py:352-365), the fixed affine map relu(z + bias)."""
+    if bn is None:
+        return ops.affine_state(lin.bias, lin.weight.shape[0], lin.weight.device)
+    stats = ops.col_stats(z)
+    if sharded:
+        comm.sum_(stats)
+    return ops.bn_finalize(stats, count, bn, update_running)
+
+
 def pairs_forward(ops, comm, P_e, L_e, hidden, final: nn.Linear, L_total: int, sharded: bool, update_running: bool,
-                  loss: Optional[LossSpec] = None, targets=None):
+                  loss: Optional[LossSpec] = None, targets=None, fusion: str = "concatenation"):
     B, d = P_e.shape
+    if len(hidden) < 2:
+        raise NotImplementedError("the training path needs OUTPUT_MLP_NUM_LAYERS >= 2 (base_config.yaml:35 has 3)")
     lin1, bn1 = hidden[0]
-    if bn1 is None or any(bn is None for _, bn in hidden):
-        raise NotImplementedError("the training path implements OUTPUT_MLP_BATCHNORM True (base_config.yaml:36)")
-    if lin1.weight.shape[1] != 2 * d:
-        raise NotImplementedError("the training path implements FEATURE_FUSION 'concatenation' (base_config.yaml:44)")
+    W1p, W1l = layer1_factors(lin1, d, fusion)
     pe = ops.split(P_e, want_T=True)
     le = ops.split(L_e, want_T=True)
-    a = ops.linear(pe, ops.pack(lin1.weight[:, :d]), out_f32=True)          # [B, H] raw protein half
-    c = ops.linear(le, ops.pack(lin1.weight[:, d:]), out_f32=True)          # [L_local, H] raw label half
-    sa = ops.col_stats_f32(a)
-    sc = ops.col_stats_f32(c)
-    if sharded:
-        comm.sum_(sc)
-    st1 = ops.bn_finalize_pair(sa, B, sc, L_total, bn1, update_running)
+    a = ops.linear(pe, ops.pack(W1p), out_f32=True)                         # [B, H] raw protein term
+    c = ops.linear(le, ops.pack(W1l), out_f32=True)                         # [L_local, H] raw label term
+    if bn1 is None:
+        st1 = ops.affine_state(lin1.bias, lin1.weight.shape[0], lin1.weight.device)
+    else:
+        sa = ops.col_stats_f32(a)
+        sc = ops.col_stats_f32(c)
+        if sharded:
+            comm.sum_(sc)
+        st1 = ops.bn_finalize_pair(sa, B, sc, L_total, bn1, update_running)
     h = ops.pair_hidden(a, c, st1, want_T=True)                             # [B * L_local, H]
     ctx = {"pe": pe, "le": le, "a": a, "c": c, "st1": st1, "layers": [], "B": B, "d": d, "hidden": hidden,
-           "final": final, "count": B * L_total}
+           "final": final, "count": B * L_total, "fusion": fusion, "W1p": W1p, "W1l": W1l}
     logits = None
     for j in range(1, len(hidden)):
         lin, bn = hidden[j]
         z = ops.linear(h, ops.pack(lin.weight), out_f32=False)
-        stats = ops.col_stats(z)
-        if sharded:
-            comm.sum_(stats)
-        st = ops.bn_finalize(stats, B * L_total, bn, update_running)
+        st = _layer_state(ops, comm, z, lin, bn, B * L_total, sharded, update_running)
         ctx["layers"].append((h, z, st, lin, bn))
         if j + 1 < len(hidden):
             h = ops.bn_relu(z, st, want_T=True)
@@ -214,6 +259,21 @@ class _Grads(dict):
         self.pending = []
 
 
+def _affine_grads(ops, comm, s, lin, bn, sharded: bool, grads: Dict):
+    """Parameter gradients of the normalisation that follows `lin`, from the two column sums of the backward statistics
+    pass (sum g_y, sum g_y * xhat).  With BatchNorm they are d beta / d gamma, and the sums - completed over the label
+    shards - go on into the BatchNorm backward.  Without BatchNorm the first sum is the gradient of the Linear's bias and
+    nothing is subtracted from g_y: the sums are cleared, which turns bwd_apply into the plain ReLU backward."""
+    if bn is not None:
+        grads[bn.weight], grads[bn.bias] = ops.bn_param_grads(s)
+        if sharded:
+            comm.sum_(s.sums)
+        return
+    if lin.bias is not None:
+        grads[lin.bias] = ops.bn_param_grads(s)[1]
+    s.sums.zero_()
+
+
 def pairs_backward(ops, comm, ctx, g_logit, sharded: bool, grads: Dict):
     hidden, final, count = ctx["hidden"], ctx["final"], ctx["count"]
     layers = ctx["layers"]
@@ -221,10 +281,8 @@ def pairs_backward(ops, comm, ctx, g_logit, sharded: bool, grads: Dict):
     h_prev, z, st, lin, bn = layers.pop()        # consumed: activations are released layer by layer
     go = ops.outer(g_logit, final.weight)
     s = ops.bwd_stats(go, z, st)
-    grads[bn.weight], grads[bn.bias] = ops.bn_param_grads(s)
     grads[final.weight], grads[final.bias] = ops.final_param_grads(s)
-    if sharded:
-        comm.sum_(s.sums)
+    _affine_grads(ops, comm, s, lin, bn, sharded, grads)
     g = ops.bwd_apply(go, z, st, s, count, want_T=True)
     grads[lin.weight] = ops.wgrad(g, h_prev)
     del h_prev, z
@@ -233,9 +291,7 @@ def pairs_backward(ops, comm, ctx, g_logit, sharded: bool, grads: Dict):
     while layers:
         h_prev, z, st, lin, bn = layers.pop()
         s = ops.bwd_stats(g, z, st)
-        grads[bn.weight], grads[bn.bias] = ops.bn_param_grads(s)
-        if sharded:
-            comm.sum_(s.sums)
+        _affine_grads(ops, comm, s, lin, bn, sharded, grads)
         g = ops.bwd_apply(g, z, st, s, count, want_T=True)
         grads[lin.weight] = ops.wgrad(g, h_prev)
         del h_prev, z
@@ -245,18 +301,18 @@ def pairs_backward(ops, comm, ctx, g_logit, sharded: bool, grads: Dict):
     d = ctx["d"]
     zp = ops.pair_source(ctx["a"], ctx["c"])
     s = ops.bwd_stats(g, zp, ctx["st1"])
-    grads[bn1.weight], grads[bn1.bias] = ops.bn_param_grads(s)
-    if sharded:
-        comm.sum_(s.sums)
+    _affine_grads(ops, comm, s, lin1, bn1, sharded, grads)
     da, dc = ops.bwd_apply_pair(g, zp, ctx["st1"], s, count)                # fp32 [B, H], [L_local, H]
     dW1 = torch.empty_like(lin1.weight)
     ga = ops.split(da, want_T=True, autoscale=True)
     gc = ops.split(dc, want_T=True, autoscale=True)
-    ops.wgrad(ga, ctx["pe"], out=dW1[:, :d])
-    ops.wgrad(gc, ctx["le"], out=dW1[:, d:])
+    ops.wgrad(ga, ctx["pe"], out=dW1[:, :d])                                # d z1 / d Wp = da^T P_e
+    ops.wgrad(gc, ctx["le"], out=dW1[:, d:2 * d])                           # d z1 / d Wl = dc^T L_e
+    if ctx["fusion"] == "concatenation_diff":                               # Wp = W_p + W_d, Wl = W_t - W_d (layer1_factors)
+        torch.sub(dW1[:, :d], dW1[:, d:2 * d], out=dW1[:, 2 * d:])
     grads[lin1.weight] = dW1
-    dPe = ops.dgrad(ga, ops.pack(lin1.weight[:, :d], transposed=True), out_f32=True)
-    dLe = ops.dgrad(gc, ops.pack(lin1.weight[:, d:], transposed=True), out_f32=True)
+    dPe = ops.dgrad(ga, ops.pack(ctx["W1p"], transposed=True), out_f32=True)
+    dLe = ops.dgrad(gc, ops.pack(ctx["W1l"], transposed=True), out_f32=True)
     return dPe, dLe
 
 
@@ -281,9 +337,17 @@ def forward_train(ops, comm, model, P_f, L_f, L_total: Optional[int] = None, upd
     wp, wl = _split_sequential(model.W_p), _split_sequential(model.W_l)
     mods = _split_sequential(model.output_layer)
     hidden, final = mods[:-1], mods[-1][0]
+    # SEQUENCE_EMBEDDING_DROPOUT / LABEL_EMBEDDING_DROPOUT (ProtNote.py:83-86): RNG-stream dependent like the label noise,
+    # so they stay the reference's own torch op, drawn in the reference's order (W_p before W_l, ProtNote.py:270-271).
+    # Every rank holds all proteins: the dropped P_f is the first rank's; label rows are per rank.
+    if input_dropout(model.W_p) > 0:
+        P_f = comm.bcast_(torch.nn.functional.dropout(P_f, input_dropout(model.W_p), True).contiguous())
+    if input_dropout(model.W_l) > 0:
+        L_f = torch.nn.functional.dropout(L_f, input_dropout(model.W_l), True)
     P_e, saved_p = head_forward(ops, comm, P_f, wp, B, False, update_running)
     L_e, saved_l = head_forward(ops, comm, L_f, wl, L_total, sharded, update_running)
-    logits, pctx = pairs_forward(ops, comm, P_e, L_e, hidden, final, L_total, sharded, update_running, loss, targets)
+    logits, pctx = pairs_forward(ops, comm, P_e, L_e, hidden, final, L_total, sharded, update_running, loss, targets,
+                                 getattr(model, "feature_fusion", "concatenation"))
     ctx = {"saved_p": saved_p, "saved_l": saved_l, "pairs": pctx, "B": B, "L_total": L_total, "sharded": sharded}
     if update_running:
         for part in (model.W_p, model.W_l, model.output_layer):

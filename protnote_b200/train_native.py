@@ -192,6 +192,17 @@ class NativeOps:
     def bn_finalize_pair(self, sa, B, sc, L, bn, update_running=True):
         return self._finalize(sa, B, sc, L, bn, update_running)
 
+    def affine_state(self, bias, cols, device):
+        """Layer state [4, cols] (scale, shift, mean, invstd - csrc/pn_train.cuh) of a hidden layer WITHOUT BatchNorm:
+        relu(z * 1 + bias).  mean 0 / invstd 1 make xhat = z in the backward kernels, where it only ever multiplies a
+        cleared sum (train._affine_grads).  Assembled from constants and the bias vector, no arithmetic."""
+        state = torch.zeros(4, int(cols), dtype=torch.float32, device=device)
+        state[0].fill_(1.0)
+        state[3].fill_(1.0)
+        if bias is not None:
+            state[1].copy_(self._f32(bias, "bias").reshape(-1))
+        return state
+
     def bn_relu(self, z: Act, st, want_T=False) -> Act:
         h = Act(z.rows, z.cols, z.hi.device, self.strict, want_T)
         with torch.cuda.device(z.hi.device):

@@ -273,6 +273,89 @@ def test_two_layer_output_mlp_and_optimizer_step():
     assert losses[-1] < losses[0]
 
 
+VARIANTS = {"no_batchnorm": dict(output_mlp_batchnorm=False),
+            "diff": dict(feature_fusion="concatenation_diff"),
+            "diff_no_batchnorm": dict(feature_fusion="concatenation_diff", output_mlp_batchnorm=False),
+            "two_layers_no_batchnorm": dict(output_mlp_num_layers=2, output_mlp_batchnorm=False)}
+
+
+def _variant_cfg(**kw):
+    base = dict(protein_embedding_dim=72, label_embedding_dim=40, latent_dim=32, output_mlp_hidden_dim_scale_factor=3,
+                output_mlp_num_layers=3, projection_head_num_layers=4, projection_head_hidden_dim_scale_factor=3)
+    base.update(kw)
+    return ScorerCfg(**base)
+
+
+@pytest.mark.parametrize("variant", sorted(VARIANTS))
+def test_training_step_variants_match_oracle(variant):
+    """OUTPUT_MLP_BATCHNORM False (hidden layers Linear+bias -> ReLU: the BatchNorm kernels run with the fixed state
+    scale 1 / shift bias and cleared backward sums) and FEATURE_FUSION concatenation_diff (folded into the layer-1 factors):
+    logits, loss, every parameter gradient incl. the hidden biases and the third block of layer 1's weight."""
+    ecfg, _, *_ = CASES["tiny_concat"]
+    scfg = _variant_cfg(**VARIANTS[variant])
+    model, logits, loss, o_logits, o_loss, o_grads, o_stats = _step((ecfg, scfg, 13), 5, 70, "strict", 17)
+    assert float((logits - o_logits).abs().max()) < 1e-4
+    assert abs(loss - o_loss) < 1e-5
+    named = dict(model.named_parameters())
+    assert set(o_grads) == {k for k in named if not k.startswith("sequence_encoder.")}
+    _check_grads(model, o_grads, _step.fp32_grads)
+    bufs = dict(model.named_buffers())
+    for k, v in o_stats.items():
+        assert float((bufs[k].cpu().double() - v).abs().max()) <= 1e-5 * max(1.0, float(v.abs().max())), k
+
+
+def test_fused_focal_loss_without_batchnorm_on_diff_features():
+    """The fused-loss entry point (train_loss) on the same variant: loss value, detached logits and gradients."""
+    from protnote_b200 import train as pn_train
+    ecfg, _, *_ = CASES["tiny_concat"]
+    scfg = _variant_cfg(**VARIANTS["diff_no_batchnorm"])
+    sd = synth_state_dict(ecfg, scfg, seed=13, calib_T=64)
+    g = torch.Generator().manual_seed(29)
+    P_f, L_f = torch.randn(4, 72, generator=g), torch.randn(66, 40, generator=g)
+    y = synth_targets(4, 66, 29)
+    model = build_b200_model(ecfg, scfg, sd, device="cuda").train()
+    loss, logits = pn_train.train_loss(model, P_f.cuda(), L_f.cuda(), y.cuda(), loss="focal", gamma=2.0, alpha=0.25)
+    loss.backward()
+    o_logits, o_loss, o_grads, _ = train_step_oracle(sd, P_f, L_f, y, scfg, loss="focal", gamma=2.0, alpha=0.25)
+    assert float((logits.cpu().double() - o_logits).abs().max()) < 1e-4
+    assert abs(float(loss.detach()) - float(o_loss)) <= 1e-5 * max(1.0, abs(float(o_loss)))
+    _check_grads(model, o_grads, train_step_oracle(sd, P_f, L_f, y, scfg, dtype=torch.float32, loss="focal", gamma=2.0,
+                                                   alpha=0.25)[2])
+
+
+def test_embedding_dropouts_on_device():
+    """SEQUENCE_EMBEDDING_DROPOUT / LABEL_EMBEDDING_DROPOUT > 0 in training: the masks are torch's own dropout draws on the
+    device (W_p's input first, then W_l's - the reference's order, ProtNote.py:270-271), so replaying the two draws with the
+    same seed gives the inputs the step really saw; the oracle on those inputs must give the same logits and gradients."""
+    import dataclasses
+    ecfg, scfg0, *_ = CASES["tiny_concat"]
+    scfg = dataclasses.replace(scfg0, sequence_embedding_dropout=0.25, label_embedding_dropout=0.4)
+    sd = synth_state_dict(ecfg, scfg, seed=42, calib_T=64)
+    assert any(k.startswith("W_p.1.") for k in sd) and any(k.startswith("W_l.1.") for k in sd)
+    g = torch.Generator().manual_seed(31)
+    P_f = torch.randn(6, scfg.protein_embedding_dim, generator=g).cuda()
+    L_f = torch.randn(50, scfg.label_embedding_dim, generator=g).cuda()
+    y = synth_targets(6, 50, 31)
+    model = build_b200_model(ecfg, scfg, sd, device="cuda").train()
+    model.sequence_encoder.eval()
+    torch.manual_seed(77)
+    logits, _ = model(sequence_embeddings=P_f, label_embeddings=L_f)
+    torch.nn.functional.binary_cross_entropy_with_logits(logits, y.cuda()).backward()
+    torch.manual_seed(77)
+    P_d = torch.nn.functional.dropout(P_f, 0.25, True).cpu()
+    L_d = torch.nn.functional.dropout(L_f, 0.4, True).cpu()
+    assert float((P_d == 0).float().mean()) > 0.1 and float((L_d == 0).float().mean()) > 0.25
+    o_logits, _, o_grads, o_stats = train_step_oracle(sd, P_d, L_d, y, scfg)
+    assert float((logits.detach().cpu().double() - o_logits).abs().max()) < 1e-4
+    _check_grads(model, o_grads, train_step_oracle(sd, P_d, L_d, y, scfg, dtype=torch.float32)[2])
+    # eval mode ignores the dropouts (nn.Dropout in eval): same logits as the model without the wrappers
+    model.eval()
+    with torch.no_grad():
+        e1, _ = model(sequence_embeddings=P_f, label_embeddings=L_f)
+        e2, _ = model(sequence_embeddings=P_f, label_embeddings=L_f)
+    assert torch.equal(e1, e2)
+
+
 @pytest.mark.parametrize("name", ["train_tiny", "train_tiny_wide"])
 def test_training_step_matches_reference_golden(name):
     """Against tests/golden/train_*.pt: logits / loss / gradients / running statistics of the reference's own ProtNote class
@@ -326,6 +409,34 @@ def test_train_mode_encoder_matches_oracle(case, B, T):
     sd2.update({k: v.float() for k, v in stats.items()})
     want_eval = proteinfer_embeddings(sd2, onehots, lengths, ecfg, "sequence_encoder.", dtype=torch.float64)
     assert float((e_eval.cpu().double() - want_eval).abs().max()) < 5e-6 * max(1.0, float(want_eval.abs().max()))
+
+
+def test_token_input_in_train_mode_equals_onehot_input():
+    """`sequence_tokens` in training mode: the ids are expanded to the one-hot layout on the device and take the same
+    train-mode kernels, so embeddings, logits and the updated running statistics are bit-identical to the one-hot input
+    (host int64 ids, device uint8 ids, and an id >= input_channels inside the padding)."""
+    from oracle.protnote_oracle import synth_inputs
+    ecfg, scfg, *_ = CASES["tiny_concat"]
+    sd = synth_state_dict(ecfg, scfg, seed=42, calib_T=64)
+    onehots, lengths, labels = synth_inputs(5, 110, 30, ecfg, scfg, ragged=True, seed=12)
+    tokens = onehots.argmax(1)
+    a = build_b200_model(ecfg, scfg, sd, device="cuda").train()
+    b = build_b200_model(ecfg, scfg, sd, device="cuda").train()
+    la, _ = a(sequence_onehots=onehots.cuda(), sequence_lengths=lengths.cuda(), label_embeddings=labels.cuda())
+    lb, _ = b(sequence_tokens=tokens, sequence_lengths=lengths, label_embeddings=labels.cuda())
+    assert torch.equal(la, lb)
+    for (k, x), (_, y) in zip(a.named_buffers(), b.named_buffers()):
+        assert torch.equal(x, y), k
+    with torch.no_grad():
+        e1 = a.sequence_encoder.get_embeddings(onehots.cuda(), lengths.cuda())
+        dev_tokens = tokens.to(torch.uint8).cuda()
+        short = int(lengths.argmin())
+        if int(lengths[short]) < tokens.shape[1]:
+            dev_tokens[short, -1] = 200                      # padding position: masked, whatever the id
+        e2 = b.sequence_encoder.get_embeddings_from_tokens(dev_tokens, lengths.cuda())
+    assert torch.equal(e1, e2)
+    with pytest.raises(ValueError):
+        b.sequence_encoder.get_embeddings_from_tokens(tokens - 1, lengths)
 
 
 def test_whole_model_train_mode_with_onehot_input():
@@ -441,7 +552,7 @@ def test_fused_loss_and_seed_match_oracle(kw):
     torch.cuda.synchronize()
     o_logits, o_loss, o_grads, _ = train_step_oracle(sd, P_f, L_f, y, scfg, **kw)
     assert (logits.cpu().double() - o_logits).abs().max() <= 1e-4
-    assert abs(float(loss) - float(o_loss)) <= 1e-5 * max(1.0, abs(float(o_loss)))
+    assert abs(float(loss.detach()) - float(o_loss)) <= 1e-5 * max(1.0, abs(float(o_loss)))
     named = dict(model.named_parameters())
     for k, g in o_grads.items():
         got = named[k].grad.cpu().double()

@@ -139,9 +139,16 @@ def test_train_mode_encoder_oracle_matches_reference():
         assert (bufs[k] - v).abs().max() < 1e-10, k
 
 
+def _variant_cfg(**kw):
+    base = dict(protein_embedding_dim=72, label_embedding_dim=40, latent_dim=32, output_mlp_hidden_dim_scale_factor=3,
+                output_mlp_num_layers=3, projection_head_num_layers=4, projection_head_hidden_dim_scale_factor=3)
+    base.update(kw)
+    return ScorerCfg(**base)
+
+
 def test_training_path_refuses_what_it_does_not_implement():
-    """Unsupported options fail loudly (no silent fallback): dropout > 0, a fusion other than 'concatenation', an output MLP
-    without BatchNorm; and the product module itself has no CPU path in training mode either."""
+    """Unsupported options fail loudly (no silent fallback): dropout > 0 inside the MLPs, 'concatenation_prod' (not a sum of
+    a protein and a label term), a one-layer output MLP; and the product module itself has no CPU path in training mode."""
     from protnote_b200._lib import ProtnoteB200Error
     ecfg, scfg, sd, P_f, L_f, y = _problem()
     model = build_b200_model(ecfg, scfg, sd, device="cpu").double().train()
@@ -154,26 +161,115 @@ def test_training_path_refuses_what_it_does_not_implement():
     for m in model.output_layer.modules():
         if isinstance(m, torch.nn.Dropout):
             m.p = 0.0
-    prod_cfg = ScorerCfg(protein_embedding_dim=72, label_embedding_dim=40, latent_dim=32,
-                         output_mlp_hidden_dim_scale_factor=3, output_mlp_num_layers=3, projection_head_num_layers=4,
-                         projection_head_hidden_dim_scale_factor=3, feature_fusion="concatenation_prod")
+    prod_cfg = _variant_cfg(feature_fusion="concatenation_prod")
     sd_prod = synth_state_dict(ecfg, prod_cfg, seed=3, calib_T=64)
     prod = build_b200_model(ecfg, prod_cfg, sd_prod, device="cpu").double().train()
     with pytest.raises(NotImplementedError):
         pn_train.forward_train(ops, None, prod, P_f.double(), L_f.double())
-    nobn_cfg = ScorerCfg(protein_embedding_dim=72, label_embedding_dim=40, latent_dim=32,
-                         output_mlp_hidden_dim_scale_factor=3, output_mlp_num_layers=3, projection_head_num_layers=4,
-                         projection_head_hidden_dim_scale_factor=3, output_mlp_batchnorm=False)
-    sd_nobn = synth_state_dict(ecfg, nobn_cfg, seed=4, calib_T=64)
-    nobn = build_b200_model(ecfg, nobn_cfg, sd_nobn, device="cpu").double().train()
+    one_cfg = _variant_cfg(output_mlp_num_layers=1)
+    one = build_b200_model(ecfg, one_cfg, synth_state_dict(ecfg, one_cfg, seed=4, calib_T=64), device="cpu").double().train()
     with pytest.raises(NotImplementedError):
-        pn_train.forward_train(ops, None, nobn, P_f.double(), L_f.double())
+        pn_train.forward_train(ops, None, one, P_f.double(), L_f.double())
     # the product module: CPU tensors in training mode -> error, never a torch fallback
     cpu_model = build_b200_model(ecfg, scfg, sd, device="cpu").train()
     with pytest.raises(ProtnoteB200Error):
         cpu_model(sequence_embeddings=P_f, label_embeddings=L_f)
     with pytest.raises(ValueError):
         cpu_model(sequence_embeddings=P_f)
+
+
+VARIANTS = {"no_batchnorm": dict(output_mlp_batchnorm=False),
+            "diff": dict(feature_fusion="concatenation_diff"),
+            "diff_no_batchnorm": dict(feature_fusion="concatenation_diff", output_mlp_batchnorm=False),
+            "two_layers_no_batchnorm": dict(output_mlp_num_layers=2, output_mlp_batchnorm=False)}
+
+
+@pytest.mark.parametrize("variant", sorted(VARIANTS))
+def test_sequencing_matches_oracle_variants(variant):
+    """OUTPUT_MLP_BATCHNORM False (Linear+bias -> ReLU layers: the BatchNorm primitives run with a fixed affine state and
+    cleared backward sums) and FEATURE_FUSION concatenation_diff (folded into the two layer-1 factors) through the same
+    primitive sequence: logits, every parameter gradient (incl. the hidden biases and the third weight block) and the
+    running statistics against the autograd oracle."""
+    ecfg, _, *_ = CASES["tiny_concat"]
+    scfg = _variant_cfg(**VARIANTS[variant])
+    sd = synth_state_dict(ecfg, scfg, seed=13, calib_T=64)
+    g = torch.Generator().manual_seed(17)
+    P_f, L_f = torch.randn(5, 72, generator=g), torch.randn(9, 40, generator=g)
+    _ours_vs_oracle(scfg, ecfg, sd, P_f, L_f, synth_targets(5, 9, 17), 1e-9)
+    if not scfg.output_mlp_batchnorm:       # the hidden biases are parameters of this variant: they must have been checked
+        assert any(k.startswith("output_layer.") and k.endswith(".bias") and k != "output_layer.6.bias"
+                   for k in train_step_oracle(sd, P_f, L_f, synth_targets(5, 9, 17), scfg)[2])
+
+
+@pytest.mark.skipif(not reference_available(), reason="needs /root/reference (build container only)")
+@pytest.mark.parametrize("variant", sorted(VARIANTS))
+def test_train_oracle_variants_match_reference(variant):
+    """The oracle's statement of those variants is the reference class's (train mode, fp64, autograd)."""
+    from oracle.make_golden import build_reference_model
+    ecfg, _, *_ = CASES["tiny_concat"]
+    scfg = _variant_cfg(**VARIANTS[variant])
+    sd = synth_state_dict(ecfg, scfg, seed=13, calib_T=64)
+    g = torch.Generator().manual_seed(17)
+    P_f, L_f = torch.randn(5, 72, generator=g), torch.randn(9, 40, generator=g)
+    y = synth_targets(5, 9, 17)
+    ref = build_reference_model(ecfg, scfg, sd).double().train()
+    logits, _ = ref(sequence_embeddings=P_f.double(), label_embeddings=L_f.double())
+    torch.nn.functional.binary_cross_entropy_with_logits(logits, y.double()).backward()
+    o_logits, _, o_grads, o_stats = train_step_oracle(sd, P_f, L_f, y, scfg)
+    assert (logits.detach() - o_logits).abs().max() < 1e-10
+    named = dict(ref.named_parameters())
+    trainable = [k for k, p in named.items() if not k.startswith("sequence_encoder.")]
+    assert set(o_grads) == set(trainable)
+    for k, gr in o_grads.items():
+        assert (named[k].grad - gr).abs().max() <= 1e-10 * max(1.0, float(gr.abs().max())), k
+    bufs = dict(ref.named_buffers())
+    for k, v in o_stats.items():
+        assert (bufs[k] - v).abs().max() < 1e-10, k
+
+
+@pytest.mark.skipif(not reference_available(), reason="needs /root/reference (build container only)")
+def test_embedding_dropouts_follow_the_reference_rng_stream():
+    """SEQUENCE_EMBEDDING_DROPOUT / LABEL_EMBEDDING_DROPOUT > 0 (ProtNote.py:83-86: W_p / W_l become Sequential(Dropout, MLP),
+    keys W_p.1.* / W_l.1.*) together with the label noise: with the same torch seed the training forward draws the same
+    noise and the same masks in the same order as the reference module, so logits and gradients agree to rounding."""
+    ProtNoteRef, _, _ = import_reference()
+    from protnote_b200.ProtNote import ProtNote
+    kw = dict(protein_embedding_dim=72, label_embedding_dim=40, latent_dim=32, label_embedding_pooling_method="mean",
+              sequence_encoder=None, label_encoder=None, inference_descriptions_per_label=1,
+              output_mlp_hidden_dim_scale_factor=3, output_mlp_num_layers=3, outout_mlp_add_batchnorm=True,
+              projection_head_num_layers=4, projection_head_hidden_dim_scale_factor=3,
+              label_encoder_num_trainable_layers=0, train_sequence_encoder=False, feature_fusion="concatenation",
+              sequence_embedding_dropout=0.25, label_embedding_dropout=0.4, label_embedding_noising_alpha=20.0)
+    torch.manual_seed(3)
+    ref = ProtNoteRef(**kw).double().train()
+    ours = ProtNote(**kw)
+    ours.load_state_dict({k: v.float() for k, v in ref.state_dict().items()}, strict=True)
+    ours = ours.double().train()
+    assert pn_train.input_dropout(ours.W_p) == 0.25 and pn_train.input_dropout(ours.W_l) == 0.4
+    g = torch.Generator().manual_seed(23)
+    P_f, L_f = torch.randn(6, 72, generator=g).double(), torch.randn(11, 40, generator=g).double()
+    counts = torch.full((11,), 7)
+    y = synth_targets(6, 11, 23).double()
+
+    torch.manual_seed(1234)
+    r_logits, _ = ref(sequence_embeddings=P_f, label_embeddings=L_f, label_token_counts=counts)
+    torch.nn.functional.binary_cross_entropy_with_logits(r_logits, y).backward()
+
+    torch.manual_seed(1234)
+    # what ProtNote._forward_train does ahead of the primitives (label noise, ProtNote.py:219-240) ...
+    noised = L_f + (2 * torch.rand_like(L_f) - 1) * (20.0 / 40 ** 0.5)
+    # ... and the primitive sequence (with the torch stand-in), which applies the two dropouts
+    logits = pn_train.train_logits(ours, P_f, noised, ops=TorchOps(torch.float64))
+    torch.nn.functional.binary_cross_entropy_with_logits(logits, y).backward()
+    assert (logits.detach() - r_logits.detach()).abs().max() < 1e-9
+    r_named, named = dict(ref.named_parameters()), dict(ours.named_parameters())
+    for k, p in r_named.items():
+        assert (named[k].grad - p.grad).abs().max() <= 1e-9 * max(1.0, float(p.grad.abs().max())), k
+    # dropout really was active: the same inputs without it give different logits
+    torch.manual_seed(1234)
+    ours.W_p[0].p = ours.W_l[0].p = 0.0
+    plain = pn_train.train_logits(ours, P_f, noised, ops=TorchOps(torch.float64))
+    assert (plain.detach() - logits.detach()).abs().max() > 1e-3
 
 
 def test_single_row_batchnorm_raises_like_torch():

@@ -24,21 +24,24 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _problem():
+def _problem(variant=False):
     ecfg, scfg, *_ = CASES["tiny_concat"]
+    if variant:      # output MLP without BatchNorm (hidden biases, nothing to all-reduce in its backward) on [p; t; p - t]
+        import dataclasses
+        scfg = dataclasses.replace(scfg, output_mlp_batchnorm=False, feature_fusion="concatenation_diff")
     sd = synth_state_dict(ecfg, scfg, seed=42, calib_T=64)
     g = torch.Generator().manual_seed(21)
     B, L = 5, 11     # 11 rows over 2 ranks: uneven shards
     return ecfg, scfg, sd, torch.randn(B, 72, generator=g), torch.randn(L, 40, generator=g), synth_targets(B, L, 21)
 
 
-def _worker(rank, world, port, q, fused=False):
+def _worker(rank, world, port, q, fused=False, variant=False):
     try:
         os.environ["MASTER_ADDR"] = "127.0.0.1"
         os.environ["MASTER_PORT"] = str(port)
         dist.init_process_group("gloo", rank=rank, world_size=world)
         torch.set_num_threads(2)
-        ecfg, scfg, sd, P_f, L_f, y = _problem()
+        ecfg, scfg, sd, P_f, L_f, y = _problem(variant)
         model = build_b200_model(ecfg, scfg, sd, device="cpu").double().train()
         comm = pn_train.Comm()
         ls, le = label_row_bounds(L_f.shape[0], 1, rank, world)
@@ -76,13 +79,14 @@ def _worker(rank, world, port, q, fused=False):
 import pytest  # noqa: E402
 
 
-@pytest.mark.parametrize("fused", [False, True], ids=["bce_via_autograd", "fused_focal_overlapped_allreduce"])
-def test_label_sharded_training_step_equals_single_process(fused):
+@pytest.mark.parametrize("fused,variant", [(False, False), (True, False), (True, True)],
+                         ids=["bce_via_autograd", "fused_focal_overlapped_allreduce", "fused_focal_diff_no_batchnorm"])
+def test_label_sharded_training_step_equals_single_process(fused, variant):
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q, fused)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, fused, variant)) for r in range(world)]
     for p in procs:
         p.start()
     results = [q.get(timeout=300) for _ in range(world)]
@@ -95,7 +99,7 @@ def test_label_sharded_training_step_equals_single_process(fused):
     grads = {k: torch.from_numpy(v) for k, v in grads.items()}
     bufs = {k: torch.from_numpy(v) for k, v in bufs.items()}
     logits0 = torch.from_numpy(logits0)
-    ecfg, scfg, sd, P_f, L_f, y = _problem()
+    ecfg, scfg, sd, P_f, L_f, y = _problem(variant)
     kw = dict(loss="focal", gamma=2.0, alpha=0.25) if fused else {}
     o_logits, o_loss, o_grads, o_stats = train_step_oracle(sd, P_f, L_f, y, scfg, **kw)
     ls, le = label_row_bounds(L_f.shape[0], 1, 0, world)
