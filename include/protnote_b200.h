@@ -290,6 +290,17 @@ int pn_t_bn_finalize(const double* stats, double count, const double* stats2, do
 /* h = relu(z * scale + shift) as planes (+ transposed planes, nullable) */
 int pn_t_bn_relu(const void* z_hi, const void* z_lo, long long rows, int cols, long long ld_z, const float* state,
                  void* h_hi, void* h_lo, long long ld_h, void* hT_hi, void* hT_lo, long long blocksT, void* stream);
+/* Dropout INSIDE W_p / W_l / output_layer (OUTPUT_MLP_DROPOUT, base_config.yaml:39; ProtNote.py:70,80,101 -> torchvision MLP
+ * and get_mlp :369-371): out = x * keep / (1 - p).  keep(row, col) is a pure function of (seed, row, col, cols) - a
+ * counter-based generator, 16 random bits per element, keep <=> bits >= round(p * 65536) - so the backward applies the SAME
+ * mask to the incoming gradient by calling the same function with the same seed; nothing is stored.  The planes variant
+ * also writes the K-blocked transposed planes (nullable) a wgrad needs; it is not in-place.  p = 0 copies. */
+int pn_t_dropout_planes(const void* x_hi, const void* x_lo, long long rows, int cols, long long ld_x,
+                        unsigned long long seed, float p, void* hi, void* lo, long long ld, void* hiT, void* loT,
+                        long long blocksT, void* stream);
+/* the same mask on an fp32 matrix (the output of a projection head); out may alias x */
+int pn_t_dropout_f32(const float* x, long long rows, int cols, long long ldx, unsigned long long seed, float p, float* out,
+                     long long ldo, void* stream);
 /* out[r] = relu(z[r] * scale + shift) . w + b  - the last hidden layer and Linear(H -> 1) (ProtNote.py:373-377) */
 int pn_t_bn_relu_dot(const void* z_hi, const void* z_lo, long long rows, int cols, long long ld_z, const float* state,
                      const float* w, const float* b, float* out, void* stream);

@@ -41,6 +41,8 @@ def build_reference_model(ecfg, scfg, sd):
                      projection_head_num_layers=scfg.projection_head_num_layers,
                      projection_head_hidden_dim_scale_factor=scfg.projection_head_hidden_dim_scale_factor,
                      label_encoder_num_trainable_layers=0, train_sequence_encoder=False,
+                     sequence_embedding_dropout=scfg.sequence_embedding_dropout,
+                     label_embedding_dropout=scfg.label_embedding_dropout, dropout=scfg.output_mlp_dropout,
                      feature_fusion=scfg.feature_fusion, temperature=scfg.temperature)
     model.load_state_dict(sd, strict=True)
     return model.eval()

@@ -67,6 +67,8 @@ class ScorerCfg:
     # which renames the state_dict keys to W_p.1.* / W_l.1.*
     sequence_embedding_dropout: float = 0.0
     label_embedding_dropout: float = 0.0
+    # OUTPUT_MLP_DROPOUT (base_config.yaml:39): Dropout modules inside W_p / W_l / output_layer; inactive in eval mode
+    output_mlp_dropout: float = 0.0
     bn_eps: float = 1e-5  # torch.nn.BatchNorm1d default used by torchvision MLP / get_mlp
 
 

@@ -71,9 +71,41 @@ def pow2_scale(absmax: float) -> float:
     return math.ldexp(1.0, 6 - e)
 
 
+def dropout_multiplier(seed: int, rows: int, cols: int, p: float) -> torch.Tensor:
+    """Statement of the keep mask of pn_t_dropout_planes / pn_t_dropout_f32 (csrc/pn_train.cuh: drop_keep8), as the fp64
+    multiplier keep * 65536 / (65536 - thr), [rows, cols].  Counter-based: element (r, c) takes 16 bits of the splitmix64
+    output of counter 2 * (r * ceil(cols / 8) + c // 8) + 1 + (c % 8) // 4; keep <=> bits >= thr = round(p * 65536)."""
+    import numpy as np
+    thr = min(int(np.rint(np.float32(p) * np.float32(65536.0))), 65535)
+    scale = float(np.float32(65536.0) / np.float32(65536 - thr))
+    groups = (cols + 7) // 8
+    r = np.arange(rows, dtype=np.uint64)[:, None]
+    c = np.arange(groups * 8, dtype=np.uint64)[None, :]
+    ctr = np.uint64(2) * (r * np.uint64(groups) + c // np.uint64(8)) + np.uint64(1) + (c % np.uint64(8)) // np.uint64(4)
+    with np.errstate(over="ignore"):
+        x = np.uint64(seed & ((1 << 64) - 1)) + ctr * np.uint64(0x9E3779B97F4A7C15)
+        x ^= x >> np.uint64(30)
+        x *= np.uint64(0xBF58476D1CE4E5B9)
+        x ^= x >> np.uint64(27)
+        x *= np.uint64(0x94D049BB133111EB)
+        x ^= x >> np.uint64(31)
+    bits = (x >> (np.uint64(16) * (c % np.uint64(4)))) & np.uint64(0xFFFF)
+    keep = (bits >= np.uint64(thr))[:, :cols]
+    return torch.from_numpy(keep.astype(np.float64)) * scale
+
+
 class TorchOps:
     def __init__(self, dtype=torch.float64):
         self.dtype = dtype
+
+    # ------------------------------------------------------------------ dropout inside the MLPs
+    def dropout(self, x: TAct, drop, want_T=False):
+        seed, p = drop
+        return TAct(x.val * dropout_multiplier(seed, x.val.shape[0], x.val.shape[1], p).to(self.dtype), x.sc, want_T)
+
+    def dropout_f32(self, x, drop):
+        seed, p = drop
+        return x * dropout_multiplier(seed, x.shape[0], x.shape[1], p).to(x.dtype)
 
     # ------------------------------------------------------------------ operands
     def split(self, x, want_T=False, autoscale=False):

@@ -56,9 +56,14 @@ def loss_oracle(logits, targets, loss="bce", pos_weight=None, gamma=2.0, alpha=-
     raise NotImplementedError(loss)
 
 
-def train_step_oracle(sd: Dict[str, torch.Tensor], P_f, L_f, targets, cfg: ScorerCfg, dtype=torch.float64, **loss_kw):
+def train_step_oracle(sd: Dict[str, torch.Tensor], P_f, L_f, targets, cfg: ScorerCfg, dtype=torch.float64, masks=None,
+                      **loss_kw):
     """Returns (logits [B, L], loss, {state_dict key: gradient}, {running-stat key: updated value}).
-    loss_kw: arguments of loss_oracle (default: BCE-with-logits, mean)."""
+    loss_kw: arguments of loss_oracle (default: BCE-with-logits, mean).
+    masks: OUTPUT_MLP_DROPOUT as explicit multipliers (keep / (1 - p)) - {("p" | "l", i): after layer i of W_p / W_l (after
+    its ReLU; after the bare last Linear: torchvision MLP, ProtNote.py:63-81), ("o", j): after the ReLU of hidden layer j of
+    output_layer (get_mlp, ProtNote.py:369-371)}; a dropout module is exactly this multiplication with a random mask."""
+    masks = masks or {}
     if not cfg.feature_fusion.startswith("concatenation"):
         raise NotImplementedError(cfg.feature_fusion)
     p = {k: v.detach().clone().to(dtype).requires_grad_(True) for k, v in sd.items()
@@ -73,6 +78,8 @@ def train_step_oracle(sd: Dict[str, torch.Tensor], P_f, L_f, targets, cfg: Score
             x = x @ full[f"{prefix}.{4 * i}.weight"].T
             if i < n - 1:
                 x = torch.relu(_bn_train(x, full, f"{prefix}.{4 * i + 1}", cfg.bn_eps, new_stats))
+            if (prefix[2], i) in masks:
+                x = x * masks[(prefix[2], i)].to(dtype)
         return x
 
     # ProtNote.py:83-86: with embedding dropouts the heads are Sequential(Dropout, MLP) and their keys move to W_p.1.* /
@@ -81,13 +88,15 @@ def train_step_oracle(sd: Dict[str, torch.Tensor], P_f, L_f, targets, cfg: Score
     L_e = head("W_l.1" if cfg.label_embedding_dropout > 0 else "W_l", L_f.to(dtype))
     x = joint_features(P_e, L_e, cfg.feature_fusion)
     hidden, last = output_mlp_layout(cfg)
-    for lin, bn in hidden:
+    for j, (lin, bn) in enumerate(hidden):
         x = x @ full[f"output_layer.{lin}.weight"].T
         if f"output_layer.{lin}.bias" in full:
             x = x + full[f"output_layer.{lin}.bias"]
         if bn is not None:
             x = _bn_train(x, full, f"output_layer.{bn}", cfg.bn_eps, new_stats)
         x = torch.relu(x)
+        if ("o", j) in masks:
+            x = x * masks[("o", j)].to(dtype)
     logits = (x @ full[f"output_layer.{last}.weight"].T + full[f"output_layer.{last}.bias"]).reshape(
         P_e.shape[0], L_e.shape[0])
     if "pos_weight" in loss_kw and loss_kw["pos_weight"] is not None:

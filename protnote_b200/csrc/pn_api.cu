@@ -1788,6 +1788,44 @@ int pn_t_bn_relu(const void* z_hi, const void* z_lo, long long rows, int cols, l
   return launch_emit(p, rows, cols, h_hi, h_lo, ld_h, hT_hi, hT_lo, blocksT, static_cast<cudaStream_t>(stream));
 }
 
+namespace {
+// thr = round(p * 65536) in [0, 65535], kept values scaled by 65536 / (65536 - thr)
+bool make_drop(unsigned long long seed, float p, int cols, Drop& d) {
+  if (!(p >= 0.f) || !(p < 1.f)) return false;
+  long t = lrintf(p * 65536.f);
+  if (t > 65535) t = 65535;
+  d.seed = seed;
+  d.thr = (unsigned)t;
+  d.scale = 65536.f / (float)(65536 - t);
+  d.groups = (cols + 7) / 8;
+  return true;
+}
+}  // namespace
+
+int pn_t_dropout_planes(const void* x_hi, const void* x_lo, long long rows, int cols, long long ld_x,
+                        unsigned long long seed, float p, void* hi, void* lo, long long ld, void* hiT, void* loT,
+                        long long blocksT, void* stream) {
+  if (!x_hi || ld_x % 8 != 0) return fail("dropout: input planes missing or pitch not a multiple of 8");
+  if ((x_lo != nullptr) != (lo != nullptr)) return fail("dropout: input and output must carry the same planes");
+  if (x_hi == hi) return fail("dropout: in-place operation is not supported (the transposed planes are written from the same tile)");
+  Drop d;
+  if (!make_drop(seed, p, cols, d)) return fail("dropout probability %f is not in [0, 1)", (double)p);
+  DropPlanesProducer prod{static_cast<const __half*>(x_hi), static_cast<const __half*>(x_lo), rows, cols, ld_x, d};
+  return launch_emit(prod, rows, cols, hi, lo, ld, hiT, loT, blocksT, static_cast<cudaStream_t>(stream));
+}
+
+int pn_t_dropout_f32(const float* x, long long rows, int cols, long long ldx, unsigned long long seed, float p, float* out,
+                     long long ldo, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (rows <= 0 || cols <= 0 || !x || !out || ldx < cols || ldo < cols) return fail("bad input to dropout_f32");
+  Drop d;
+  if (!make_drop(seed, p, cols, d)) return fail("dropout probability %f is not in [0, 1)", (double)p);
+  dropout_f32_kernel<<<ew_grid(rows * d.groups), 256, 0, stream>>>(x, rows, cols, ldx, d, out, ldo);
+  g_launches++;
+  PN_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int pn_t_bn_relu_dot(const void* z_hi, const void* z_lo, long long rows, int cols, long long ld_z, const float* state,
                      const float* w, const float* b, float* out, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);

@@ -251,6 +251,86 @@ struct PairHiddenProducer {     // relu((a[b] + c[l]) * scale + shift), row r = 
   }
 };
 
+// ------------------------------------------------------------------------------------------------
+// Dropout inside W_p / W_l / output_layer (OUTPUT_MLP_DROPOUT, ProtNote.py:70,80,101 -> torchvision MLP / get_mlp :369-371).
+// The keep mask is a pure function of (seed, row, column): a counter-based generator (splitmix64 finaliser over the
+// counter of an 8-column group, 16 random bits per element), so forward and backward regenerate the same mask from 20 bytes
+// of state and nothing is stored.  keep <=> bits >= thr, thr = round(p * 65536); kept values are scaled by
+// 65536 / (65536 - thr) (the inverse of the quantised keep probability, so the expectation is exact).
+// ------------------------------------------------------------------------------------------------
+struct Drop {
+  unsigned long long seed;
+  unsigned thr;
+  float scale;
+  int groups;            // ceil(cols / 8): 8-column groups per row
+};
+__host__ __device__ __forceinline__ unsigned long long drop_mix64(unsigned long long x) {
+  x ^= x >> 30;
+  x *= 0xbf58476d1ce4e5b9ULL;
+  x ^= x >> 27;
+  x *= 0x94d049bb133111ebULL;
+  x ^= x >> 31;
+  return x;
+}
+// bit j = keep element (r, c0 + j); c0 is a multiple of 8
+__device__ __forceinline__ unsigned drop_keep8(const Drop& d, long long r, int c0) {
+  const unsigned long long ctr = 2ULL * ((unsigned long long)r * (unsigned long long)d.groups + (unsigned long long)(c0 >> 3));
+  const unsigned long long u0 = drop_mix64(d.seed + (ctr + 1ULL) * 0x9e3779b97f4a7c15ULL);
+  const unsigned long long u1 = drop_mix64(d.seed + (ctr + 2ULL) * 0x9e3779b97f4a7c15ULL);
+  unsigned m = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    m |= (((unsigned)(u0 >> (16 * j)) & 0xffffu) >= d.thr ? 1u : 0u) << j;
+    m |= (((unsigned)(u1 >> (16 * j)) & 0xffffu) >= d.thr ? 1u : 0u) << (4 + j);
+  }
+  return m;
+}
+
+struct DropPlanesProducer {     // x * keep * scale, x given as planes (true value x / sc: the scale stays with the tensor)
+  const __half* xh; const __half* xl; long long rows; int cols; long long ld; Drop d;
+  struct Ctx { int unused; };
+  struct Raw { Raw8 a, b; };
+  __device__ __forceinline__ void init(int c0, Ctx& k) const { k.unused = 0; }
+  template <bool LO>
+  __device__ __forceinline__ void load(long long r, int c0, Raw& q) const {
+    if (c0 >= cols) return;
+    if (r < rows) raw_load<LO>(xh, xl, r * ld + c0, q.a);
+    if (r + 1 < rows) raw_load<LO>(xh, xl, (r + 1) * ld + c0, q.b);
+  }
+  template <bool LO>
+  __device__ __forceinline__ void eval(const Ctx& k, const Raw& q, long long r, int c0, float (&va)[8], float (&vb)[8]) const {
+    zero8(va);
+    zero8(vb);
+    if (c0 >= cols) return;
+    if (r < rows) {
+      raw_to_f32<LO>(q.a, va);
+      const unsigned m = drop_keep8(d, r, c0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) va[j] = (c0 + j < cols && ((m >> j) & 1u)) ? va[j] * d.scale : 0.f;
+    }
+    if (r + 1 < rows) {
+      raw_to_f32<LO>(q.b, vb);
+      const unsigned m = drop_keep8(d, r + 1, c0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) vb[j] = (c0 + j < cols && ((m >> j) & 1u)) ? vb[j] * d.scale : 0.f;
+    }
+  }
+};
+
+// the same mask on a small fp32 matrix (the output of a projection head, [n][latent]): one thread per 8-column group
+__global__ void dropout_f32_kernel(const float* __restrict__ x, long long rows, int cols, long long ldx, Drop d,
+                                   float* __restrict__ out, long long ldo) {
+  const long long total = rows * d.groups;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / d.groups;
+    const int c0 = (int)(i % d.groups) * 8;
+    const unsigned m = drop_keep8(d, r, c0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (c0 + j < cols) out[r * ldo + c0 + j] = ((m >> j) & 1u) ? x[r * ldx + c0 + j] * d.scale : 0.f;
+  }
+}
+
 // Sources of the BatchNorm+ReLU backward.  kind 0: g planes, z planes.  kind 1: g = g_logit[r] * w[n] (the gradient of
 // the final Linear(H -> 1), never materialised), z planes.  kind 2: g planes, z = a[r / L] + c[r % L].
 struct BwdSrc {

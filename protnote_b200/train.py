@@ -36,6 +36,7 @@ class Comm:
         self.dist = dist
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
 
     def sum_(self, t: torch.Tensor):
         if self.world > 1:
@@ -64,6 +65,7 @@ class Comm:
 
 class _NoComm:
     world = 1
+    rank = 0
 
     def sum_(self, t):
         return t
@@ -111,54 +113,91 @@ def input_dropout(seq: nn.Module) -> float:
     return _unwrap(seq)[1]
 
 
-def _split_sequential(seq: nn.Module) -> List[Tuple[nn.Linear, Optional[nn.BatchNorm1d]]]:
-    """[(Linear, BatchNorm1d or None)] of a torchvision-MLP-shaped Sequential (ProtNote.py:63-81,337-378).
-    Dropout layers INSIDE the MLP (OUTPUT_MLP_DROPOUT) must be inactive (p == 0): the reference's default
-    (base_config.yaml:39).  The input dropout of a Sequential(Dropout, MLP) wrapper is applied by forward_train."""
+def _split_sequential(seq: nn.Module) -> List[Tuple[nn.Linear, Optional[nn.BatchNorm1d], float]]:
+    """[(Linear, BatchNorm1d or None, p)] of a torchvision-MLP-shaped Sequential (ProtNote.py:63-81,337-378); p is the
+    probability of the Dropout module that follows the layer (after its BatchNorm / ReLU; after the bare Linear at the end of
+    a projection head) - OUTPUT_MLP_DROPOUT, 0 by default (base_config.yaml:39).  The input dropout of a
+    Sequential(Dropout, MLP) wrapper is not part of this list (forward_train applies it)."""
     mods, _ = _unwrap(seq)
     out = []
     for i, m in enumerate(mods):
         if isinstance(m, nn.Dropout) and m.p > 0:
-            raise NotImplementedError("OUTPUT_MLP_DROPOUT > 0 (dropout inside W_p / W_l / output_layer) is not implemented "
-                                      "on the sm_100a training path")
+            if not out:
+                raise NotImplementedError("a Dropout in front of the first Linear (get_mlp's input_dropout) is not implemented "
+                                          "on the sm_100a training path; the reference never sets it (ProtNote.py:94-102)")
+            out[-1] = (out[-1][0], out[-1][1], float(m.p))
         if isinstance(m, nn.Linear):
             bn = mods[i + 1] if i + 1 < len(mods) and isinstance(mods[i + 1], nn.BatchNorm1d) else None
-            out.append((m, bn))
+            out.append((m, bn, 0.0))
     return out
+
+
+_SITE_STRIDE = 0xD1B54A32D192ED03
+_RANK_STRIDE = 0x9E3779B97F4A7C15
+_U64 = (1 << 64) - 1
+
+
+def dropout_plan(wp, wl, mods, base_seed: int, rank: int = 0):
+    """{site: (seed, p)} for every active Dropout inside W_p ('p', i), W_l ('l', i) and output_layer ('o', j).  The mask of a
+    site is a pure function of (seed, row, column) (pn_t_dropout_planes): one seed per site from the step's base seed.
+    Sites whose rows are this rank's label rows or pairs get a rank-dependent seed; W_p's rows (all B proteins) are
+    replicated on every rank and must see the same mask everywhere."""
+    plan = {}
+    for tag, layers, off, salted in (("p", wp, 0, False), ("l", wl, 1000, True), ("o", mods, 2000, True)):
+        for i, (_, _, p) in enumerate(layers):
+            if p > 0:
+                seed = base_seed + (off + i + 1) * _SITE_STRIDE + (rank * _RANK_STRIDE if salted else 0)
+                plan[(tag, i)] = (seed & _U64, float(p))
+    return plan
 
 
 # --------------------------------------------------------------------------------------------------------------------
 # projection heads W_p / W_l  (ProtNote.py:63-81):  [Linear(no bias), BN, ReLU] x (n-1), Linear(no bias)
 # --------------------------------------------------------------------------------------------------------------------
-def head_forward(ops, comm, x_f32, layers, rows_total: int, sharded: bool, update_running: bool):
-    if rows_total <= 1 and any(bn is not None for _, bn in layers):
+def head_forward(ops, comm, x_f32, layers, rows_total: int, sharded: bool, update_running: bool, drops=None):
+    """drops: {layer index: (seed, p)} of the Dropout modules inside the head (after ReLU of a hidden layer, after the
+    final Linear: torchvision MLP order, ProtNote.py:63-81)."""
+    drops = drops or {}
+    if rows_total <= 1 and any(bn is not None for _, bn, _ in layers):
         # same error as torch.nn.BatchNorm1d in training mode, which the reference module raises here
         raise ValueError(f"Expected more than 1 value per channel when training, got input size {tuple(x_f32.shape)}")
     x = ops.split(x_f32, want_T=True)
     saved, out = [], None
-    for lin, bn in layers:
+    for i, (lin, bn, _) in enumerate(layers):
         if lin.bias is not None:
             raise NotImplementedError("projection heads are bias-free in the reference (ProtNote.py:67,77)")
         W = ops.pack(lin.weight)
+        drop = drops.get(i)
         if bn is None:
             out = ops.linear(x, W, out_f32=True)
-            saved.append((x, None, None, lin, None))
+            if drop:
+                out = ops.dropout_f32(out, drop)
+            saved.append((x, None, None, lin, None, drop))
         else:
             z = ops.linear(x, W, out_f32=False)
             stats = ops.col_stats(z)
             if sharded:
                 comm.sum_(stats)
             st = ops.bn_finalize(stats, rows_total, bn, update_running)
-            saved.append((x, z, st, lin, bn))
-            x = ops.bn_relu(z, st, want_T=True)
+            saved.append((x, z, st, lin, bn, drop))
+            x = _relu_dropout(ops, ops.bn_relu(z, st, want_T=not drop), drop)
     return out, saved
 
 
+def _relu_dropout(ops, h, drop):
+    """Dropout after a hidden layer's ReLU: the masked / rescaled copy (with the transposed planes the next wgrad reads)."""
+    return ops.dropout(h, drop, want_T=True) if drop else h
+
+
 def head_backward(ops, comm, g_f32, saved, rows_total: int, sharded: bool, grads: Dict):
+    if saved and saved[-1][5]:                   # Dropout after the head's last Linear: same mask on the incoming gradient
+        g_f32 = ops.dropout_f32(g_f32, saved[-1][5])
     g = ops.split(g_f32, want_T=True, autoscale=True)
     for idx in range(len(saved) - 1, -1, -1):
-        x, z, st, lin, bn = saved.pop()          # consumed: activations are released layer by layer
-        if st is not None:                       # g is the gradient w.r.t. the ReLU output of this layer
+        x, z, st, lin, bn, drop = saved.pop()    # consumed: activations are released layer by layer
+        if st is not None:                       # g is the gradient w.r.t. this layer's output (after ReLU and Dropout)
+            if drop:
+                g = ops.dropout(g, drop)
             s = ops.bwd_stats(g, z, st)
             grads[bn.weight], grads[bn.bias] = ops.bn_param_grads(s)        # this rank's rows only (before the sum)
             if sharded:
@@ -199,11 +238,17 @@ def _layer_state(ops, comm, z, lin, bn, count, sharded, update_running):
 
 
 def pairs_forward(ops, comm, P_e, L_e, hidden, final: nn.Linear, L_total: int, sharded: bool, update_running: bool,
-                  loss: Optional[LossSpec] = None, targets=None, fusion: str = "concatenation"):
+                  loss: Optional[LossSpec] = None, targets=None, fusion: str = "concatenation", drops=None):
+    """drops: {hidden layer index: (seed, p)} of the Dropout modules get_mlp puts after every ReLU but the last
+    (ProtNote.py:369-371)."""
+    drops = drops or {}
     B, d = P_e.shape
     if len(hidden) < 2:
         raise NotImplementedError("the training path needs OUTPUT_MLP_NUM_LAYERS >= 2 (base_config.yaml:35 has 3)")
-    lin1, bn1 = hidden[0]
+    lin1, bn1 = hidden[0][0], hidden[0][1]
+    if drops.get(len(hidden) - 1):
+        raise NotImplementedError("a Dropout between the last hidden layer and the output neuron is not implemented "
+                                  "(get_mlp has none there, ProtNote.py:369-371)")
     W1p, W1l = layer1_factors(lin1, d, fusion)
     pe = ops.split(P_e, want_T=True)
     le = ops.split(L_e, want_T=True)
@@ -217,17 +262,17 @@ def pairs_forward(ops, comm, P_e, L_e, hidden, final: nn.Linear, L_total: int, s
         if sharded:
             comm.sum_(sc)
         st1 = ops.bn_finalize_pair(sa, B, sc, L_total, bn1, update_running)
-    h = ops.pair_hidden(a, c, st1, want_T=True)                             # [B * L_local, H]
-    ctx = {"pe": pe, "le": le, "a": a, "c": c, "st1": st1, "layers": [], "B": B, "d": d, "hidden": hidden,
+    h = _relu_dropout(ops, ops.pair_hidden(a, c, st1, want_T=not drops.get(0)), drops.get(0))   # [B * L_local, H]
+    ctx = {"drops": drops, "pe": pe, "le": le, "a": a, "c": c, "st1": st1, "layers": [], "B": B, "d": d, "hidden": hidden,
            "final": final, "count": B * L_total, "fusion": fusion, "W1p": W1p, "W1l": W1l}
     logits = None
     for j in range(1, len(hidden)):
-        lin, bn = hidden[j]
+        lin, bn = hidden[j][0], hidden[j][1]
         z = ops.linear(h, ops.pack(lin.weight), out_f32=False)
         st = _layer_state(ops, comm, z, lin, bn, B * L_total, sharded, update_running)
         ctx["layers"].append((h, z, st, lin, bn))
         if j + 1 < len(hidden):
-            h = ops.bn_relu(z, st, want_T=True)
+            h = _relu_dropout(ops, ops.bn_relu(z, st, want_T=not drops.get(j)), drops.get(j))
         elif loss is None:                                                  # the last hidden layer is never stored:
             logits = ops.bn_relu_dot(z, st, final.weight, final.bias)       # relu(BN(z)) . w_out + b_out per pair
         else:                                                               # ... and the loss + its gradient seed are fused in
@@ -276,7 +321,7 @@ def _affine_grads(ops, comm, s, lin, bn, sharded: bool, grads: Dict):
 
 def pairs_backward(ops, comm, ctx, g_logit, sharded: bool, grads: Dict):
     hidden, final, count = ctx["hidden"], ctx["final"], ctx["count"]
-    layers = ctx["layers"]
+    layers, drops = ctx["layers"], ctx["drops"]
     # ---- last hidden layer: the incoming gradient is the outer product g_logit (x) w_out, generated on the fly
     h_prev, z, st, lin, bn = layers.pop()        # consumed: activations are released layer by layer
     go = ops.outer(g_logit, final.weight)
@@ -290,6 +335,8 @@ def pairs_backward(ops, comm, ctx, g_logit, sharded: bool, grads: Dict):
     # ---- middle layers
     while layers:
         h_prev, z, st, lin, bn = layers.pop()
+        if drops.get(len(layers) + 1):           # g is the gradient w.r.t. the dropped output of hidden layer len(layers) + 1
+            g = ops.dropout(g, drops[len(layers) + 1])
         s = ops.bwd_stats(g, z, st)
         _affine_grads(ops, comm, s, lin, bn, sharded, grads)
         g = ops.bwd_apply(g, z, st, s, count, want_T=True)
@@ -297,8 +344,10 @@ def pairs_backward(ops, comm, ctx, g_logit, sharded: bool, grads: Dict):
         del h_prev, z
         g = ops.dgrad(g, ops.pack(lin.weight, transposed=True))
     # ---- layer 1: z1 = a[b] + c[l] is regenerated, its gradient is reduced to the two factors
-    lin1, bn1 = hidden[0]
+    lin1, bn1 = hidden[0][0], hidden[0][1]
     d = ctx["d"]
+    if drops.get(0):
+        g = ops.dropout(g, drops[0])
     zp = ops.pair_source(ctx["a"], ctx["c"])
     s = ops.bwd_stats(g, zp, ctx["st1"])
     _affine_grads(ops, comm, s, lin1, bn1, sharded, grads)
@@ -327,7 +376,7 @@ def trainable_parameters(model) -> List[nn.Parameter]:
 
 
 def forward_train(ops, comm, model, P_f, L_f, L_total: Optional[int] = None, update_running: bool = True,
-                  loss: Optional[LossSpec] = None, targets=None):
+                  loss: Optional[LossSpec] = None, targets=None, drop_seed: Optional[int] = None):
     """P_f [B, protein_dim] (all proteins), L_f [L_local, label_dim] (this rank's label rows) -> logits [B, L_local].
     With `loss` (and targets [B, L_local]) the last kernel also leaves ctx['pairs']['loss_sum'] / ['g_seed']."""
     comm = comm or _NoComm()
@@ -344,11 +393,24 @@ def forward_train(ops, comm, model, P_f, L_f, L_total: Optional[int] = None, upd
         P_f = comm.bcast_(torch.nn.functional.dropout(P_f, input_dropout(model.W_p), True).contiguous())
     if input_dropout(model.W_l) > 0:
         L_f = torch.nn.functional.dropout(L_f, input_dropout(model.W_l), True)
-    P_e, saved_p = head_forward(ops, comm, P_f, wp, B, False, update_running)
-    L_e, saved_l = head_forward(ops, comm, L_f, wl, L_total, sharded, update_running)
+    # OUTPUT_MLP_DROPOUT: one base seed per step from torch's CPU generator (so torch.manual_seed governs it), the first
+    # rank's on every rank; per-site seeds in dropout_plan
+    plan = {}
+    if any(p > 0 for _, _, p in wp + wl + mods):
+        if drop_seed is None:
+            drop_seed = int(torch.randint(0, 1 << 62, (1,), dtype=torch.int64))
+        if sharded:
+            drop_seed = int(comm.bcast_(torch.tensor([drop_seed], dtype=torch.int64, device=P_f.device)))
+        plan = dropout_plan(wp, wl, mods, drop_seed, comm.rank if sharded else 0)
+    P_e, saved_p = head_forward(ops, comm, P_f, wp, B, False, update_running,
+                                {i: v for (t, i), v in plan.items() if t == "p"})
+    L_e, saved_l = head_forward(ops, comm, L_f, wl, L_total, sharded, update_running,
+                                {i: v for (t, i), v in plan.items() if t == "l"})
     logits, pctx = pairs_forward(ops, comm, P_e, L_e, hidden, final, L_total, sharded, update_running, loss, targets,
-                                 getattr(model, "feature_fusion", "concatenation"))
-    ctx = {"saved_p": saved_p, "saved_l": saved_l, "pairs": pctx, "B": B, "L_total": L_total, "sharded": sharded}
+                                 getattr(model, "feature_fusion", "concatenation"),
+                                 {i: v for (t, i), v in plan.items() if t == "o"})
+    ctx = {"saved_p": saved_p, "saved_l": saved_l, "pairs": pctx, "B": B, "L_total": L_total, "sharded": sharded,
+           "drop_plan": plan}
     if update_running:
         for part in (model.W_p, model.W_l, model.output_layer):
             for m in part.modules():

@@ -203,6 +203,28 @@ class NativeOps:
             state[1].copy_(self._f32(bias, "bias").reshape(-1))
         return state
 
+    # ------------------------------------------------------------------ dropout inside the MLPs (OUTPUT_MLP_DROPOUT)
+    def dropout(self, x: Act, drop, want_T=False) -> Act:
+        """x * keep / (1 - p) as new planes (+ transposed planes); drop = (seed, p).  The mask depends on (seed, row, column)
+        only, so the backward calls this on the incoming gradient with the forward's seed.  The tensor's scale is kept."""
+        seed, p = drop
+        out = Act(x.rows, x.cols, x.hi.device, x.lo is not None, want_T)
+        out.sc = x.sc
+        with torch.cuda.device(x.hi.device):
+            check(self.lib.pn_t_dropout_planes(ptr(x.hi), ptr(x.lo), x.rows, x.cols, x.ld, C.c_ulonglong(seed), C.c_float(p),
+                                               ptr(out.hi), ptr(out.lo), out.ld, ptr(out.hiT), ptr(out.loT), out.ldT,
+                                               stream_ptr()))
+        return out
+
+    def dropout_f32(self, x, drop):
+        seed, p = drop
+        x = self._f32(x, "input")
+        out = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            check(self.lib.pn_t_dropout_f32(ptr(x), x.shape[0], x.shape[1], x.stride(0), C.c_ulonglong(seed), C.c_float(p),
+                                            ptr(out), out.stride(0), stream_ptr()))
+        return out
+
     def bn_relu(self, z: Act, st, want_T=False) -> Act:
         h = Act(z.rows, z.cols, z.hi.device, self.strict, want_T)
         with torch.cuda.device(z.hi.device):

@@ -68,6 +68,7 @@ def build_b200_model(ecfg, scfg, sd, device="cuda", precision="strict"):
                      label_encoder_num_trainable_layers=0, train_sequence_encoder=False,
                      sequence_embedding_dropout=scfg.sequence_embedding_dropout,
                      label_embedding_dropout=scfg.label_embedding_dropout,
+                     dropout=scfg.output_mlp_dropout,
                      feature_fusion=scfg.feature_fusion, temperature=scfg.temperature, precision=precision)
     model.load_state_dict(sd, strict=True)
     return model.to(device).eval()

@@ -356,6 +356,78 @@ def test_embedding_dropouts_on_device():
     assert torch.equal(e1, e2)
 
 
+@pytest.mark.parametrize("rows,cols,p", [(70, 40, 0.3), (257, 300, 0.1), (130, 1100, 0.5), (64, 64, 0.0)])
+def test_dropout_primitives(rows, cols, p):
+    """pn_t_dropout_planes / pn_t_dropout_f32 against their statement (oracle.train_ops.dropout_multiplier): the keep mask
+    bit for bit, the kept values rescaled, row-major and transposed planes equal, the tensor's scale carried along; the
+    same call on a gradient tensor applies the same mask (what the backward relies on)."""
+    from oracle.train_ops import dropout_multiplier
+    nat, ref = _ops("strict")
+    g = torch.Generator().manual_seed(rows + cols)
+    x = torch.randn(rows, cols, generator=g)
+    x[x.abs() < 1e-3] = 0.5                                   # no exact zeros in the input: zeros in the output are the mask
+    seed = 0x9E3779B97F4A7C15 + rows                          # > 2^63: the whole unsigned range must travel
+    mult = dropout_multiplier(seed, rows, cols, p)
+    assert abs(float((mult > 0).double().mean()) - (1 - p)) < 0.03
+    xa = nat.split(x.cuda(), want_T=False)
+    out = nat.dropout(xa, (seed, p), want_T=True)
+    got = _val(out)
+    assert torch.equal(got != 0, mult != 0)
+    assert _rel(got, x.double() * mult) < 1e-6
+    assert torch.equal(got, _valT(out))
+    ga = nat.split(x.cuda() * 1e-7, want_T=False, autoscale=True)      # a gradient-like tensor with a device scale
+    gout = nat.dropout(ga, (seed, p))
+    assert gout.sc is ga.sc and gout.hiT is None
+    assert _rel(_val(gout), x.double() * 1e-7 * mult) < 1e-6
+    f = nat.dropout_f32(x.cuda(), (seed, p)).cpu().double()
+    assert torch.equal(f != 0, mult != 0) and _rel(f, x.double() * mult) < 1e-6
+    fast, _ = _ops("fast")
+    fo = fast.dropout(fast.split(x.cuda(), want_T=False), (seed, p), want_T=True)
+    assert fo.lo is None and torch.equal(_val(fo) != 0, mult != 0) and _rel(_val(fo), x.double() * mult) < 2e-3
+
+
+@pytest.mark.parametrize("variant", ["default", "no_batchnorm"])
+def test_training_step_with_output_mlp_dropout(variant):
+    """OUTPUT_MLP_DROPOUT > 0 through the module interface: the step's base seed comes from torch's CPU generator, so the
+    test re-derives the per-site seeds (train.dropout_plan), states the masks (oracle.train_ops.dropout_multiplier) and the
+    autograd oracle multiplies with them where the reference has its nn.Dropout modules (pinned on the CPU against the
+    reference class: tests/test_train_cpu.py::test_dropout_mask_placement_is_the_reference_modules)."""
+    from oracle.train_ops import dropout_multiplier
+    from protnote_b200 import train as pn_train
+    ecfg, _, *_ = CASES["tiny_concat"]
+    scfg = _variant_cfg(output_mlp_dropout=0.3, **({"output_mlp_batchnorm": False} if variant == "no_batchnorm" else {}))
+    sd = synth_state_dict(ecfg, scfg, seed=13, calib_T=64)
+    B, L = 6, 70
+    g = torch.Generator().manual_seed(37)
+    P_f, L_f = torch.randn(B, 72, generator=g), torch.randn(L, 40, generator=g)
+    y = synth_targets(B, L, 37)
+    model = build_b200_model(ecfg, scfg, sd, device="cuda").train()
+    torch.manual_seed(91)
+    logits, _ = model(sequence_embeddings=P_f.cuda(), label_embeddings=L_f.cuda())
+    torch.nn.functional.binary_cross_entropy_with_logits(logits, y.cuda()).backward()
+    torch.manual_seed(91)
+    base = int(torch.randint(0, 1 << 62, (1,), dtype=torch.int64))
+    wp, wl = pn_train._split_sequential(model.W_p), pn_train._split_sequential(model.W_l)
+    mods = pn_train._split_sequential(model.output_layer)
+    plan = pn_train.dropout_plan(wp, wl, mods, base)
+    assert len(plan) == 4 + 4 + 2
+    rows, layers = {"p": B, "l": L, "o": B * L}, {"p": wp, "l": wl, "o": mods}
+    masks = {(t, i): dropout_multiplier(sd_, rows[t], layers[t][i][0].weight.shape[0], p) for (t, i), (sd_, p) in plan.items()}
+    o_logits, _, o_grads, o_stats = train_step_oracle(sd, P_f, L_f, y, scfg, masks=masks)
+    assert float((logits.detach().cpu().double() - o_logits).abs().max()) < 1e-4
+    assert float((train_step_oracle(sd, P_f, L_f, y, scfg)[0] - o_logits).abs().max()) > 1e-2     # dropout was active
+    _check_grads(model, o_grads, train_step_oracle(sd, P_f, L_f, y, scfg, dtype=torch.float32, masks=masks)[2])
+    bufs = dict(model.named_buffers())
+    for k, v in o_stats.items():
+        assert float((bufs[k].cpu().double() - v).abs().max()) <= 1e-5 * max(1.0, float(v.abs().max())), k
+    # eval mode: the Dropout modules are inactive, the fused inference path is unchanged by them
+    model.eval()
+    with torch.no_grad():
+        e1, _ = model(sequence_embeddings=P_f.cuda(), label_embeddings=L_f.cuda())
+        e2, _ = model(sequence_embeddings=P_f.cuda(), label_embeddings=L_f.cuda())
+    assert torch.equal(e1, e2)
+
+
 @pytest.mark.parametrize("name", ["train_tiny", "train_tiny_wide"])
 def test_training_step_matches_reference_golden(name):
     """Against tests/golden/train_*.pt: logits / loss / gradients / running statistics of the reference's own ProtNote class

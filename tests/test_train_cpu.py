@@ -147,20 +147,16 @@ def _variant_cfg(**kw):
 
 
 def test_training_path_refuses_what_it_does_not_implement():
-    """Unsupported options fail loudly (no silent fallback): dropout > 0 inside the MLPs, 'concatenation_prod' (not a sum of
-    a protein and a label term), a one-layer output MLP; and the product module itself has no CPU path in training mode."""
+    """Unsupported options fail loudly (no silent fallback): a Dropout in front of the first Linear of an MLP,
+    'concatenation_prod' (not a sum of a protein and a label term), a one-layer output MLP; and the product module itself
+    has no CPU path in training mode."""
     from protnote_b200._lib import ProtnoteB200Error
     ecfg, scfg, sd, P_f, L_f, y = _problem()
     model = build_b200_model(ecfg, scfg, sd, device="cpu").double().train()
     ops = TorchOps(torch.float64)
-    for m in model.output_layer.modules():
-        if isinstance(m, torch.nn.Dropout):
-            m.p = 0.1
+    model.output_layer = torch.nn.Sequential(torch.nn.Dropout(0.1), *list(model.output_layer))     # get_mlp(input_dropout=)
     with pytest.raises(NotImplementedError):
         pn_train.forward_train(ops, None, model, P_f.double(), L_f.double())
-    for m in model.output_layer.modules():
-        if isinstance(m, torch.nn.Dropout):
-            m.p = 0.0
     prod_cfg = _variant_cfg(feature_fusion="concatenation_prod")
     sd_prod = synth_state_dict(ecfg, prod_cfg, seed=3, calib_T=64)
     prod = build_b200_model(ecfg, prod_cfg, sd_prod, device="cpu").double().train()
@@ -225,6 +221,99 @@ def test_train_oracle_variants_match_reference(variant):
     bufs = dict(ref.named_buffers())
     for k, v in o_stats.items():
         assert (bufs[k] - v).abs().max() < 1e-10, k
+
+
+def _dropout_masks(model, P_rows, L_rows, base_seed, rank=0):
+    """The multipliers of every active Dropout inside W_p / W_l / output_layer for the step seeded with `base_seed`:
+    the plan of protnote_b200.train (site -> seed) and the statement of the device mask (oracle.train_ops)."""
+    from oracle.train_ops import dropout_multiplier
+    wp, wl = pn_train._split_sequential(model.W_p), pn_train._split_sequential(model.W_l)
+    mods = pn_train._split_sequential(model.output_layer)
+    plan = pn_train.dropout_plan(wp, wl, mods, base_seed, rank)
+    rows = {"p": P_rows, "l": L_rows, "o": P_rows * L_rows}
+    layers = {"p": wp, "l": wl, "o": mods}
+    return {(t, i): dropout_multiplier(seed, rows[t], layers[t][i][0].weight.shape[0], p) for (t, i), (seed, p) in plan.items()}
+
+
+@pytest.mark.parametrize("variant", ["default", "no_batchnorm", "two_layers"])
+def test_output_mlp_dropout_sequencing_matches_oracle(variant):
+    """OUTPUT_MLP_DROPOUT > 0 (Dropout after every hidden ReLU and after the last Linear of W_p / W_l, after every hidden
+    ReLU but the last of output_layer): the forward masks the activations, the backward the gradients, with masks that are
+    a pure function of (seed, row, column) - against the autograd oracle multiplying with the same masks."""
+    ecfg, _, *_ = CASES["tiny_concat"]
+    kw = {"default": {}, "no_batchnorm": dict(output_mlp_batchnorm=False), "two_layers": dict(output_mlp_num_layers=2)}[variant]
+    scfg = _variant_cfg(output_mlp_dropout=0.3, **kw)
+    sd = synth_state_dict(ecfg, scfg, seed=13, calib_T=64)
+    g = torch.Generator().manual_seed(19)
+    P_f, L_f = torch.randn(6, 72, generator=g), torch.randn(10, 40, generator=g)
+    y = synth_targets(6, 10, 19)
+    model = build_b200_model(ecfg, scfg, sd, device="cpu").double().train()
+    ops = TorchOps(torch.float64)
+    logits, ctx = pn_train.forward_train(ops, None, model, P_f.double(), L_f.double(), drop_seed=987654321)
+    masks = _dropout_masks(model, 6, 10, 987654321)
+    n_hidden = scfg.output_mlp_num_layers
+    assert set(masks) == ({("p", i) for i in range(4)} | {("l", i) for i in range(4)} | {("o", j) for j in range(n_hidden - 1)})
+    o_logits, _, o_grads, o_stats = train_step_oracle(sd, P_f, L_f, y, scfg, masks=masks)
+    assert (logits - o_logits).abs().max() < 1e-9
+    plain, *_ = train_step_oracle(sd, P_f, L_f, y, scfg)
+    assert (plain - o_logits).abs().max() > 1e-2                      # the masks really changed the step
+    grads = pn_train.backward_train(ops, None, ctx, (torch.sigmoid(logits) - y.double()) / logits.numel())
+    named = dict(model.named_parameters())
+    for k, gr in o_grads.items():
+        assert (grads[named[k]] - gr).abs().max() <= 1e-9 * max(1.0, float(gr.abs().max())), k
+    bufs = dict(model.named_buffers())
+    for k, v in o_stats.items():
+        assert (bufs[k] - v).abs().max() < 1e-9, k
+    # the base seed comes from torch's CPU generator when it is not given: same torch seed, same step
+    torch.manual_seed(5)
+    a, _ = pn_train.forward_train(ops, None, model, P_f.double(), L_f.double(), update_running=False)
+    torch.manual_seed(5)
+    b, _ = pn_train.forward_train(ops, None, model, P_f.double(), L_f.double(), update_running=False)
+    c, _ = pn_train.forward_train(ops, None, model, P_f.double(), L_f.double(), update_running=False)
+    assert torch.equal(a, b) and not torch.equal(a, c)
+
+
+@pytest.mark.skipif(not reference_available(), reason="needs /root/reference (build container only)")
+def test_dropout_mask_placement_is_the_reference_modules():
+    """The oracle multiplies where the reference has its nn.Dropout modules: replace every Dropout of the reference
+    class's W_p / W_l / output_layer (in module order) by a fixed multiplier and compare logits and gradients."""
+    from oracle.make_golden import build_reference_model
+    from oracle.train_ops import dropout_multiplier
+
+    class Mul(torch.nn.Module):
+        def __init__(self, m):
+            super().__init__()
+            self.m = m
+
+        def forward(self, x):
+            return x * self.m
+
+    ecfg, _, *_ = CASES["tiny_concat"]
+    scfg = _variant_cfg(output_mlp_dropout=0.25)
+    sd = synth_state_dict(ecfg, scfg, seed=13, calib_T=64)
+    g = torch.Generator().manual_seed(19)
+    P_f, L_f = torch.randn(5, 72, generator=g), torch.randn(7, 40, generator=g)
+    y = synth_targets(5, 7, 19)
+    ref = build_reference_model(ecfg, scfg, sd).double().train()
+    masks, seed = {}, 100
+    for tag, part, rows in (("p", ref.W_p, 5), ("l", ref.W_l, 7), ("o", ref.output_layer, 35)):
+        mods, layer, width = list(part), -1, None
+        for i, m in enumerate(mods):
+            if isinstance(m, torch.nn.Linear):
+                layer, width = layer + 1, m.out_features
+            if isinstance(m, torch.nn.Dropout):
+                assert m.p == 0.25
+                seed += 1
+                masks[(tag, layer)] = dropout_multiplier(seed, rows, width, 0.25)
+                part[i] = Mul(masks[(tag, layer)])
+    assert len(masks) == 4 + 4 + 2
+    logits, _ = ref(sequence_embeddings=P_f.double(), label_embeddings=L_f.double())
+    torch.nn.functional.binary_cross_entropy_with_logits(logits, y.double()).backward()
+    o_logits, _, o_grads, _ = train_step_oracle(sd, P_f, L_f, y, scfg, masks=masks)
+    assert (logits.detach() - o_logits).abs().max() < 1e-10
+    named = dict(ref.named_parameters())
+    for k, gr in o_grads.items():
+        assert (named[k].grad - gr).abs().max() <= 1e-10 * max(1.0, float(gr.abs().max())), k
 
 
 @pytest.mark.skipif(not reference_available(), reason="needs /root/reference (build container only)")
