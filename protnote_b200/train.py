@@ -243,8 +243,6 @@ def pairs_forward(ops, comm, P_e, L_e, hidden, final: nn.Linear, L_total: int, s
     (ProtNote.py:369-371)."""
     drops = drops or {}
     B, d = P_e.shape
-    if len(hidden) < 2:
-        raise NotImplementedError("the training path needs OUTPUT_MLP_NUM_LAYERS >= 2 (base_config.yaml:35 has 3)")
     lin1, bn1 = hidden[0][0], hidden[0][1]
     if drops.get(len(hidden) - 1):
         raise NotImplementedError("a Dropout between the last hidden layer and the output neuron is not implemented "
@@ -262,10 +260,22 @@ def pairs_forward(ops, comm, P_e, L_e, hidden, final: nn.Linear, L_total: int, s
         if sharded:
             comm.sum_(sc)
         st1 = ops.bn_finalize_pair(sa, B, sc, L_total, bn1, update_running)
-    h = _relu_dropout(ops, ops.pair_hidden(a, c, st1, want_T=not drops.get(0)), drops.get(0))   # [B * L_local, H]
+    h = ops.pair_hidden(a, c, st1, want_T=len(hidden) > 1 and not drops.get(0))                 # [B * L_local, H]
+    h = _relu_dropout(ops, h, drops.get(0))
     ctx = {"drops": drops, "pe": pe, "le": le, "a": a, "c": c, "st1": st1, "layers": [], "B": B, "d": d, "hidden": hidden,
            "final": final, "count": B * L_total, "fusion": fusion, "W1p": W1p, "W1l": W1l}
     logits = None
+    if len(hidden) == 1:
+        # OUTPUT_MLP_NUM_LAYERS 1: the output neuron follows layer 1 directly.  h1 >= 0, so relu(h1 * 1 + 0) = h1 and the
+        # dot kernel of the last hidden layer applies to the h1 planes with the identity state
+        ident = ops.affine_state(None, lin1.weight.shape[0], lin1.weight.device)
+        ctx["one_layer"] = (h, ident)
+        if loss is None:
+            logits = ops.bn_relu_dot(h, ident, final.weight, final.bias)
+        else:
+            loss.grad_scale = 1.0 / float(B * L_total) if loss.reduction == "mean" else 1.0
+            logits, ctx["g_seed"], ctx["loss_sum"] = ops.bn_relu_dot_loss(h, ident, final.weight, final.bias, targets,
+                                                                          L_e.shape[0], loss)
     for j in range(1, len(hidden)):
         lin, bn = hidden[j][0], hidden[j][1]
         z = ops.linear(h, ops.pack(lin.weight), out_f32=False)
@@ -323,15 +333,25 @@ def pairs_backward(ops, comm, ctx, g_logit, sharded: bool, grads: Dict):
     hidden, final, count = ctx["hidden"], ctx["final"], ctx["count"]
     layers, drops = ctx["layers"], ctx["drops"]
     # ---- last hidden layer: the incoming gradient is the outer product g_logit (x) w_out, generated on the fly
-    h_prev, z, st, lin, bn = layers.pop()        # consumed: activations are released layer by layer
     go = ops.outer(g_logit, final.weight)
-    s = ops.bwd_stats(go, z, st)
-    grads[final.weight], grads[final.bias] = ops.final_param_grads(s)
-    _affine_grads(ops, comm, s, lin, bn, sharded, grads)
-    g = ops.bwd_apply(go, z, st, s, count, want_T=True)
-    grads[lin.weight] = ops.wgrad(g, h_prev)
-    del h_prev, z
-    g = ops.dgrad(g, ops.pack(lin.weight, transposed=True))
+    if "one_layer" in ctx:
+        # the same pass over the h1 planes with the identity state: d w_out = sum g_logit * h1, d b_out, and the gradient
+        # w.r.t. h1 - masked where h1 = 0, which is the mask layer 1's own backward applies to it anyway
+        h, ident = ctx.pop("one_layer")
+        s = ops.bwd_stats(go, h, ident)
+        grads[final.weight], grads[final.bias] = ops.final_param_grads(s)
+        s.sums.zero_()
+        g = ops.bwd_apply(go, h, ident, s, count)
+        del h
+    else:
+        h_prev, z, st, lin, bn = layers.pop()    # consumed: activations are released layer by layer
+        s = ops.bwd_stats(go, z, st)
+        grads[final.weight], grads[final.bias] = ops.final_param_grads(s)
+        _affine_grads(ops, comm, s, lin, bn, sharded, grads)
+        g = ops.bwd_apply(go, z, st, s, count, want_T=True)
+        grads[lin.weight] = ops.wgrad(g, h_prev)
+        del h_prev, z
+        g = ops.dgrad(g, ops.pack(lin.weight, transposed=True))
     # ---- middle layers
     while layers:
         h_prev, z, st, lin, bn = layers.pop()

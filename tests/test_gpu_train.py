@@ -276,7 +276,10 @@ def test_two_layer_output_mlp_and_optimizer_step():
 VARIANTS = {"no_batchnorm": dict(output_mlp_batchnorm=False),
             "diff": dict(feature_fusion="concatenation_diff"),
             "diff_no_batchnorm": dict(feature_fusion="concatenation_diff", output_mlp_batchnorm=False),
-            "two_layers_no_batchnorm": dict(output_mlp_num_layers=2, output_mlp_batchnorm=False)}
+            "two_layers_no_batchnorm": dict(output_mlp_num_layers=2, output_mlp_batchnorm=False),
+            "one_layer": dict(output_mlp_num_layers=1),
+            "one_layer_diff_no_batchnorm": dict(output_mlp_num_layers=1, output_mlp_batchnorm=False,
+                                                feature_fusion="concatenation_diff")}
 
 
 def _variant_cfg(**kw):

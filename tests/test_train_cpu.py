@@ -148,8 +148,8 @@ def _variant_cfg(**kw):
 
 def test_training_path_refuses_what_it_does_not_implement():
     """Unsupported options fail loudly (no silent fallback): a Dropout in front of the first Linear of an MLP,
-    'concatenation_prod' (not a sum of a protein and a label term), a one-layer output MLP; and the product module itself
-    has no CPU path in training mode."""
+    'concatenation_prod' (not a sum of a protein and a label term); and the product module itself has no CPU path in
+    training mode."""
     from protnote_b200._lib import ProtnoteB200Error
     ecfg, scfg, sd, P_f, L_f, y = _problem()
     model = build_b200_model(ecfg, scfg, sd, device="cpu").double().train()
@@ -162,10 +162,6 @@ def test_training_path_refuses_what_it_does_not_implement():
     prod = build_b200_model(ecfg, prod_cfg, sd_prod, device="cpu").double().train()
     with pytest.raises(NotImplementedError):
         pn_train.forward_train(ops, None, prod, P_f.double(), L_f.double())
-    one_cfg = _variant_cfg(output_mlp_num_layers=1)
-    one = build_b200_model(ecfg, one_cfg, synth_state_dict(ecfg, one_cfg, seed=4, calib_T=64), device="cpu").double().train()
-    with pytest.raises(NotImplementedError):
-        pn_train.forward_train(ops, None, one, P_f.double(), L_f.double())
     # the product module: CPU tensors in training mode -> error, never a torch fallback
     cpu_model = build_b200_model(ecfg, scfg, sd, device="cpu").train()
     with pytest.raises(ProtnoteB200Error):
@@ -177,7 +173,10 @@ def test_training_path_refuses_what_it_does_not_implement():
 VARIANTS = {"no_batchnorm": dict(output_mlp_batchnorm=False),
             "diff": dict(feature_fusion="concatenation_diff"),
             "diff_no_batchnorm": dict(feature_fusion="concatenation_diff", output_mlp_batchnorm=False),
-            "two_layers_no_batchnorm": dict(output_mlp_num_layers=2, output_mlp_batchnorm=False)}
+            "two_layers_no_batchnorm": dict(output_mlp_num_layers=2, output_mlp_batchnorm=False),
+            "one_layer": dict(output_mlp_num_layers=1),
+            "one_layer_diff_no_batchnorm": dict(output_mlp_num_layers=1, output_mlp_batchnorm=False,
+                                                feature_fusion="concatenation_diff")}
 
 
 @pytest.mark.parametrize("variant", sorted(VARIANTS))
@@ -193,8 +192,9 @@ def test_sequencing_matches_oracle_variants(variant):
     P_f, L_f = torch.randn(5, 72, generator=g), torch.randn(9, 40, generator=g)
     _ours_vs_oracle(scfg, ecfg, sd, P_f, L_f, synth_targets(5, 9, 17), 1e-9)
     if not scfg.output_mlp_batchnorm:       # the hidden biases are parameters of this variant: they must have been checked
-        assert any(k.startswith("output_layer.") and k.endswith(".bias") and k != "output_layer.6.bias"
-                   for k in train_step_oracle(sd, P_f, L_f, synth_targets(5, 9, 17), scfg)[2])
+        hidden_biases = [k for k in train_step_oracle(sd, P_f, L_f, synth_targets(5, 9, 17), scfg)[2]
+                         if k.startswith("output_layer.") and k.endswith(".bias")]
+        assert len(hidden_biases) == scfg.output_mlp_num_layers + 1
 
 
 @pytest.mark.skipif(not reference_available(), reason="needs /root/reference (build container only)")
