@@ -26,8 +26,10 @@ def _free_port():
 
 def _problem(variant=False):
     ecfg, scfg, *_ = CASES["tiny_concat"]
-    if variant:      # output MLP without BatchNorm (hidden biases, nothing to all-reduce in its backward) on [p; t; p - t]
-        import dataclasses
+    import dataclasses
+    if variant == "dropout":     # OUTPUT_MLP_DROPOUT: one base seed for all ranks, rank-salted masks on the sharded rows
+        scfg = dataclasses.replace(scfg, output_mlp_dropout=0.3)
+    elif variant:    # output MLP without BatchNorm (hidden biases, nothing to all-reduce in its backward) on [p; t; p - t]
         scfg = dataclasses.replace(scfg, output_mlp_batchnorm=False, feature_fusion="concatenation_diff")
     sd = synth_state_dict(ecfg, scfg, seed=42, calib_T=64)
     g = torch.Generator().manual_seed(21)
@@ -45,6 +47,8 @@ def _worker(rank, world, port, q, fused=False, variant=False):
         model = build_b200_model(ecfg, scfg, sd, device="cpu").double().train()
         comm = pn_train.Comm()
         ls, le = label_row_bounds(L_f.shape[0], 1, rank, world)
+        if variant == "dropout":
+            torch.manual_seed(1000 + rank)       # ranks seeded differently, as ProtNoteTrainer's seed_everything(seed + rank)
         if fused:
             # loss fused into the last forward primitive (focal, the reference's default LOSS_FN) and the parameter
             # gradients all-reduced inside the backward, overlapped with it: no allreduce_gradients call
@@ -79,8 +83,38 @@ def _worker(rank, world, port, q, fused=False, variant=False):
 import pytest  # noqa: E402
 
 
-@pytest.mark.parametrize("fused,variant", [(False, False), (True, False), (True, True)],
-                         ids=["bce_via_autograd", "fused_focal_overlapped_allreduce", "fused_focal_diff_no_batchnorm"])
+def _sharded_masks(ecfg, scfg, sd, B, L, world):
+    """The masks of the label-sharded step as one set of global multipliers: the base seed is rank 0's first CPU draw
+    after torch.manual_seed(1000) (broadcast to all ranks); W_p's sites are the same on every rank, W_l's and the output
+    MLP's are each rank's own rows (rank-salted seeds, local row indices) and are stitched together along the label axis."""
+    from oracle.train_ops import dropout_multiplier
+    torch.manual_seed(1000)
+    base = int(torch.randint(0, 1 << 62, (1,), dtype=torch.int64))
+    model = build_b200_model(ecfg, scfg, sd, device="cpu")
+    wp, wl = pn_train._split_sequential(model.W_p), pn_train._split_sequential(model.W_l)
+    mods = pn_train._split_sequential(model.output_layer)
+    layers = {"p": wp, "l": wl, "o": mods}
+    masks = {}
+    plans = [pn_train.dropout_plan(wp, wl, mods, base, r) for r in range(world)]
+    bounds = [label_row_bounds(L, 1, r, world) for r in range(world)]
+    for (t, i), (seed0, p) in plans[0].items():
+        width = layers[t][i][0].weight.shape[0]
+        if t == "p":
+            assert all(pl[(t, i)][0] == seed0 for pl in plans)
+            masks[(t, i)] = dropout_multiplier(seed0, B, width, p)
+        elif t == "l":
+            assert len({pl[(t, i)][0] for pl in plans}) == world
+            masks[(t, i)] = torch.cat([dropout_multiplier(pl[(t, i)][0], le - ls, width, p)
+                                       for pl, (ls, le) in zip(plans, bounds)])
+        else:
+            masks[(t, i)] = torch.cat([dropout_multiplier(pl[(t, i)][0], B * (le - ls), width, p).reshape(B, le - ls, width)
+                                       for pl, (ls, le) in zip(plans, bounds)], dim=1).reshape(B * L, width)
+    return masks
+
+
+@pytest.mark.parametrize("fused,variant", [(False, False), (True, False), (True, True), (True, "dropout")],
+                         ids=["bce_via_autograd", "fused_focal_overlapped_allreduce", "fused_focal_diff_no_batchnorm",
+                              "fused_focal_output_mlp_dropout"])
 def test_label_sharded_training_step_equals_single_process(fused, variant):
     world = 2
     ctx = mp.get_context("spawn")
@@ -101,6 +135,8 @@ def test_label_sharded_training_step_equals_single_process(fused, variant):
     logits0 = torch.from_numpy(logits0)
     ecfg, scfg, sd, P_f, L_f, y = _problem(variant)
     kw = dict(loss="focal", gamma=2.0, alpha=0.25) if fused else {}
+    if variant == "dropout":
+        kw["masks"] = _sharded_masks(ecfg, scfg, sd, P_f.shape[0], L_f.shape[0], world)
     o_logits, o_loss, o_grads, o_stats = train_step_oracle(sd, P_f, L_f, y, scfg, **kw)
     ls, le = label_row_bounds(L_f.shape[0], 1, 0, world)
     assert (logits0 - o_logits[:, ls:le]).abs().max() < 1e-9
