@@ -325,6 +325,19 @@ int pn_t_pair_hidden(const float* a, long long B, const float* c, long long L, i
 
 /* Source of a BatchNorm+ReLU backward.  kind 0: g planes, z planes.  kind 1: g = g_logit[r] * w[n] (gradient of the final
  * Linear(H -> 1), generated on the fly), z planes.  kind 2: g planes, z[r] = a[r / L] + c[r % L] (layer 1). */
+/* FEATURE_FUSION concatenation_prod in training (ProtNote.py:140-150): the product block of layer 1 is a real GEMM.
+ *   pn_t_pair_product   q[b*L + l] = p[b] (.) t[l]   (p [B][d], t [L][d] fp32) as planes (+ K-blocked transposed planes)
+ *   pn_t_pair_add       z1[b*L + l] = x[b*L + l] + a[b] + c[l]   (x planes [B*L][H], a [B][H], c [L][H] fp32) as planes
+ *   pn_t_pair_marginals out_b[b] = (1/g_sc) sum_l G[b*L + l] (.) wl[l],  out_l[l] = (1/g_sc) sum_b G[b*L + l] (.) wb[b]
+ *                       (G planes [B*L][cols] carrying the device scale g_sc, nullable; wl [L][cols] / wb [B][cols] fp32,
+ *                       null = ones; either output nullable): the two marginals of a pair-grid gradient. */
+int pn_t_pair_product(const float* p, long long B, const float* t, long long L, int d, void* hi, void* lo, long long ld,
+                      void* hiT, void* loT, long long blocksT, void* stream);
+int pn_t_pair_add(const void* x_hi, const void* x_lo, long long ld_x, const float* a, long long B, const float* c,
+                  long long L, int H, void* hi, void* lo, long long ld, void* stream);
+int pn_t_pair_marginals(const void* g_hi, const void* g_lo, long long ld_g, const float* g_sc, long long B, long long L,
+                        int cols, const float* wb, const float* wl, float* out_b, float* out_l, void* stream);
+
 typedef struct pn_bwd_src {
   int kind;
   long long rows;

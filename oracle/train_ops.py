@@ -118,13 +118,34 @@ class TorchOps:
         return TPacked(W.t().contiguous() if transposed else W.contiguous())
 
     # ------------------------------------------------------------------ GEMMs
-    def linear(self, x: TAct, W: TPacked, out_f32=False):
+    def linear(self, x: TAct, W: TPacked, out_f32=False, accumulate_into=None):
         y = (x.val / x.sc) @ W.w.t()
+        if accumulate_into is not None:
+            accumulate_into += y.to(accumulate_into.dtype)
+            return accumulate_into
         return y if out_f32 else TAct(y, 1.0, False)
 
-    def dgrad(self, g: TAct, WT: TPacked, out_f32=False):
+    def dgrad(self, g: TAct, WT: TPacked, out_f32=False, accumulate_into=None):
         y = (g.val / g.sc) @ WT.w.t()
+        if accumulate_into is not None:
+            accumulate_into += y.to(accumulate_into.dtype)
+            return accumulate_into
         return y if out_f32 else TAct(y * g.sc, g.sc, False)
+
+    # ------------------------------------------------------------------ FEATURE_FUSION concatenation_prod
+    def pair_product(self, P_e, L_e, want_T=False):
+        P_e, L_e = P_e.detach().to(self.dtype), L_e.detach().to(self.dtype)
+        return TAct((P_e[:, None, :] * L_e[None, :, :]).reshape(-1, P_e.shape[1]), 1.0, want_T)
+
+    def pair_add(self, x: TAct, a, c):
+        z = (a.to(self.dtype)[:, None, :] + c.to(self.dtype)[None, :, :]).reshape(-1, a.shape[1])
+        return TAct(x.val / x.sc + z, 1.0, False)
+
+    def pair_marginals(self, g: TAct, B, L, wb=None, wl=None):
+        G = (g.val / g.sc).reshape(B, L, -1)
+        gb = G if wl is None else G * wl.detach().to(self.dtype)[None, :, :]
+        gl = G if wb is None else G * wb.detach().to(self.dtype)[:, None, :]
+        return gb.sum(1), gl.sum(0)
 
     def wgrad(self, g: TAct, x: TAct, out=None):
         assert g.has_T and x.has_T, "wgrad contracts over rows: both operands need their transposed planes"

@@ -275,9 +275,9 @@ class ProtNote(nn.Module):
             raise ValueError("Incompatible label parameters passed to forward method.")
         if self.label_embedding_pooling_method == "all":
             raise ProtnoteB200Error("LABEL_EMBEDDING_POOLING_METHOD 'all' is not on the cached-embedding path")
-        if self.feature_fusion not in ("concatenation", "concatenation_diff"):
-            raise ProtnoteB200Error("the training path implements FEATURE_FUSION 'concatenation' (base_config.yaml:44) and "
-                                    "'concatenation_diff' (both are sums of a protein term and a label term in layer 1)")
+        if not self.feature_fusion.startswith("concatenation"):
+            raise ProtnoteB200Error("the training path implements FEATURE_FUSION 'concatenation' (base_config.yaml:44), "
+                                    "'concatenation_diff' and 'concatenation_prod'; 'similarity' is evaluation only")
         dev = next(self.W_p.parameters()).device
         L_f = label_embeddings.to(dev, non_blocking=True)
         # label-embedding noise (ProtNote.py:219-240): RNG-stream dependent, kept as the reference's own torch ops

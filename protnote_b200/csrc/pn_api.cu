@@ -1866,6 +1866,48 @@ int pn_t_pair_hidden(const float* a, long long B, const float* c, long long L, i
   return launch_emit(p, B * L, H, hi, lo, ld, hiT, loT, blocksT, static_cast<cudaStream_t>(stream));
 }
 
+int pn_t_pair_product(const float* p, long long B, const float* t, long long L, int d, void* hi, void* lo, long long ld,
+                      void* hiT, void* loT, long long blocksT, void* stream) {
+  if (B <= 0 || L <= 0 || !p || !t) return fail("empty pair grid");
+  PairProdProducer prod{p, t, L, B * L, d};
+  return launch_emit(prod, B * L, d, hi, lo, ld, hiT, loT, blocksT, static_cast<cudaStream_t>(stream));
+}
+
+int pn_t_pair_add(const void* x_hi, const void* x_lo, long long ld_x, const float* a, long long B, const float* c,
+                  long long L, int H, void* hi, void* lo, long long ld, void* stream) {
+  if (B <= 0 || L <= 0 || !a || !c) return fail("empty pair grid");
+  if (!x_hi || ld_x % 8 != 0 || ld_x < H) return fail("pair_add: planes missing or bad pitch");
+  if ((x_lo != nullptr) != (lo != nullptr)) return fail("pair_add: input and output must carry the same planes");
+  PairAddProducer prod{static_cast<const __half*>(x_hi), static_cast<const __half*>(x_lo), ld_x, a, c, L, B * L, H};
+  return launch_emit(prod, B * L, H, hi, lo, ld, nullptr, nullptr, 0, static_cast<cudaStream_t>(stream));
+}
+
+int pn_t_pair_marginals(const void* g_hi, const void* g_lo, long long ld_g, const float* g_sc, long long B, long long L,
+                        int cols, const float* wb, const float* wl, float* out_b, float* out_l, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (B <= 0 || L <= 0 || cols <= 0 || !g_hi || ld_g % 8 != 0 || ld_g < cols) return fail("pair_marginals: bad planes");
+  if (!out_b && !out_l) return fail("pair_marginals: no output requested");
+  const int col_blocks = (cols + 255) / 256;
+  const long long l_blocks = (L + 7) / 8;
+  if (B > 2147483647LL || l_blocks > 65535 || col_blocks > 65535) return fail("pair_marginals: grid too large (B %lld, L %lld)", B, L);
+  const __half* gh = static_cast<const __half*>(g_hi);
+  const __half* gl = static_cast<const __half*>(g_lo);
+  if (out_l) {
+    const dim3 grid(col_blocks, (unsigned)l_blocks);
+    if (gl) pair_marginal_l_kernel<true><<<grid, dim3(32, 8), 0, stream>>>(gh, gl, ld_g, g_sc, B, L, cols, wb, out_l);
+    else pair_marginal_l_kernel<false><<<grid, dim3(32, 8), 0, stream>>>(gh, gl, ld_g, g_sc, B, L, cols, wb, out_l);
+    g_launches++;
+  }
+  if (out_b) {
+    const dim3 grid((unsigned)B, col_blocks);
+    if (gl) pair_marginal_b_kernel<true><<<grid, dim3(32, 8), 0, stream>>>(gh, gl, ld_g, g_sc, B, L, cols, wl, out_b);
+    else pair_marginal_b_kernel<false><<<grid, dim3(32, 8), 0, stream>>>(gh, gl, ld_g, g_sc, B, L, cols, wl, out_b);
+    g_launches++;
+  }
+  PN_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int pn_t_bwd_stats(const pn_bwd_src* src, double* sums, float* maxes, double* dw, double* db, float* gyl, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   PN_TRY(check_src(src));

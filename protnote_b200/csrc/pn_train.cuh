@@ -331,6 +331,158 @@ __global__ void dropout_f32_kernel(const float* __restrict__ x, long long rows, 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// FEATURE_FUSION concatenation_prod in training (ProtNote.py:140-150): the third feature block p (.) t is not a sum of a
+// protein and a label term, so its share of layer 1, x = (p (.) t) Wx^T, is a real [B*L, d] x [d, H] GEMM:
+//   PairProdProducer   q[b*L + l] = P_e[b] (.) L_e[l] as planes (+ transposed planes for d Wx = g_z1^T q)
+//   PairAddProducer    z1[b*L + l] = x[b*L + l] + a[b] + c[l] as planes - from there layer 1 is an ordinary layer
+//   pair_marginals     out_b[b] = sum_l G[b,l] (.) wl[l],  out_l[l] = sum_b G[b,l] (.) wb[b]  (unit weights when null):
+//                      da / dc from g_z1, and the product block's share of d P_e / d L_e from g_q
+// ------------------------------------------------------------------------------------------------
+struct PairProdProducer {
+  const float* p; const float* t; long long L; long long rows; int cols;
+  struct Ctx { int unused; };
+  struct Raw { float ta[8], tb[8]; int b0, b1; };
+  __device__ __forceinline__ void init(int c0, Ctx& k) const { k.unused = 0; }
+  template <bool LO>
+  __device__ __forceinline__ void load(long long r, int c0, Raw& q) const {
+    if (c0 >= cols || r >= rows) return;
+    const long long b0 = r / L;
+    long long l0 = r - b0 * L, l1 = l0 + 1, b1 = b0;
+    if (l1 == L) {
+      l1 = 0;
+      ++b1;
+    }
+    q.b0 = (int)b0;
+    q.b1 = (int)b1;
+    load8_f32(t + l0 * cols + c0, cols - c0, q.ta);
+    if (r + 1 < rows) load8_f32(t + l1 * cols + c0, cols - c0, q.tb);
+  }
+  template <bool LO>
+  __device__ __forceinline__ void eval(const Ctx& k, const Raw& q, long long r, int c0, float (&va)[8], float (&vb)[8]) const {
+    zero8(va);
+    zero8(vb);
+    if (c0 >= cols || r >= rows) return;
+    float pv[8];
+    load8_f32(p + (long long)q.b0 * cols + c0, cols - c0, pv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) va[j] = c0 + j < cols ? pv[j] * q.ta[j] : 0.f;
+    if (r + 1 < rows) {
+      if (q.b1 != q.b0) load8_f32(p + (long long)q.b1 * cols + c0, cols - c0, pv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) vb[j] = c0 + j < cols ? pv[j] * q.tb[j] : 0.f;
+    }
+  }
+};
+
+struct PairAddProducer {
+  const __half* xh; const __half* xl; long long ld; const float* a; const float* c; long long L; long long rows; int cols;
+  struct Ctx { int unused; };
+  struct Raw { Raw8 xa, xb; float ca[8], cb[8]; int b0, b1; };
+  __device__ __forceinline__ void init(int c0, Ctx& k) const { k.unused = 0; }
+  template <bool LO>
+  __device__ __forceinline__ void load(long long r, int c0, Raw& q) const {
+    if (c0 >= cols || r >= rows) return;
+    const long long b0 = r / L;
+    long long l0 = r - b0 * L, l1 = l0 + 1, b1 = b0;
+    if (l1 == L) {
+      l1 = 0;
+      ++b1;
+    }
+    q.b0 = (int)b0;
+    q.b1 = (int)b1;
+    raw_load<LO>(xh, xl, r * ld + c0, q.xa);
+    load8_f32(c + l0 * cols + c0, cols - c0, q.ca);
+    if (r + 1 < rows) {
+      raw_load<LO>(xh, xl, (r + 1) * ld + c0, q.xb);
+      load8_f32(c + l1 * cols + c0, cols - c0, q.cb);
+    }
+  }
+  template <bool LO>
+  __device__ __forceinline__ void eval(const Ctx& k, const Raw& q, long long r, int c0, float (&va)[8], float (&vb)[8]) const {
+    zero8(va);
+    zero8(vb);
+    if (c0 >= cols || r >= rows) return;
+    float av[8], xv[8];
+    load8_f32(a + (long long)q.b0 * cols + c0, cols - c0, av);
+    raw_to_f32<LO>(q.xa, xv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) va[j] = c0 + j < cols ? xv[j] + av[j] + q.ca[j] : 0.f;
+    if (r + 1 < rows) {
+      if (q.b1 != q.b0) load8_f32(a + (long long)q.b1 * cols + c0, cols - c0, av);
+      raw_to_f32<LO>(q.xb, xv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) vb[j] = c0 + j < cols ? xv[j] + av[j] + q.cb[j] : 0.f;
+    }
+  }
+};
+
+// out_l[l][n] = (1/sc) * sum_b G[b*L + l][n] * (wb ? wb[b][n] : 1).  grid (ceil(cols/256), ceil(L/8)), block (32, 8):
+// one thread per (label row, 8 columns) walks the B proteins (rows L apart, coalesced along the columns); fp64 sums.
+template <bool LO>
+__global__ void __launch_bounds__(256) pair_marginal_l_kernel(const __half* __restrict__ gh, const __half* __restrict__ gl,
+                                                              long long ld, const float* __restrict__ sc, long long B,
+                                                              long long L, int cols, const float* __restrict__ wb,
+                                                              float* __restrict__ out) {
+  const int c0 = blockIdx.x * 256 + threadIdx.x * 8;
+  const long long l = (long long)blockIdx.y * 8 + threadIdx.y;
+  if (c0 >= cols || l >= L) return;
+  double acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.0;
+  for (long long b = 0; b < B; ++b) {
+    Raw8 q;
+    float g[8], w[8];
+    raw_load<LO>(gh, gl, (b * L + l) * ld + c0, q);
+    raw_to_f32<LO>(q, g);
+    if (wb) load8_f32(wb + b * cols + c0, cols - c0, w);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += (double)(wb ? g[j] * w[j] : g[j]);
+  }
+  const double inv = sc ? 1.0 / (double)__ldg(sc) : 1.0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (c0 + j < cols) out[l * cols + c0 + j] = (float)(acc[j] * inv);
+}
+
+// out_b[b][n] = (1/sc) * sum_l G[b*L + l][n] * (wl ? wl[l][n] : 1).  grid (B, ceil(cols/256)), block (32, 8): the 8 row
+// phases of a block walk the L rows of protein b, fp64 partial sums, one shared-memory reduction (deterministic).
+template <bool LO>
+__global__ void __launch_bounds__(256) pair_marginal_b_kernel(const __half* __restrict__ gh, const __half* __restrict__ gl,
+                                                              long long ld, const float* __restrict__ sc, long long B,
+                                                              long long L, int cols, const float* __restrict__ wl,
+                                                              float* __restrict__ out) {
+  __shared__ double sh[8][8][32];        // [row phase][element][lane]
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const long long b = blockIdx.x;
+  const int c0 = blockIdx.y * 256 + tx * 8;
+  double acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.0;
+  if (c0 < cols) {
+    for (long long l = ty; l < L; l += 8) {
+      Raw8 q;
+      float g[8], w[8];
+      raw_load<LO>(gh, gl, (b * L + l) * ld + c0, q);
+      raw_to_f32<LO>(q, g);
+      if (wl) load8_f32(wl + l * cols + c0, cols - c0, w);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += (double)(wl ? g[j] * w[j] : g[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sh[ty][j][tx] = acc[j];
+  __syncthreads();
+  const int i = ty * 32 + tx;            // column i of the block = lane i / 8, element i % 8
+  const int c = blockIdx.y * 256 + i;
+  if (c < cols) {
+    double tot = 0.0;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) tot += sh[y][i & 7][i >> 3];
+    out[b * cols + c] = (float)(tot * (sc ? 1.0 / (double)__ldg(sc) : 1.0));
+  }
+}
+
 // Sources of the BatchNorm+ReLU backward.  kind 0: g planes, z planes.  kind 1: g = g_logit[r] * w[n] (the gradient of
 // the final Linear(H -> 1), never materialised), z planes.  kind 2: g planes, z = a[r / L] + c[r % L].
 struct BwdSrc {

@@ -216,14 +216,19 @@ def layer1_factors(lin1: nn.Linear, d: int, fusion: str):
     (ProtNote.py:112-152): z1[b,l] = P_e[b] Wp^T + L_e[l] Wl^T.
       'concatenation'       [p; t]        Wp = W[:, :d],               Wl = W[:, d:2d]
       'concatenation_diff'  [p; t; p - t] Wp = W[:, :d] + W[:, 2d:],   Wl = W[:, d:2d] - W[:, 2d:]
-    ([H, d] parameter arithmetic, once per step; 'concatenation_prod' is not a sum of two such terms.)"""
+      'concatenation_prod'  [p; t; p * t] Wp = W[:, :d],               Wl = W[:, d:2d]   plus the product block, which is
+                            not of this form: x[b,l] = (P_e[b] * L_e[l]) W[:, 2d:]^T is added by pairs_forward
+    ([H, d] parameter arithmetic, once per step.)"""
     W = lin1.weight.detach()
     if fusion == "concatenation" and W.shape[1] == 2 * d:
         return W[:, :d], W[:, d:]
     if fusion == "concatenation_diff" and W.shape[1] == 3 * d:
         return W[:, :d] + W[:, 2 * d:], W[:, d:2 * d] - W[:, 2 * d:]
-    raise NotImplementedError(f"the training path implements FEATURE_FUSION 'concatenation' (base_config.yaml:44) and "
-                              f"'concatenation_diff'; got '{fusion}' with {W.shape[1]} input features for latent_dim {d}")
+    if fusion == "concatenation_prod" and W.shape[1] == 3 * d:
+        return W[:, :d], W[:, d:2 * d]
+    raise NotImplementedError(f"the training path implements FEATURE_FUSION 'concatenation' (base_config.yaml:44), "
+                              f"'concatenation_diff' and 'concatenation_prod'; got '{fusion}' with {W.shape[1]} input "
+                              f"features for latent_dim {d}")
 
 
 def _layer_state(ops, comm, z, lin, bn, count, sharded, update_running):
@@ -252,17 +257,29 @@ def pairs_forward(ops, comm, P_e, L_e, hidden, final: nn.Linear, L_total: int, s
     le = ops.split(L_e, want_T=True)
     a = ops.linear(pe, ops.pack(W1p), out_f32=True)                         # [B, H] raw protein term
     c = ops.linear(le, ops.pack(W1l), out_f32=True)                         # [L_local, H] raw label term
-    if bn1 is None:
-        st1 = ops.affine_state(lin1.bias, lin1.weight.shape[0], lin1.weight.device)
+    want_T1 = len(hidden) > 1 and not drops.get(0)
+    prod = None
+    if fusion == "concatenation_prod":
+        # layer 1 with the product block: z1 = x + a[b] + c[l], x = (P_e[b] * L_e[l]) Wx^T a real GEMM over all pairs; with
+        # z1 as planes it is an ordinary layer (statistics pass, BN + ReLU), factorised only in its two linear blocks
+        W1x = lin1.weight.detach()[:, 2 * d:]
+        q = ops.pair_product(P_e, L_e, want_T=True)                         # [B * L_local, d]
+        z1 = ops.pair_add(ops.linear(q, ops.pack(W1x), out_f32=False), a, c)
+        st1 = _layer_state(ops, comm, z1, lin1, bn1, B * L_total, sharded, update_running)
+        h = ops.bn_relu(z1, st1, want_T=want_T1)
+        prod = {"q": q, "z1": z1, "W1x": W1x, "P_e": P_e, "L_e": L_e}
     else:
-        sa = ops.col_stats_f32(a)
-        sc = ops.col_stats_f32(c)
-        if sharded:
-            comm.sum_(sc)
-        st1 = ops.bn_finalize_pair(sa, B, sc, L_total, bn1, update_running)
-    h = ops.pair_hidden(a, c, st1, want_T=len(hidden) > 1 and not drops.get(0))                 # [B * L_local, H]
+        if bn1 is None:
+            st1 = ops.affine_state(lin1.bias, lin1.weight.shape[0], lin1.weight.device)
+        else:
+            sa = ops.col_stats_f32(a)
+            sc = ops.col_stats_f32(c)
+            if sharded:
+                comm.sum_(sc)
+            st1 = ops.bn_finalize_pair(sa, B, sc, L_total, bn1, update_running)
+        h = ops.pair_hidden(a, c, st1, want_T=want_T1)                      # [B * L_local, H]
     h = _relu_dropout(ops, h, drops.get(0))
-    ctx = {"drops": drops, "pe": pe, "le": le, "a": a, "c": c, "st1": st1, "layers": [], "B": B, "d": d, "hidden": hidden,
+    ctx = {"drops": drops, "prod": prod, "pe": pe, "le": le, "a": a, "c": c, "st1": st1, "layers": [], "B": B, "d": d, "hidden": hidden,
            "final": final, "count": B * L_total, "fusion": fusion, "W1p": W1p, "W1l": W1l}
     logits = None
     if len(hidden) == 1:
@@ -368,6 +385,8 @@ def pairs_backward(ops, comm, ctx, g_logit, sharded: bool, grads: Dict):
     d = ctx["d"]
     if drops.get(0):
         g = ops.dropout(g, drops[0])
+    if ctx["prod"] is not None:
+        return _layer1_backward_prod(ops, comm, ctx, g, sharded, grads)
     zp = ops.pair_source(ctx["a"], ctx["c"])
     s = ops.bwd_stats(g, zp, ctx["st1"])
     _affine_grads(ops, comm, s, lin1, bn1, sharded, grads)
@@ -382,6 +401,31 @@ def pairs_backward(ops, comm, ctx, g_logit, sharded: bool, grads: Dict):
     grads[lin1.weight] = dW1
     dPe = ops.dgrad(ga, ops.pack(ctx["W1p"], transposed=True), out_f32=True)
     dLe = ops.dgrad(gc, ops.pack(ctx["W1l"], transposed=True), out_f32=True)
+    return dPe, dLe
+
+
+def _layer1_backward_prod(ops, comm, ctx, g, sharded: bool, grads: Dict):
+    """Layer 1 of the output MLP on [p; t; p * t]: an ordinary layer backward on the z1 planes, then the gradient w.r.t.
+    z1[b,l] = a[b] + c[l] + q[b,l] Wx^T goes three ways: its two marginals to the linear blocks (da, dc), d Wx = g_z1^T q, and
+    through g_q = g_z1 Wx to d P_e[b] += sum_l g_q[b,l] * L_e[l], d L_e[l] += sum_b g_q[b,l] * P_e[b]."""
+    lin1, bn1 = ctx["hidden"][0][0], ctx["hidden"][0][1]
+    d, B, pr = ctx["d"], ctx["B"], ctx["prod"]
+    L = ctx["c"].shape[0]
+    s = ops.bwd_stats(g, pr["z1"], ctx["st1"])
+    _affine_grads(ops, comm, s, lin1, bn1, sharded, grads)
+    gz = ops.bwd_apply(g, pr["z1"], ctx["st1"], s, ctx["count"], want_T=True)
+    dW1 = torch.empty_like(lin1.weight)
+    ops.wgrad(gz, pr["q"], out=dW1[:, 2 * d:])
+    da, dc = ops.pair_marginals(gz, B, L)                                   # fp32 [B, H], [L_local, H]
+    gq = ops.dgrad(gz, ops.pack(pr["W1x"], transposed=True))                # [B * L_local, d]
+    dPe, dLe = ops.pair_marginals(gq, B, L, wb=pr["P_e"], wl=pr["L_e"])
+    ga = ops.split(da, want_T=True, autoscale=True)
+    gc = ops.split(dc, want_T=True, autoscale=True)
+    ops.wgrad(ga, ctx["pe"], out=dW1[:, :d])
+    ops.wgrad(gc, ctx["le"], out=dW1[:, d:2 * d])
+    grads[lin1.weight] = dW1
+    ops.dgrad(ga, ops.pack(ctx["W1p"], transposed=True), out_f32=True, accumulate_into=dPe)
+    ops.dgrad(gc, ops.pack(ctx["W1l"], transposed=True), out_f32=True, accumulate_into=dLe)
     return dPe, dLe
 
 

@@ -132,12 +132,15 @@ class NativeOps:
     def _promote(self, rows):
         return self.promote_small if rows <= (1 << 17) else self.promote_fwd
 
-    def linear(self, x: Act, W: Packed, out_f32=False):
+    def linear(self, x: Act, W: Packed, out_f32=False, accumulate_into=None):
         assert x.cols == W.K
         if out_f32:
-            out = torch.empty(x.rows, W.N, dtype=torch.float32, device=x.hi.device)
+            out = accumulate_into
+            if out is None:
+                out = torch.empty(x.rows, W.N, dtype=torch.float32, device=x.hi.device)
+            assert out.dtype == torch.float32 and tuple(out.shape) == (x.rows, W.N) and out.stride(1) == 1
             self._gemm(x.hi, x.lo, x.rows, x.cols, x.ld, W.hi, W.lo, W.N, W.ld, [W.ws, x.sc], out_f32=out,
-                       promote=self._promote(x.rows))
+                       accumulate=accumulate_into is not None, promote=self._promote(x.rows))
             return out
         z = Act(x.rows, W.N, x.hi.device, self.strict, False)
         z.sc = x.sc
@@ -145,8 +148,9 @@ class NativeOps:
                    promote=self._promote(x.rows))
         return z
 
-    def dgrad(self, g: Act, WT: Packed, out_f32=False):
-        return self.linear(g, WT, out_f32=out_f32)      # g_x = g_z W = g_z (W^T)^T; planes keep g's scale
+    def dgrad(self, g: Act, WT: Packed, out_f32=False, accumulate_into=None):
+        # g_x = g_z W = g_z (W^T)^T; planes keep g's scale; accumulate_into: fp32 tensor the result is added to
+        return self.linear(g, WT, out_f32=out_f32, accumulate_into=accumulate_into)
 
     def wgrad(self, g: Act, x: Act, out: Optional[torch.Tensor] = None):
         if not (g.has_T and x.has_T):
@@ -275,6 +279,40 @@ class NativeOps:
             check(self.lib.pn_t_pair_hidden(ptr(a), B, ptr(c), L, H, ptr(st), ptr(h.hi), ptr(h.lo), h.ld, ptr(h.hiT),
                                             ptr(h.loT), h.ldT, stream_ptr()))
         return h
+
+    # ------------------------------------------------------------------ FEATURE_FUSION concatenation_prod
+    def pair_product(self, P_e, L_e, want_T=False) -> Act:
+        """q[b*L + l] = P_e[b] * L_e[l] (elementwise) as planes [B*L, d]"""
+        P_e, L_e = self._f32(P_e, "sequence embeddings"), self._f32(L_e, "label embeddings")
+        (B, d), L = P_e.shape, L_e.shape[0]
+        q = Act(B * L, d, P_e.device, self.strict, want_T)
+        with torch.cuda.device(P_e.device):
+            check(self.lib.pn_t_pair_product(ptr(P_e), B, ptr(L_e), L, d, ptr(q.hi), ptr(q.lo), q.ld, ptr(q.hiT), ptr(q.loT),
+                                             q.ldT, stream_ptr()))
+        return q
+
+    def pair_add(self, x: Act, a, c) -> Act:
+        """z[b*L + l] = x[b*L + l] + a[b] + c[l] as planes"""
+        assert x.sc is None and x.rows == a.shape[0] * c.shape[0] and x.cols == a.shape[1] == c.shape[1]
+        a, c = self._f32(a, "protein term"), self._f32(c, "label term")
+        z = Act(x.rows, x.cols, x.hi.device, x.lo is not None, False)
+        with torch.cuda.device(x.hi.device):
+            check(self.lib.pn_t_pair_add(ptr(x.hi), ptr(x.lo), x.ld, ptr(a), a.shape[0], ptr(c), c.shape[0], x.cols, ptr(z.hi),
+                                         ptr(z.lo), z.ld, stream_ptr()))
+        return z
+
+    def pair_marginals(self, g: Act, B, L, wb=None, wl=None):
+        """(sum_l g[b,l] * wl[l], sum_b g[b,l] * wb[b]) of a pair-grid tensor g [B*L, cols] (true scale); unit weights if None"""
+        assert g.rows == B * L
+        dev = g.hi.device
+        wb = None if wb is None else self._f32(wb, "protein weights")
+        wl = None if wl is None else self._f32(wl, "label weights")
+        out_b = torch.empty(B, g.cols, dtype=torch.float32, device=dev)
+        out_l = torch.empty(L, g.cols, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(self.lib.pn_t_pair_marginals(ptr(g.hi), ptr(g.lo), g.ld, ptr(g.sc), B, L, g.cols, ptr(wb), ptr(wl),
+                                               ptr(out_b), ptr(out_l), stream_ptr()))
+        return out_b, out_l
 
     # ------------------------------------------------------------------ BatchNorm + ReLU backward
     def outer(self, g_logit, w):

@@ -277,6 +277,9 @@ VARIANTS = {"no_batchnorm": dict(output_mlp_batchnorm=False),
             "diff": dict(feature_fusion="concatenation_diff"),
             "diff_no_batchnorm": dict(feature_fusion="concatenation_diff", output_mlp_batchnorm=False),
             "two_layers_no_batchnorm": dict(output_mlp_num_layers=2, output_mlp_batchnorm=False),
+            "prod": dict(feature_fusion="concatenation_prod"),
+            "prod_no_batchnorm": dict(feature_fusion="concatenation_prod", output_mlp_batchnorm=False),
+            "one_layer_prod": dict(feature_fusion="concatenation_prod", output_mlp_num_layers=1),
             "one_layer": dict(output_mlp_num_layers=1),
             "one_layer_diff_no_batchnorm": dict(output_mlp_num_layers=1, output_mlp_batchnorm=False,
                                                 feature_fusion="concatenation_diff")}
@@ -357,6 +360,39 @@ def test_embedding_dropouts_on_device():
         e1, _ = model(sequence_embeddings=P_f, label_embeddings=L_f)
         e2, _ = model(sequence_embeddings=P_f, label_embeddings=L_f)
     assert torch.equal(e1, e2)
+
+
+@pytest.mark.parametrize("B,L,d,H", [(3, 50, 32, 96), (5, 13, 40, 300), (2, 130, 72, 36), (1, 1, 8, 8)])
+def test_pair_product_primitives(B, L, d, H):
+    """The three primitives FEATURE_FUSION concatenation_prod adds to the training step, against their statements:
+    pair_product (planes + transposed planes of P_e[b] * L_e[l]), pair_add (x + a[b] + c[l]) and pair_marginals (the two
+    marginal sums of a pair-grid tensor, with and without weights, on a tensor that carries a device scale)."""
+    nat, ref = _ops("strict")
+    g = torch.Generator().manual_seed(B * 1000 + L)
+    P, T = torch.randn(B, d, generator=g), torch.randn(L, d, generator=g)
+    q = nat.pair_product(P.cuda(), T.cuda(), want_T=True)
+    qr = ref.pair_product(P, T, want_T=True)
+    assert _rel(_val(q), qr.val) < 1e-6 and torch.equal(_val(q), _valT(q))
+    x = torch.randn(B * L, H, generator=g)
+    a, c = torch.randn(B, H, generator=g), torch.randn(L, H, generator=g)
+    xa = nat.split(x.cuda(), want_T=False)
+    z = nat.pair_add(xa, a.cuda(), c.cuda())
+    zr = ref.pair_add(ref.split(x), a.double(), c.double())
+    assert _rel(_val(z), zr.val) < 1e-6
+    gs = nat.split(x.cuda() * 3e-6, want_T=False, autoscale=True)           # gradient-like: carries a device scale
+    gr = ref.split(x * 3e-6)
+    ob, ol = nat.pair_marginals(gs, B, L)
+    rb, rl = ref.pair_marginals(gr, B, L)
+    assert _rel(ob.cpu().double(), rb) < 1e-5 and _rel(ol.cpu().double(), rl) < 1e-5
+    wb, wl = torch.randn(B, H, generator=g), torch.randn(L, H, generator=g)
+    ob, ol = nat.pair_marginals(gs, B, L, wb=wb.cuda(), wl=wl.cuda())
+    rb, rl = ref.pair_marginals(gr, B, L, wb=wb.double(), wl=wl.double())
+    assert _rel(ob.cpu().double(), rb) < 1e-5 and _rel(ol.cpu().double(), rl) < 1e-5
+    fast, _ = _ops("fast")
+    qf = fast.pair_product(P.cuda(), T.cuda(), want_T=True)
+    assert qf.lo is None and _rel(_val(qf), qr.val) < 2e-3 and torch.equal(_val(qf), _valT(qf))
+    fb, fl = fast.pair_marginals(fast.split(x.cuda(), want_T=False), B, L)
+    assert _rel(fb.cpu().double(), ref.pair_marginals(ref.split(x), B, L)[0]) < 2e-3
 
 
 @pytest.mark.parametrize("rows,cols,p", [(70, 40, 0.3), (257, 300, 0.1), (130, 1100, 0.5), (64, 64, 0.0)])

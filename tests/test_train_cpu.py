@@ -147,9 +147,8 @@ def _variant_cfg(**kw):
 
 
 def test_training_path_refuses_what_it_does_not_implement():
-    """Unsupported options fail loudly (no silent fallback): a Dropout in front of the first Linear of an MLP,
-    'concatenation_prod' (not a sum of a protein and a label term); and the product module itself has no CPU path in
-    training mode."""
+    """Unsupported options fail loudly (no silent fallback): a Dropout in front of the first Linear of an MLP, training
+    with FEATURE_FUSION 'similarity'; and the product module itself has no CPU path in training mode."""
     from protnote_b200._lib import ProtnoteB200Error
     ecfg, scfg, sd, P_f, L_f, y = _problem()
     model = build_b200_model(ecfg, scfg, sd, device="cpu").double().train()
@@ -157,11 +156,10 @@ def test_training_path_refuses_what_it_does_not_implement():
     model.output_layer = torch.nn.Sequential(torch.nn.Dropout(0.1), *list(model.output_layer))     # get_mlp(input_dropout=)
     with pytest.raises(NotImplementedError):
         pn_train.forward_train(ops, None, model, P_f.double(), L_f.double())
-    prod_cfg = _variant_cfg(feature_fusion="concatenation_prod")
-    sd_prod = synth_state_dict(ecfg, prod_cfg, seed=3, calib_T=64)
-    prod = build_b200_model(ecfg, prod_cfg, sd_prod, device="cpu").double().train()
-    with pytest.raises(NotImplementedError):
-        pn_train.forward_train(ops, None, prod, P_f.double(), L_f.double())
+    sim_cfg = _variant_cfg(feature_fusion="similarity")
+    sim = build_b200_model(ecfg, sim_cfg, synth_state_dict(ecfg, sim_cfg, seed=3, calib_T=64), device="cpu").train()
+    with pytest.raises(ProtnoteB200Error, match="similarity"):
+        sim(sequence_embeddings=P_f, label_embeddings=L_f)
     # the product module: CPU tensors in training mode -> error, never a torch fallback
     cpu_model = build_b200_model(ecfg, scfg, sd, device="cpu").train()
     with pytest.raises(ProtnoteB200Error):
@@ -174,6 +172,9 @@ VARIANTS = {"no_batchnorm": dict(output_mlp_batchnorm=False),
             "diff": dict(feature_fusion="concatenation_diff"),
             "diff_no_batchnorm": dict(feature_fusion="concatenation_diff", output_mlp_batchnorm=False),
             "two_layers_no_batchnorm": dict(output_mlp_num_layers=2, output_mlp_batchnorm=False),
+            "prod": dict(feature_fusion="concatenation_prod"),
+            "prod_no_batchnorm": dict(feature_fusion="concatenation_prod", output_mlp_batchnorm=False),
+            "one_layer_prod": dict(feature_fusion="concatenation_prod", output_mlp_num_layers=1),
             "one_layer": dict(output_mlp_num_layers=1),
             "one_layer_diff_no_batchnorm": dict(output_mlp_num_layers=1, output_mlp_batchnorm=False,
                                                 feature_fusion="concatenation_diff")}
@@ -235,13 +236,14 @@ def _dropout_masks(model, P_rows, L_rows, base_seed, rank=0):
     return {(t, i): dropout_multiplier(seed, rows[t], layers[t][i][0].weight.shape[0], p) for (t, i), (seed, p) in plan.items()}
 
 
-@pytest.mark.parametrize("variant", ["default", "no_batchnorm", "two_layers"])
+@pytest.mark.parametrize("variant", ["default", "no_batchnorm", "two_layers", "prod"])
 def test_output_mlp_dropout_sequencing_matches_oracle(variant):
     """OUTPUT_MLP_DROPOUT > 0 (Dropout after every hidden ReLU and after the last Linear of W_p / W_l, after every hidden
     ReLU but the last of output_layer): the forward masks the activations, the backward the gradients, with masks that are
     a pure function of (seed, row, column) - against the autograd oracle multiplying with the same masks."""
     ecfg, _, *_ = CASES["tiny_concat"]
-    kw = {"default": {}, "no_batchnorm": dict(output_mlp_batchnorm=False), "two_layers": dict(output_mlp_num_layers=2)}[variant]
+    kw = {"default": {}, "no_batchnorm": dict(output_mlp_batchnorm=False), "two_layers": dict(output_mlp_num_layers=2),
+          "prod": dict(feature_fusion="concatenation_prod")}[variant]
     scfg = _variant_cfg(output_mlp_dropout=0.3, **kw)
     sd = synth_state_dict(ecfg, scfg, seed=13, calib_T=64)
     g = torch.Generator().manual_seed(19)

@@ -27,7 +27,9 @@ def _free_port():
 def _problem(variant=False):
     ecfg, scfg, *_ = CASES["tiny_concat"]
     import dataclasses
-    if variant == "dropout":     # OUTPUT_MLP_DROPOUT: one base seed for all ranks, rank-salted masks on the sharded rows
+    if variant == "prod":        # [p; t; p * t]: layer 1 is an ordinary (statistics-all-reduced) layer plus two marginals
+        scfg = dataclasses.replace(scfg, feature_fusion="concatenation_prod")
+    elif variant == "dropout":   # OUTPUT_MLP_DROPOUT: one base seed for all ranks, rank-salted masks on the sharded rows
         scfg = dataclasses.replace(scfg, output_mlp_dropout=0.3)
     elif variant:    # output MLP without BatchNorm (hidden biases, nothing to all-reduce in its backward) on [p; t; p - t]
         scfg = dataclasses.replace(scfg, output_mlp_batchnorm=False, feature_fusion="concatenation_diff")
@@ -112,9 +114,9 @@ def _sharded_masks(ecfg, scfg, sd, B, L, world):
     return masks
 
 
-@pytest.mark.parametrize("fused,variant", [(False, False), (True, False), (True, True), (True, "dropout")],
+@pytest.mark.parametrize("fused,variant", [(False, False), (True, False), (True, True), (True, "dropout"), (True, "prod")],
                          ids=["bce_via_autograd", "fused_focal_overlapped_allreduce", "fused_focal_diff_no_batchnorm",
-                              "fused_focal_output_mlp_dropout"])
+                              "fused_focal_output_mlp_dropout", "fused_focal_prod"])
 def test_label_sharded_training_step_equals_single_process(fused, variant):
     world = 2
     ctx = mp.get_context("spawn")
