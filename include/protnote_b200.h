@@ -338,6 +338,14 @@ int pn_t_pair_add(const void* x_hi, const void* x_lo, long long ld_x, const floa
 int pn_t_pair_marginals(const void* g_hi, const void* g_lo, long long ld_g, const float* g_sc, long long B, long long L,
                         int cols, const float* wb, const float* wl, float* out_b, float* out_l, void* stream);
 
+/* FEATURE_FUSION similarity in training (ProtNote.py:281-284; logits = normalize(P_e) normalize(L_e)^T / temperature, the
+ * matrix product itself is pn_t_gemm).  y = x * scale / max(|x|_2, 1e-12) per row of a contiguous fp32 [rows][cols] matrix
+ * (torch.nn.functional.normalize's eps), inv_norm[r] = 1 / max(|x|_2, 1e-12); backward dx = scale * inv_norm *
+ * (dy - u (u . dy)) with u = y / scale. */
+int pn_t_normalize_rows(const float* x, long long rows, int cols, float scale, float* y, float* inv_norm, void* stream);
+int pn_t_normalize_rows_bwd(const float* y, const float* inv_norm, const float* dy, long long rows, int cols, float scale,
+                            float* dx, void* stream);
+
 typedef struct pn_bwd_src {
   int kind;
   long long rows;

@@ -132,6 +132,17 @@ class TorchOps:
             return accumulate_into
         return y if out_f32 else TAct(y * g.sc, g.sc, False)
 
+    # ------------------------------------------------------------------ FEATURE_FUSION similarity
+    def normalize_rows(self, x, scale=1.0):
+        x = x.detach().to(self.dtype)
+        inv = 1.0 / x.norm(dim=1).clamp_min(1e-12)
+        return x * inv[:, None] * scale, inv
+
+    def normalize_rows_bwd(self, y, inv_norm, dy, scale=1.0):
+        u = y / scale
+        dy = dy.to(self.dtype)
+        return scale * inv_norm[:, None] * (dy - u * (u * dy).sum(1, keepdim=True))
+
     # ------------------------------------------------------------------ FEATURE_FUSION concatenation_prod
     def pair_product(self, P_e, L_e, want_T=False):
         P_e, L_e = P_e.detach().to(self.dtype), L_e.detach().to(self.dtype)

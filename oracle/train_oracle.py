@@ -64,7 +64,7 @@ def train_step_oracle(sd: Dict[str, torch.Tensor], P_f, L_f, targets, cfg: Score
     its ReLU; after the bare last Linear: torchvision MLP, ProtNote.py:63-81), ("o", j): after the ReLU of hidden layer j of
     output_layer (get_mlp, ProtNote.py:369-371)}; a dropout module is exactly this multiplication with a random mask."""
     masks = masks or {}
-    if not cfg.feature_fusion.startswith("concatenation"):
+    if not (cfg.feature_fusion.startswith("concatenation") or cfg.feature_fusion == "similarity"):
         raise NotImplementedError(cfg.feature_fusion)
     p = {k: v.detach().clone().to(dtype).requires_grad_(True) for k, v in sd.items()
          if v.is_floating_point() and not k.startswith("sequence_encoder.") and "running_" not in k}
@@ -86,6 +86,9 @@ def train_step_oracle(sd: Dict[str, torch.Tensor], P_f, L_f, targets, cfg: Score
     # W_l.1.*.  The dropout itself is a random draw: this oracle takes P_f / L_f AFTER it (the caller replays the masks).
     P_e = head("W_p.1" if cfg.sequence_embedding_dropout > 0 else "W_p", P_f.to(dtype))
     L_e = head("W_l.1" if cfg.label_embedding_dropout > 0 else "W_l", L_f.to(dtype))
+    if cfg.feature_fusion == "similarity":      # ProtNote.py:281-284
+        logits = F.normalize(P_e, dim=-1, p=2) @ F.normalize(L_e, dim=-1, p=2).t() / cfg.temperature
+        return _finish(logits, targets, p, new_stats, dtype, loss_kw)
     x = joint_features(P_e, L_e, cfg.feature_fusion)
     hidden, last = output_mlp_layout(cfg)
     for j, (lin, bn) in enumerate(hidden):
@@ -99,6 +102,10 @@ def train_step_oracle(sd: Dict[str, torch.Tensor], P_f, L_f, targets, cfg: Score
             x = x * masks[("o", j)].to(dtype)
     logits = (x @ full[f"output_layer.{last}.weight"].T + full[f"output_layer.{last}.bias"]).reshape(
         P_e.shape[0], L_e.shape[0])
+    return _finish(logits, targets, p, new_stats, dtype, loss_kw)
+
+
+def _finish(logits, targets, p, new_stats, dtype, loss_kw):
     if "pos_weight" in loss_kw and loss_kw["pos_weight"] is not None:
         loss_kw = dict(loss_kw, pos_weight=loss_kw["pos_weight"].to(dtype))
     loss = loss_oracle(logits, targets.to(dtype), **loss_kw)

@@ -275,9 +275,8 @@ class ProtNote(nn.Module):
             raise ValueError("Incompatible label parameters passed to forward method.")
         if self.label_embedding_pooling_method == "all":
             raise ProtnoteB200Error("LABEL_EMBEDDING_POOLING_METHOD 'all' is not on the cached-embedding path")
-        if not self.feature_fusion.startswith("concatenation"):
-            raise ProtnoteB200Error("the training path implements FEATURE_FUSION 'concatenation' (base_config.yaml:44), "
-                                    "'concatenation_diff' and 'concatenation_prod'; 'similarity' is evaluation only")
+        if not (self.feature_fusion.startswith("concatenation") or self.feature_fusion == "similarity"):
+            raise ValueError("feature fusion method not implemented")
         dev = next(self.W_p.parameters()).device
         L_f = label_embeddings.to(dev, non_blocking=True)
         # label-embedding noise (ProtNote.py:219-240): RNG-stream dependent, kept as the reference's own torch ops

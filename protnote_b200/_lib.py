@@ -98,6 +98,8 @@ SIGNATURES = {
     "pn_t_pair_product": (_I, [_P, _LL, _P, _LL, _I, _P, _P, _LL, _P, _P, _LL, _P]),
     "pn_t_pair_add": (_I, [_P, _P, _LL, _P, _LL, _P, _LL, _I, _P, _P, _LL, _P]),
     "pn_t_pair_marginals": (_I, [_P, _P, _LL, _P, _LL, _LL, _I, _P, _P, _P, _P, _P]),
+    "pn_t_normalize_rows": (_I, [_P, _LL, _I, C.c_float, _P, _P, _P]),
+    "pn_t_normalize_rows_bwd": (_I, [_P, _P, _P, _LL, _I, C.c_float, _P, _P]),
     "pn_t_bwd_stats": (_I, [C.POINTER(BwdSrc), _P, _P, _P, _P, _P, _P]),
     "pn_t_bwd_scale": (_I, [_P, _P, _P, C.c_double, _I, _P, _P, _P]),
     "pn_t_bwd_apply": (_I, [C.POINTER(BwdSrc), _P, _P, _P, _P, _LL, _P, _P, _LL, _P]),

@@ -1908,6 +1908,25 @@ int pn_t_pair_marginals(const void* g_hi, const void* g_lo, long long ld_g, cons
   return 0;
 }
 
+int pn_t_normalize_rows(const float* x, long long rows, int cols, float scale, float* y, float* inv_norm, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (rows <= 0 || cols <= 0 || !x || !y || !inv_norm || !(scale != 0.f)) return fail("bad input to normalize_rows");
+  normalize_rows_kernel<<<ew_grid(rows * 32), 256, 0, stream>>>(x, rows, cols, scale, y, inv_norm);
+  g_launches++;
+  PN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int pn_t_normalize_rows_bwd(const float* y, const float* inv_norm, const float* dy, long long rows, int cols, float scale,
+                            float* dx, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (rows <= 0 || cols <= 0 || !y || !inv_norm || !dy || !dx || !(scale != 0.f)) return fail("bad input to normalize_rows_bwd");
+  normalize_rows_bwd_kernel<<<ew_grid(rows * 32), 256, 0, stream>>>(y, inv_norm, dy, rows, cols, scale, dx);
+  g_launches++;
+  PN_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int pn_t_bwd_stats(const pn_bwd_src* src, double* sums, float* maxes, double* dw, double* db, float* gyl, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   PN_TRY(check_src(src));

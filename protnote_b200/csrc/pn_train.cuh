@@ -483,6 +483,47 @@ __global__ void __launch_bounds__(256) pair_marginal_b_kernel(const __half* __re
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// FEATURE_FUSION similarity in training (ProtNote.py:281-284): logits = normalize(P_e) normalize(L_e)^T / temperature.
+// One warp per row of a small fp32 matrix ([B][latent], [L][latent]); fp64 row sums.
+//   forward   y = x * scale / max(|x|_2, 1e-12)  (F.normalize's eps), inv_norm[r] = 1 / max(|x|_2, 1e-12)
+//   backward  dx = scale * inv_norm * (dy - u (u . dy)),  u = y / scale the unit row
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) normalize_rows_kernel(const float* __restrict__ x, long long rows, int cols,
+                                                             float scale, float* __restrict__ y,
+                                                             float* __restrict__ inv_norm) {
+  const long long r = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  double ss = 0.0;
+  for (int c = lane; c < cols; c += 32) {
+    const double v = (double)x[r * cols + c];
+    ss += v * v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const double n = sqrt(ss);
+  const float inv = (float)(1.0 / (n > 1e-12 ? n : 1e-12));
+  if (lane == 0) inv_norm[r] = inv;
+  for (int c = lane; c < cols; c += 32) y[r * cols + c] = x[r * cols + c] * inv * scale;
+}
+
+__global__ void __launch_bounds__(256) normalize_rows_bwd_kernel(const float* __restrict__ y,
+                                                                 const float* __restrict__ inv_norm,
+                                                                 const float* __restrict__ dy, long long rows, int cols,
+                                                                 float scale, float* __restrict__ dx) {
+  const long long r = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const float inv_scale = 1.f / scale;
+  double dot = 0.0;
+  for (int c = lane; c < cols; c += 32) dot += (double)(y[r * cols + c] * inv_scale) * (double)dy[r * cols + c];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+  const float d = (float)dot, k = scale * inv_norm[r];
+  for (int c = lane; c < cols; c += 32) dx[r * cols + c] = k * (dy[r * cols + c] - y[r * cols + c] * inv_scale * d);
+}
+
 // Sources of the BatchNorm+ReLU backward.  kind 0: g planes, z planes.  kind 1: g = g_logit[r] * w[n] (the gradient of
 // the final Linear(H -> 1), never materialised), z planes.  kind 2: g planes, z = a[r / L] + c[r % L].
 struct BwdSrc {

@@ -430,11 +430,34 @@ def _layer1_backward_prod(ops, comm, ctx, g, sharded: bool, grads: Dict):
 
 
 # --------------------------------------------------------------------------------------------------------------------
+# FEATURE_FUSION similarity (ProtNote.py:281-284): logits = normalize(P_e) normalize(L_e)^T / temperature, no output MLP
+# --------------------------------------------------------------------------------------------------------------------
+def similarity_forward(ops, P_e, L_e, temperature: float):
+    scale = 1.0 / float(temperature)
+    Pn, ip = ops.normalize_rows(P_e, scale)                                 # the 1 / temperature rides on the protein rows
+    Ln, il = ops.normalize_rows(L_e, 1.0)
+    logits = ops.linear(ops.split(Pn), ops.pack(Ln), out_f32=True)          # [B, L_local]
+    return logits, {"Pn": Pn, "ip": ip, "Ln": Ln, "il": il, "scale": scale}
+
+
+def similarity_backward(ops, sctx, g_logits):
+    """g_logits [B, L_local] -> (d P_e, d L_e): d Pn = G Ln, d Ln = G^T Pn (tensor-core engine), then the row-normalisation's
+    backward.  Linear in G, so per-rank label slabs add up like every other gradient of the sharded step."""
+    g = ops.split(g_logits, want_T=True, autoscale=True)
+    dPn = ops.dgrad(g, ops.pack(sctx["Ln"], transposed=True), out_f32=True)             # [B, d]
+    dLn = ops.wgrad(g, ops.split(sctx["Pn"], want_T=True))                               # [L_local, d]
+    return (ops.normalize_rows_bwd(sctx["Pn"], sctx["ip"], dPn, sctx["scale"]),
+            ops.normalize_rows_bwd(sctx["Ln"], sctx["il"], dLn, 1.0))
+
+
+# --------------------------------------------------------------------------------------------------------------------
 # whole step
 # --------------------------------------------------------------------------------------------------------------------
 def trainable_parameters(model) -> List[nn.Parameter]:
     ps = []
-    for part in (model.W_p, model.W_l, model.output_layer):
+    for part in (model.W_p, model.W_l, getattr(model, "output_layer", None)):
+        if part is None:        # FEATURE_FUSION similarity has no output MLP (ProtNote.py:93)
+            continue
         ps += [p for p in part.parameters()]
     return ps
 
@@ -448,8 +471,12 @@ def forward_train(ops, comm, model, P_f, L_f, L_total: Optional[int] = None, upd
     L_total = int(L_total if L_total is not None else L_f.shape[0])
     B = P_f.shape[0]
     wp, wl = _split_sequential(model.W_p), _split_sequential(model.W_l)
-    mods = _split_sequential(model.output_layer)
-    hidden, final = mods[:-1], mods[-1][0]
+    similarity = getattr(model, "feature_fusion", "concatenation") == "similarity"
+    if similarity and loss is not None:
+        raise NotImplementedError("the fused loss lives in the output MLP's last kernel; with FEATURE_FUSION 'similarity' "
+                                  "take train_logits() and compute the loss from the logits")
+    mods = [] if similarity else _split_sequential(model.output_layer)
+    hidden, final = (mods[:-1], mods[-1][0]) if mods else ([], None)
     # SEQUENCE_EMBEDDING_DROPOUT / LABEL_EMBEDDING_DROPOUT (ProtNote.py:83-86): RNG-stream dependent like the label noise,
     # so they stay the reference's own torch op, drawn in the reference's order (W_p before W_l, ProtNote.py:270-271).
     # Every rank holds all proteins: the dropped P_f is the first rank's; label rows are per rank.
@@ -470,13 +497,16 @@ def forward_train(ops, comm, model, P_f, L_f, L_total: Optional[int] = None, upd
                                 {i: v for (t, i), v in plan.items() if t == "p"})
     L_e, saved_l = head_forward(ops, comm, L_f, wl, L_total, sharded, update_running,
                                 {i: v for (t, i), v in plan.items() if t == "l"})
-    logits, pctx = pairs_forward(ops, comm, P_e, L_e, hidden, final, L_total, sharded, update_running, loss, targets,
-                                 getattr(model, "feature_fusion", "concatenation"),
-                                 {i: v for (t, i), v in plan.items() if t == "o"})
+    if similarity:
+        logits, pctx = similarity_forward(ops, P_e, L_e, model.temperature)
+    else:
+        logits, pctx = pairs_forward(ops, comm, P_e, L_e, hidden, final, L_total, sharded, update_running, loss, targets,
+                                     getattr(model, "feature_fusion", "concatenation"),
+                                     {i: v for (t, i), v in plan.items() if t == "o"})
     ctx = {"saved_p": saved_p, "saved_l": saved_l, "pairs": pctx, "B": B, "L_total": L_total, "sharded": sharded,
-           "drop_plan": plan}
+           "drop_plan": plan, "similarity": similarity}
     if update_running:
-        for part in (model.W_p, model.W_l, model.output_layer):
+        for part in (model.W_p, model.W_l) + (() if similarity else (model.output_layer,)):
             for m in part.modules():
                 if isinstance(m, nn.BatchNorm1d) and m.num_batches_tracked is not None:
                     m.num_batches_tracked += 1
@@ -496,7 +526,10 @@ def backward_train(ops, comm, ctx, g_logits, reduce_gradients: bool = False) -> 
     comm = comm or _NoComm()
     sharded = ctx["sharded"]
     grads = _Grads(comm if (reduce_gradients and sharded) else None)
-    dPe, dLe = pairs_backward(ops, comm, ctx["pairs"], g_logits.reshape(-1), sharded, grads)
+    if ctx["similarity"]:
+        dPe, dLe = similarity_backward(ops, ctx["pairs"], g_logits)
+    else:
+        dPe, dLe = pairs_backward(ops, comm, ctx["pairs"], g_logits.reshape(-1), sharded, grads)
     head_backward(ops, comm, dLe, ctx["saved_l"], ctx["L_total"], sharded, grads)      # the larger head first
     head_backward(ops, comm, dPe, ctx["saved_p"], ctx["B"], False, grads)
     grads.wait()

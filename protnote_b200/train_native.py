@@ -314,6 +314,25 @@ class NativeOps:
                                                ptr(out_b), ptr(out_l), stream_ptr()))
         return out_b, out_l
 
+    # ------------------------------------------------------------------ FEATURE_FUSION similarity
+    def normalize_rows(self, x, scale=1.0):
+        """(x * scale / max(|x|, 1e-12) per row, 1 / max(|x|, 1e-12) [rows])"""
+        x = self._f32(x, "embeddings")
+        y = torch.empty_like(x)
+        inv = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            check(self.lib.pn_t_normalize_rows(ptr(x), x.shape[0], x.shape[1], C.c_float(scale), ptr(y), ptr(inv),
+                                               stream_ptr()))
+        return y, inv
+
+    def normalize_rows_bwd(self, y, inv_norm, dy, scale=1.0):
+        y, dy = self._f32(y, "normalised embeddings"), self._f32(dy, "gradient")
+        dx = torch.empty_like(y)
+        with torch.cuda.device(y.device):
+            check(self.lib.pn_t_normalize_rows_bwd(ptr(y), ptr(inv_norm), ptr(dy), y.shape[0], y.shape[1], C.c_float(scale),
+                                                   ptr(dx), stream_ptr()))
+        return dx
+
     # ------------------------------------------------------------------ BatchNorm + ReLU backward
     def outer(self, g_logit, w):
         return Outer(self._f32(g_logit, "logit gradient").reshape(-1), self._f32(w, "output weight").reshape(-1))

@@ -277,6 +277,7 @@ VARIANTS = {"no_batchnorm": dict(output_mlp_batchnorm=False),
             "diff": dict(feature_fusion="concatenation_diff"),
             "diff_no_batchnorm": dict(feature_fusion="concatenation_diff", output_mlp_batchnorm=False),
             "two_layers_no_batchnorm": dict(output_mlp_num_layers=2, output_mlp_batchnorm=False),
+            "similarity": dict(feature_fusion="similarity", temperature=0.07),
             "prod": dict(feature_fusion="concatenation_prod"),
             "prod_no_batchnorm": dict(feature_fusion="concatenation_prod", output_mlp_batchnorm=False),
             "one_layer_prod": dict(feature_fusion="concatenation_prod", output_mlp_num_layers=1),
@@ -393,6 +394,28 @@ def test_pair_product_primitives(B, L, d, H):
     assert qf.lo is None and _rel(_val(qf), qr.val) < 2e-3 and torch.equal(_val(qf), _valT(qf))
     fb, fl = fast.pair_marginals(fast.split(x.cuda(), want_T=False), B, L)
     assert _rel(fb.cpu().double(), ref.pair_marginals(ref.split(x), B, L)[0]) < 2e-3
+
+
+@pytest.mark.parametrize("rows,cols", [(7, 32), (130, 1024), (3, 37)])
+def test_normalize_rows_primitives(rows, cols):
+    """Row normalisation of FEATURE_FUSION similarity and its backward against torch.nn.functional.normalize under autograd
+    (fp64), with the 1 / temperature scale; an all-zero row takes F.normalize's eps path."""
+    nat, ref = _ops("strict")
+    g = torch.Generator().manual_seed(rows + cols)
+    x = torch.randn(rows, cols, generator=g)
+    x[0] = 0.0
+    dy = torch.randn(rows, cols, generator=g)
+    scale = 1.0 / 0.07
+    y, inv = nat.normalize_rows(x.cuda(), scale)
+    dx = nat.normalize_rows_bwd(y, inv, dy.cuda(), scale)
+    xr = x.double().requires_grad_(True)
+    yr = torch.nn.functional.normalize(xr, dim=-1, p=2) * scale
+    (dxr,) = torch.autograd.grad(yr, xr, dy.double())
+    assert _rel(y.cpu().double(), yr.detach()) < 1e-6
+    assert float((dx.cpu().double()[1:] - dxr[1:]).abs().max()) < 1e-5 * float(dxr.abs().max())
+    assert float(y[0].abs().max()) == 0.0
+    yo, io = ref.normalize_rows(x, scale)
+    assert _rel(ref.normalize_rows_bwd(yo, io, dy, scale)[1:], dxr[1:]) < 1e-12
 
 
 @pytest.mark.parametrize("rows,cols,p", [(70, 40, 0.3), (257, 300, 0.1), (130, 1100, 0.5), (64, 64, 0.0)])

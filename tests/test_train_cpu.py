@@ -147,8 +147,9 @@ def _variant_cfg(**kw):
 
 
 def test_training_path_refuses_what_it_does_not_implement():
-    """Unsupported options fail loudly (no silent fallback): a Dropout in front of the first Linear of an MLP, training
-    with FEATURE_FUSION 'similarity'; and the product module itself has no CPU path in training mode."""
+    """Unsupported options fail loudly (no silent fallback): a Dropout in front of the first Linear of an MLP, the fused
+    loss with FEATURE_FUSION 'similarity' (no output MLP to fuse it into); and the product module itself has no CPU path in
+    training mode."""
     from protnote_b200._lib import ProtnoteB200Error
     ecfg, scfg, sd, P_f, L_f, y = _problem()
     model = build_b200_model(ecfg, scfg, sd, device="cpu").double().train()
@@ -157,9 +158,9 @@ def test_training_path_refuses_what_it_does_not_implement():
     with pytest.raises(NotImplementedError):
         pn_train.forward_train(ops, None, model, P_f.double(), L_f.double())
     sim_cfg = _variant_cfg(feature_fusion="similarity")
-    sim = build_b200_model(ecfg, sim_cfg, synth_state_dict(ecfg, sim_cfg, seed=3, calib_T=64), device="cpu").train()
-    with pytest.raises(ProtnoteB200Error, match="similarity"):
-        sim(sequence_embeddings=P_f, label_embeddings=L_f)
+    sim = build_b200_model(ecfg, sim_cfg, synth_state_dict(ecfg, sim_cfg, seed=3, calib_T=64), device="cpu").double().train()
+    with pytest.raises(NotImplementedError, match="similarity"):
+        pn_train.train_loss(sim, P_f.double(), L_f.double(), y.double(), ops=ops)
     # the product module: CPU tensors in training mode -> error, never a torch fallback
     cpu_model = build_b200_model(ecfg, scfg, sd, device="cpu").train()
     with pytest.raises(ProtnoteB200Error):
@@ -172,6 +173,7 @@ VARIANTS = {"no_batchnorm": dict(output_mlp_batchnorm=False),
             "diff": dict(feature_fusion="concatenation_diff"),
             "diff_no_batchnorm": dict(feature_fusion="concatenation_diff", output_mlp_batchnorm=False),
             "two_layers_no_batchnorm": dict(output_mlp_num_layers=2, output_mlp_batchnorm=False),
+            "similarity": dict(feature_fusion="similarity", temperature=0.07),
             "prod": dict(feature_fusion="concatenation_prod"),
             "prod_no_batchnorm": dict(feature_fusion="concatenation_prod", output_mlp_batchnorm=False),
             "one_layer_prod": dict(feature_fusion="concatenation_prod", output_mlp_num_layers=1),
