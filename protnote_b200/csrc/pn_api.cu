@@ -614,7 +614,7 @@ int check_scorer_cfg(const pn_scorer_cfg* c) {
     return fail("bad scorer dims");
   if (c->proj_layers < 1) return fail("proj_layers must be >= 1");
   if (c->fusion < 0 || c->fusion > 3) return fail("unknown fusion %d", c->fusion);
-  if (c->fusion != PN_FUSION_SIMILARITY && c->out_layers < 2) return fail("out_layers must be >= 2 (got %d)", c->out_layers);
+  if (c->fusion != PN_FUSION_SIMILARITY && c->out_layers < 1) return fail("out_layers must be >= 1 (got %d)", c->out_layers);
   if (c->descriptions_per_label < 1) return fail("descriptions_per_label must be >= 1");
   return 0;
 }
@@ -1423,7 +1423,7 @@ int pn_score_pairs_ex(const pn_scorer_cfg* cfg, const void* packed, const float*
   const int H = c.out_hidden;
   const int ld_h = (int)round_up(H, 64);
   // the fused generator reads a / c with 16-byte loads over whole 32-wide k-blocks
-  const bool fuse_ok = g_fuse_features && c.fusion != PN_FUSION_CONCAT_PROD && H % 32 == 0 &&
+  const bool fuse_ok = g_fuse_features && !L.hidden.empty() && c.fusion != PN_FUSION_CONCAT_PROD && H % 32 == 0 &&
                        (reinterpret_cast<uintptr_t>(a) & 15) == 0 && (reinterpret_cast<uintptr_t>(c_in) & 15) == 0;
   const int parts = 4 * tiles_n_for(H);   // one partial dot (two floats: hi, lo of an fp64 sum) per (N tile, column half)
   const size_t per_row = scorer_row_bytes(c);
@@ -1508,7 +1508,18 @@ int pn_score_pairs_ex(const pn_scorer_cfg* cfg, const void* packed, const float*
         PN_TRY(launch_gemm(A, ConvView(), weight_planes(pk, pl), H, e, mode, stream, kStageScorer));
         cur ^= 1;
       }
-      finalize_logits_kernel<<<ew_grid(rows / k), 256, 0, stream>>>(partial, parts, pk.at<float>(L.b_out), (int)b0, (int)l0,
+      int nparts = parts;
+      if (L.hidden.empty()) {
+        // OUTPUT_MLP_NUM_LAYERS 1: the output neuron follows layer 1.  h1 = relu(...) is in buffer 0 as planes; one warp
+        // per pair takes its dot product with w_out (the training step's last-layer kernel with the identity state)
+        if (hidden_out) return fail("hidden_out is the activation in front of the last hidden layer: a one-layer output MLP has none");
+        bn_relu_dot_kernel<<<ew_grid(rows * 32), 256, 0, stream>>>(buf_hi[0], mode == PN_STRICT ? buf_lo[0] : nullptr, rows, H,
+                                                                   ld_h, nullptr, pk.at<float>(L.w_out), nullptr, partial);
+        g_launches++;
+        PN_CUDA(cudaGetLastError());
+        nparts = 1;
+      }
+      finalize_logits_kernel<<<ew_grid(rows / k), 256, 0, stream>>>(partial, nparts, pk.at<float>(L.b_out), (int)b0, (int)l0,
                                                                     (int)nl, rows, k, logits, ld_logits);
       g_launches++;
       PN_CUDA(cudaGetLastError());

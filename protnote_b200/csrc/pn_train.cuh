@@ -818,8 +818,16 @@ __global__ void __launch_bounds__(256) bn_relu_dot_kernel(const __half* __restri
       const int c0 = ch * 8;
       float v[8], sc[8], sf[8], wv[8];
       load8(zh + r * ld + c0, zl ? zl + r * ld + c0 : nullptr, v);
-      load8_f32(state + c0, cols - c0, sc);
-      load8_f32(state + cols + c0, cols - c0, sf);
+      if (state) {                  // null state = identity (scale 1, shift 0)
+        load8_f32(state + c0, cols - c0, sc);
+        load8_f32(state + cols + c0, cols - c0, sf);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          sc[j] = 1.f;
+          sf[j] = 0.f;
+        }
+      }
       load8_f32(w + c0, cols - c0, wv);
 #pragma unroll
       for (int j = 0; j < 8; ++j)
