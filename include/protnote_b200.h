@@ -154,7 +154,7 @@ typedef struct pn_scorer_cfg {
   int proj_hidden;       /* 3072 latent_dim * PROJECTION_HEAD_HIDDEN_DIM_SCALE_FACTOR    */
   int proj_layers;       /* 4    PROJECTION_HEAD_NUM_LAYERS (>= 1)                       */
   int out_hidden;        /* 3072 int(round(OUTPUT_MLP_HIDDEN_DIM_SCALE_FACTOR * latent)) */
-  int out_layers;        /* 3    OUTPUT_MLP_NUM_LAYERS hidden layers (>= 2)              */
+  int out_layers;        /* 3    OUTPUT_MLP_NUM_LAYERS hidden layers (>= 1)              */
   int out_batchnorm;     /* 1    OUTPUT_MLP_BATCHNORM (0: hidden Linear layers have a bias) */
   int fusion;            /* PN_FUSION_*                                                  */
   int descriptions_per_label; /* k: consecutive label rows ensembled per label (>= 1)   */
