@@ -38,8 +38,10 @@ def test_sizes_and_argument_errors_without_a_device(lib):
     assert lib.pn_scorer_num_params(C.byref(sc)) == 49
     assert lib.pn_scorer_packed_bytes(C.byref(sc)) > 3 * 3072 * 3072 * 4
     assert lib.pn_scorer_min_workspace_bytes(C.byref(sc)) > 0
-    sc_bad = _lib.ScorerCfg(1100, 1024, 1024, 3072, 4, 3072, 1, 1, 0, 1, 1e-5)
-    assert lib.pn_scorer_num_params(C.byref(sc_bad)) == -1
+    sc_one = _lib.ScorerCfg(1100, 1024, 1024, 3072, 4, 3072, 1, 1, 0, 1, 1e-5)       # OUTPUT_MLP_NUM_LAYERS 1
+    assert lib.pn_scorer_num_params(C.byref(sc_one)) == 2 * 16 + 5 + 2
+    sc_bad = _lib.ScorerCfg(1100, 1024, 1024, 3072, 4, 3072, 0, 1, 0, 1, 1e-5)
+    assert lib.pn_scorer_num_params(C.byref(sc_bad)) == -1 and b"out_layers" in lib.pn_last_error()
     assert lib.pn_set_option(b"bk", 48) != 0 and lib.pn_set_option(b"no_such_option", 1) != 0
     assert lib.pn_set_option(b"bk", 0) == 0
 
