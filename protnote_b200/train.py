@@ -132,6 +132,21 @@ def _split_sequential(seq: nn.Module) -> List[Tuple[nn.Linear, Optional[nn.Batch
     return out
 
 
+def mlp_layers(model):
+    """(W_p layers, W_l layers, output_layer layers) as _split_sequential lists; output_layer is [] for 'similarity'."""
+    out = getattr(model, "output_layer", None)
+    return _split_sequential(model.W_p), _split_sequential(model.W_l), [] if out is None else _split_sequential(out)
+
+
+def dropout_sites(model, base_seed: int, rank: int = 0):
+    """{(tag, layer index): (seed, p, width)} of a module's active OUTPUT_MLP_DROPOUT sites for one step seeded
+    with `base_seed` (tests restate the masks from this; tag 'p' / 'l' / 'o' = W_p / W_l / output_layer)."""
+    wp, wl, mods = mlp_layers(model)
+    layers = {"p": wp, "l": wl, "o": mods}
+    return {(t, i): (seed, p, layers[t][i][0].weight.shape[0])
+            for (t, i), (seed, p) in dropout_plan(wp, wl, mods, base_seed, rank).items()}
+
+
 _SITE_STRIDE = 0xD1B54A32D192ED03
 _RANK_STRIDE = 0x9E3779B97F4A7C15
 _U64 = (1 << 64) - 1

@@ -469,12 +469,10 @@ def test_training_step_with_output_mlp_dropout(variant):
     torch.nn.functional.binary_cross_entropy_with_logits(logits, y.cuda()).backward()
     torch.manual_seed(91)
     base = int(torch.randint(0, 1 << 62, (1,), dtype=torch.int64))
-    wp, wl = pn_train._split_sequential(model.W_p), pn_train._split_sequential(model.W_l)
-    mods = pn_train._split_sequential(model.output_layer)
-    plan = pn_train.dropout_plan(wp, wl, mods, base)
-    assert len(plan) == 4 + 4 + 2
-    rows, layers = {"p": B, "l": L, "o": B * L}, {"p": wp, "l": wl, "o": mods}
-    masks = {(t, i): dropout_multiplier(sd_, rows[t], layers[t][i][0].weight.shape[0], p) for (t, i), (sd_, p) in plan.items()}
+    sites = pn_train.dropout_sites(model, base)
+    assert len(sites) == 4 + 4 + 2
+    rows = {"p": B, "l": L, "o": B * L}
+    masks = {(t, i): dropout_multiplier(seed, rows[t], width, p) for (t, i), (seed, p, width) in sites.items()}
     o_logits, _, o_grads, o_stats = train_step_oracle(sd, P_f, L_f, y, scfg, masks=masks)
     assert float((logits.detach().cpu().double() - o_logits).abs().max()) < 1e-4
     assert float((train_step_oracle(sd, P_f, L_f, y, scfg)[0] - o_logits).abs().max()) > 1e-2     # dropout was active

@@ -228,14 +228,11 @@ def test_train_oracle_variants_match_reference(variant):
 
 def _dropout_masks(model, P_rows, L_rows, base_seed, rank=0):
     """The multipliers of every active Dropout inside W_p / W_l / output_layer for the step seeded with `base_seed`:
-    the plan of protnote_b200.train (site -> seed) and the statement of the device mask (oracle.train_ops)."""
+    the sites of protnote_b200.train (site -> seed, p, width) and the statement of the device mask (oracle.train_ops)."""
     from oracle.train_ops import dropout_multiplier
-    wp, wl = pn_train._split_sequential(model.W_p), pn_train._split_sequential(model.W_l)
-    mods = pn_train._split_sequential(model.output_layer)
-    plan = pn_train.dropout_plan(wp, wl, mods, base_seed, rank)
     rows = {"p": P_rows, "l": L_rows, "o": P_rows * L_rows}
-    layers = {"p": wp, "l": wl, "o": mods}
-    return {(t, i): dropout_multiplier(seed, rows[t], layers[t][i][0].weight.shape[0], p) for (t, i), (seed, p) in plan.items()}
+    return {(t, i): dropout_multiplier(seed, rows[t], width, p)
+            for (t, i), (seed, p, width) in pn_train.dropout_sites(model, base_seed, rank).items()}
 
 
 @pytest.mark.parametrize("variant", ["default", "no_batchnorm", "two_layers", "prod"])

@@ -93,14 +93,10 @@ def _sharded_masks(ecfg, scfg, sd, B, L, world):
     torch.manual_seed(1000)
     base = int(torch.randint(0, 1 << 62, (1,), dtype=torch.int64))
     model = build_b200_model(ecfg, scfg, sd, device="cpu")
-    wp, wl = pn_train._split_sequential(model.W_p), pn_train._split_sequential(model.W_l)
-    mods = pn_train._split_sequential(model.output_layer)
-    layers = {"p": wp, "l": wl, "o": mods}
     masks = {}
-    plans = [pn_train.dropout_plan(wp, wl, mods, base, r) for r in range(world)]
+    plans = [pn_train.dropout_sites(model, base, r) for r in range(world)]
     bounds = [label_row_bounds(L, 1, r, world) for r in range(world)]
-    for (t, i), (seed0, p) in plans[0].items():
-        width = layers[t][i][0].weight.shape[0]
+    for (t, i), (seed0, p, width) in plans[0].items():
         if t == "p":
             assert all(pl[(t, i)][0] == seed0 for pl in plans)
             masks[(t, i)] = dropout_multiplier(seed0, B, width, p)
