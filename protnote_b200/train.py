@@ -14,6 +14,11 @@ those primitives, and - when the label axis is sharded over ranks - all-reduces 
 the shards (BatchNorm sums in forward, the two BatchNorm-backward sums in backward).  The same sequencing is exercised on
 the CPU by the tests with a torch stand-in for the primitives (oracle/train_ops.py, test infrastructure only).
 
+Configuration coverage (each checked on the CPU against the reference class's autograd and on B200 against the oracle):
+every FEATURE_FUSION ('concatenation' / '_diff' folded into the two layer-1 factors, '_prod' with the product block as a
+real GEMM, 'similarity'), OUTPUT_MLP_BATCHNORM True / False, OUTPUT_MLP_NUM_LAYERS >= 1, SEQUENCE_ / LABEL_EMBEDDING_DROPOUT
+(torch's draw, the reference's RNG order), OUTPUT_MLP_DROPOUT (device-side counter-based masks), the label noise.
+
 Exact identities used (so that the [B*L, 2d] joint tensor never exists in training either):
   layer 1 of the output MLP is linear in [p; t]:  z1[b,l] = a[b] + c[l],  a = P_e W1p^T, c = L_e W1l^T
   its batch statistics over the full B x L grid follow from the factors:
